@@ -1,0 +1,96 @@
+// Library-level state of libfvit_sm100.so: error strings, launch counter, TMA descriptor encoding.
+#include "common.h"
+
+#include <cstring>
+#include <mutex>
+
+#include "../../include/fvit.h"
+
+namespace fvit {
+
+std::atomic<int64_t> g_launches{0};
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    n = p.multiProcessorCount;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error("TMA base pointer %p is not 16-byte aligned", base);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0)
+        return set_error("TMA global stride %llu B (dim %d) is not a multiple of 16",
+                         (unsigned long long)gstr[i - 1], i);
+    }
+  }
+  // FLOAT16 covers fp16 and bf16 alike for a tiled copy (no arithmetic on the elements).
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu box %u,%u)",
+                     (int)r, rank, (unsigned long long)dims[0],
+                     (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+  return 0;
+}
+
+}  // namespace fvit
+
+extern "C" {
+int fvit_abi_version(void) { return FVIT_ABI_VERSION; }
+const char* fvit_last_error(void) { return fvit::err_buf(); }
+int64_t fvit_launch_count(void) { return fvit::g_launches.load(); }
+void fvit_reset_launch_count(void) { fvit::g_launches.store(0); }
+}

@@ -1,0 +1,588 @@
+// fvit_gemm: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0      : TMA producer (one elected lane) — cp.async.bulk.tensor boxes into a ring of
+//                 128B-swizzled shared-memory stages, mbarrier complete_tx signalling
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane) — tcgen05.mma.kind::f16, M=128,
+//                 N = tile_n (runtime, multiple of 16), K=16 per instruction, fp32 accumulators in
+//                 TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the
+//                 main loop of tile i+1
+//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32b x 16 columns), fused scale/shift/activation/
+//                 layer-scale/residual, optional per-column statistics, row-map scatter, vectorised
+//                 global stores
+//
+// The A operand of K-block kb is the 2-D box at row (m0 + tap_shift[tap]) of plane tap_plane[tap]:
+// with 9 taps this is an im2col-free 3x3 convolution over a zero-bordered NHWC activation matrix
+// (out-of-range rows are zero-filled by TMA). See include/fvit.h for the exact contract.
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/fvit.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace fvit {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = 128 B: one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;  // TMEM column stride between the two accumulator stages
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem base, placed after the stage ring
+constexpr int SMEM_ALIGN_SLACK = 1024;
+
+struct GemmParams {
+  int m, n;
+  int num_kb;      // K-blocks (of 64) over all taps
+  int kb_per_tap;  // ceil(kc / 64)
+  int a_mn, b_mn;
+  int a_row_off, b_row_off;
+  int tile_n;
+  int tiles_m, tiles_n, split_k;
+  int atomic_out;  // split-K style accumulation: atomicAdd(alpha * acc) into out_f32
+  int stages;
+  uint32_t idesc;
+  int tap_shift[16];
+  int tap_plane[16];
+  // epilogue
+  float alpha;
+  int act;
+  int bf16;
+  int vec_ok;
+  const float* col_scale;
+  const float* col_shift;
+  const float* col_scale2;
+  const void* aux;
+  long long ld_aux;
+  const float* resid;
+  long long ld_resid;
+  const int* row_map;
+  float* out_f32;
+  long long ld_o32;
+  void* out_f16;
+  long long ld_o16;
+  float* col_sum;
+  float* col_sumsq;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float load16_as_float(const void* base, long long idx, int bf16) {
+  if (bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+}
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving).
+// On return lane L (even lanes are the owners) holds in v[0] the total of column
+// ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int width = 8, mask = 16; width >= 1; width >>= 1, mask >>= 1) {
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < width) {
+        const float send = upper ? v[i] : v[i + width];
+        const float keep = upper ? v[i + width] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int colsum16_owner_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                        const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SW128 atoms
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int b_stage_bytes = p.tile_n * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t* ctrl = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int work_total = p.tiles_m * p.tiles_n * p.split_k;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int split = w % p.split_k;
+        const int t = w / p.split_k;
+        const int tn = t % p.tiles_n;
+        const int tm = t / p.tiles_n;
+        const int m0 = tm * BM;
+        const int n0 = tn * p.tile_n;
+        const int kb0 = (int)((long long)p.num_kb * split / p.split_k);
+        const int kb1 = (int)((long long)p.num_kb * (split + 1) / p.split_k);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (!p.a_mn) {
+            const int tap = kb / p.kb_per_tap;
+            const int kc0 = (kb - tap * p.kb_per_tap) * BK;
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], kc0, m0 + p.tap_shift[tap],
+                        p.tap_plane[tap]);
+          } else {
+            // A stored [K rows][M cols]: two 64-wide MN atoms of BK rows each
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], m0, kb * BK + p.a_row_off, 0);
+            tma_load_3d(sa + BK * 128, &tmap_a, &full_bar[stage], m0 + 64, kb * BK + p.a_row_off,
+                        0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else {
+            for (int j = 0; j < p.tile_n / 64; ++j)
+              tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64,
+                          kb * BK + p.b_row_off);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      // descriptor templates: K-major SW128: SBO = 1024 (8 rows x 128 B), LBO unused;
+      // MN-major SW128: LBO = BK*128 (next 64-wide MN atom), SBO = 1024 (next 8 K rows).
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16;
+      const uint32_t b_lbo = p.b_mn ? BK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int split = w % p.split_k;
+        const int kb0 = (int)((long long)p.num_kb * split / p.split_k);
+        const int kb1 = (int)((long long)p.num_kb * (split + 1) / p.split_k);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
+            umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool splitk = p.atomic_out != 0;
+    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      const int t = w / p.split_k;
+      const int tn = t % p.tiles_n;
+      const int tm = t / p.tiles_n;
+      const int row = tm * BM + quad * 32 + lane;
+      const int n0 = tn * p.tile_n;
+      long long orow = -1;
+      if (row < p.m) orow = p.row_map ? (long long)p.row_map[row] : (long long)row;
+      const bool valid = orow >= 0;
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+
+      for (int c0 = 0; c0 < p.tile_n; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + c0, raw);
+        tmem_ld_wait();
+        const int nbase = n0 + c0;
+        if (nbase >= p.n) continue;  // warp-uniform
+        const bool full16 = nbase + 16 <= p.n;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+
+        if (splitk) {
+          if (valid) {
+            float* o = p.out_f32 + orow * p.ld_o32 + nbase;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nbase + i < p.n) atomicAdd(o + i, v[i]);
+          }
+          __syncwarp();
+          continue;
+        }
+
+        if (p.col_scale) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full16 || nbase + i < p.n) v[i] *= __ldg(p.col_scale + nbase + i);
+        }
+        if (p.col_shift) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full16 || nbase + i < p.n) v[i] += __ldg(p.col_shift + nbase + i);
+        }
+        if (p.col_sum) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = valid ? v[i] : 0.f;
+            s1[i] = x;
+            s2[i] = x * x;
+          }
+          warp_colsum16(s1, lane);
+          warp_colsum16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int c = nbase + colsum16_owner_col(lane);
+            if (c < p.n) {
+              atomicAdd(p.col_sum + c, s1[0]);
+              atomicAdd(p.col_sumsq + c, s2[0]);
+            }
+          }
+        }
+        if (valid) {  // lane-divergent region: no warp-collective ops inside
+        if (p.act == FVIT_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (p.act == FVIT_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+        } else if (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) {
+          const long long abase = (long long)row * p.ld_aux + nbase;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (full16 || nbase + i < p.n) {
+              const float a = load16_as_float(p.aux, abase + i, p.bf16);
+              v[i] *= (p.act == FVIT_ACT_GELU_BWD) ? gelu_erf_grad(a) : (a > 0.f ? 1.f : 0.f);
+            }
+          }
+        }
+        if (p.col_scale2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full16 || nbase + i < p.n) v[i] *= __ldg(p.col_scale2 + nbase + i);
+        }
+        if (p.resid) {
+          const float* r = p.resid + orow * p.ld_resid + nbase;
+          if (full16 && p.vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 rv = *reinterpret_cast<const float4*>(r + 4 * q);
+              v[4 * q + 0] += rv.x;
+              v[4 * q + 1] += rv.y;
+              v[4 * q + 2] += rv.z;
+              v[4 * q + 3] += rv.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nbase + i < p.n) v[i] += r[i];
+          }
+        }
+        if (p.out_f32) {
+          float* o = p.out_f32 + orow * p.ld_o32 + nbase;
+          if (full16 && p.vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(o + 4 * q) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nbase + i < p.n) o[i] = v[i];
+          }
+        }
+        if (p.out_f16) {
+          uint16_t* o = reinterpret_cast<uint16_t*>(p.out_f16) + orow * p.ld_o16 + nbase;
+          if (full16 && p.vec_ok) {
+            uint4 w0, w1;
+            w0.x = pack2_16(v[0], v[1], p.bf16);
+            w0.y = pack2_16(v[2], v[3], p.bf16);
+            w0.z = pack2_16(v[4], v[5], p.bf16);
+            w0.w = pack2_16(v[6], v[7], p.bf16);
+            w1.x = pack2_16(v[8], v[9], p.bf16);
+            w1.y = pack2_16(v[10], v[11], p.bf16);
+            w1.z = pack2_16(v[12], v[13], p.bf16);
+            w1.w = pack2_16(v[14], v[15], p.bf16);
+            *reinterpret_cast<uint4*>(o) = w0;
+            *reinterpret_cast<uint4*>(o + 8) = w1;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (nbase + i < p.n) {
+                const uint32_t pk = pack2_16(v[i], 0.f, p.bf16);
+                o[i] = (uint16_t)(pk & 0xFFFF);
+              }
+            }
+          }
+        }
+        }  // valid
+        __syncwarp();  // reconverge before the next .sync.aligned TMEM load
+      }
+      // hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int pick_tile_n(int m, int n, int split_k, int b_mn, int sms) {
+  const int tiles_m = ceil_div(m, BM);
+  const int step = b_mn ? 64 : 16;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn = step; bn <= 256; bn += step) {
+    const int tiles_n = ceil_div(n, bn);
+    const long long work = (long long)tiles_m * tiles_n * split_k;
+    const long long waves = (work + sms - 1) / sms;
+    // per-tile cost: MMA time ~ bn, plus a fixed part for the A stream / epilogue setup
+    const double cost = (double)waves * (bn + 48.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t d0, d1, d2, s1, s2;
+  uint32_t b0, b1;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 &&
+           b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(k.d0), mix(k.d1), mix(k.d2), mix(k.s1), mix(k.s2), mix(k.b0), mix(k.b1);
+    return h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+// 3-D (or degenerate) 16-bit tensor map with a {b0, b1, 1} box, cached by geometry.
+static int get_tmap(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, int rank) {
+  TmapKey key{base, d0, d1, d2, s1_bytes, s2_bytes, b0, b1};
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  uint64_t dims[3] = {d0, d1, d2};
+  uint64_t strides[2] = {s1_bytes, s2_bytes};
+  uint32_t box[3] = {b0, b1, 1};
+  int rc = encode_tmap_16bit(out, base, rank, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(g_tmap_mu);
+  if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+}  // namespace fvit
+
+extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
+  using namespace fvit;
+  FVIT_CHECK(a != nullptr, "fvit_gemm: null args");
+  FVIT_CHECK(a->m > 0 && a->n > 0 && a->kc > 0, "fvit_gemm: bad dims m=%d n=%d kc=%d", a->m, a->n,
+             a->kc);
+  FVIT_CHECK(a->ntaps >= 1 && a->ntaps <= 16, "fvit_gemm: ntaps=%d out of range", a->ntaps);
+  FVIT_CHECK(a->a && a->b, "fvit_gemm: null operand");
+  FVIT_CHECK(a->lda % 8 == 0 && a->ldb % 8 == 0, "fvit_gemm: lda/ldb must be multiples of 8");
+  FVIT_CHECK(!(a->a_mn_major && a->ntaps != 1), "fvit_gemm: taps need a K-major A operand");
+  FVIT_CHECK(a->out_f32 || a->out_f16, "fvit_gemm: no output");
+  const int split_k = a->split_k > 1 ? a->split_k : 1;
+  if (split_k > 1)
+    FVIT_CHECK(a->out_f32 && !a->out_f16 && !a->col_sum, "fvit_gemm: split_k needs out_f32 only");
+  if (a->act == FVIT_ACT_GELU_BWD || a->act == FVIT_ACT_RELU_BWD)
+    FVIT_CHECK(a->aux != nullptr, "fvit_gemm: backward activation needs aux");
+  FVIT_CHECK((a->col_sum == nullptr) == (a->col_sumsq == nullptr),
+             "fvit_gemm: col_sum and col_sumsq go together");
+
+  const int sms = num_sms();
+  int tile_n = a->tile_n;
+  if (tile_n <= 0) tile_n = pick_tile_n(a->m, a->n, split_k, a->b_mn_major, sms);
+  FVIT_CHECK(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "fvit_gemm: tile_n=%d invalid",
+             tile_n);
+  if (a->b_mn_major) FVIT_CHECK(tile_n % 64 == 0, "fvit_gemm: MN-major B needs tile_n %% 64 == 0");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m = a->m;
+  p.n = a->n;
+  p.kb_per_tap = ceil_div(a->kc, BK);
+  p.num_kb = p.kb_per_tap * a->ntaps;
+  p.a_mn = a->a_mn_major ? 1 : 0;
+  p.b_mn = a->b_mn_major ? 1 : 0;
+  p.a_row_off = a->a_row_off;
+  p.b_row_off = a->b_row_off;
+  p.tile_n = tile_n;
+  p.tiles_m = ceil_div(a->m, BM);
+  p.tiles_n = ceil_div(a->n, tile_n);
+  p.split_k = split_k < p.num_kb ? split_k : p.num_kb;
+  if (p.split_k < 1) p.split_k = 1;
+  p.atomic_out = split_k > 1 ? 1 : 0;
+  const int stage_bytes = A_STAGE_BYTES + tile_n * BK * 2;
+  int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  FVIT_CHECK(stages >= 2, "fvit_gemm: not enough shared memory for 2 stages");
+  p.stages = stages;
+  p.idesc = make_idesc_f16(BM, tile_n, p.a_mn, p.b_mn, a->bf16 ? 1u : 0u);
+  for (int i = 0; i < 16; ++i) {
+    p.tap_shift[i] = i < a->ntaps ? a->tap_shift[i] : 0;
+    p.tap_plane[i] = i < a->ntaps ? a->tap_plane[i] : 0;
+  }
+  p.alpha = a->alpha;
+  p.act = a->act;
+  p.bf16 = a->bf16 ? 1 : 0;
+  p.col_scale = a->col_scale;
+  p.col_shift = a->col_shift;
+  p.col_scale2 = a->col_scale2;
+  p.aux = a->aux;
+  p.ld_aux = a->ld_aux;
+  p.resid = a->resid;
+  p.ld_resid = a->ld_resid;
+  p.row_map = a->row_map;
+  p.out_f32 = a->out_f32;
+  p.ld_o32 = a->ld_out_f32;
+  p.out_f16 = a->out_f16;
+  p.ld_o16 = a->ld_out_f16;
+  p.col_sum = a->col_sum;
+  p.col_sumsq = a->col_sumsq;
+  // vector path: every touched row segment must be 16-byte aligned
+  bool vec = true;
+  if (a->out_f32)
+    vec = vec && (a->ld_out_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0);
+  if (a->out_f16)
+    vec = vec && (a->ld_out_f16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->out_f16) & 15) == 0);
+  if (a->resid)
+    vec = vec && (a->ld_resid % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->resid) & 15) == 0);
+  p.vec_ok = vec ? 1 : 0;
+  CUtensorMap tma, tmb;
+  int rc;
+  if (!p.a_mn) {
+    const int planes = a->a_planes > 0 ? a->a_planes : 1;
+    rc = get_tmap(&tma, a->a, (uint64_t)a->kc, (uint64_t)a->a_rows, (uint64_t)planes,
+                  (uint64_t)a->lda * 2,
+                  (uint64_t)(planes > 1 ? a->a_plane_stride : a->a_rows * a->lda) * 2, BK, BM, 3);
+  } else {
+    rc = get_tmap(&tma, a->a, (uint64_t)a->m, (uint64_t)a->a_rows, 1, (uint64_t)a->lda * 2,
+                  (uint64_t)a->a_rows * a->lda * 2, 64, BK, 3);
+  }
+  if (rc) return rc;
+  if (!p.b_mn) {
+    const uint64_t kdim = a->ntaps == 1 ? (uint64_t)a->kc : (uint64_t)p.num_kb * BK;
+    rc = get_tmap(&tmb, a->b, kdim, (uint64_t)a->n, 1, (uint64_t)a->ldb * 2, 0, BK,
+                  (uint32_t)tile_n, 2);
+  } else {
+    rc = get_tmap(&tmb, a->b, (uint64_t)a->n, (uint64_t)a->b_rows, 1, (uint64_t)a->ldb * 2, 0, 64,
+                  BK, 2);
+  }
+  if (rc) return rc;
+
+  const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FVIT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SMEM_BUDGET));
+    attr_set = true;
+  }
+  const long long work = (long long)p.tiles_m * p.tiles_n * p.split_k;
+  const int grid = (int)(work < sms ? work : sms);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tma, tmb, p);
+  return post_launch("gemm_tcgen05_kernel");
+}

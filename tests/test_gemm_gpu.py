@@ -1,0 +1,217 @@
+"""GPU parity tests of fvit_gemm (tcgen05 GEMM + taps + fused epilogue) against torch fp32 math on the
+same 16-bit operands. Tolerances: fp32 accumulation-order noise only (operands are identical)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from fastervit_b200 import lib
+    lib.load()
+    return lib
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20)).item()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (300, 200, 136), (4096, 768, 256), (1000, 1000, 520),
+                                   (128 * 200 + 5, 512, 192), (53 * 64, 2352, 784)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_nt_plain(m, n, k, dtype):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    a = torch.randn(m, k, device="cuda", generator=g).to(dtype)
+    b = torch.randn(n, k, device="cuda", generator=g).to(dtype)
+    out = torch.full((m, n), float("nan"), device="cuda")
+    lib.gemm(a, b, out_f32=out)
+    ref = a.float() @ b.float().t()
+    assert _rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("tile_n", [16, 48, 64, 112, 208, 256])
+def test_gemm_tile_n(tile_n):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(tile_n)
+    m, n, k = 777, 400, 264
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = torch.randn(n, k, device="cuda", generator=g).half()
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(a, b, out_f32=out, tile_n=tile_n)
+    assert _rel(out, a.float() @ b.float().t()) < 2e-5
+
+
+def test_gemm_strided_operands():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    m, n, k = 500, 196, 196
+    abuf = torch.randn(m, 200, device="cuda", generator=g).half()   # lda = 200 (fv4 C=196 padded)
+    bbuf = torch.randn(n, 208, device="cuda", generator=g).half()
+    a, b = abuf[:, :k], bbuf[:, :k]
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(a, b, out_f32=out)
+    assert _rel(out, a.float() @ b.float().t()) < 2e-5
+
+
+def test_gemm_epilogue_full():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    m, n, k = 1000, 328, 256
+    a = (torch.randn(m, k, device="cuda", generator=g) * 0.2).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.2).half()
+    cs = torch.rand(n, device="cuda", generator=g) + 0.5
+    sh = torch.randn(n, device="cuda", generator=g)
+    cs2 = torch.rand(n, device="cuda", generator=g) + 0.5
+    perm = torch.randperm(m, device="cuda", generator=g).int()
+    perm[::17] = -1
+    resid = torch.randn(m, n, device="cuda", generator=g)
+    o32 = torch.full((m, n), 7.0, device="cuda")
+    o16 = torch.full((m, n), 7.0, device="cuda").half()
+    lib.gemm(a, b, alpha=0.5, col_scale=cs, col_shift=sh, act=lib.ACT_GELU, col_scale2=cs2,
+             resid=resid, row_map=perm, out_f32=o32, out_f16=o16)
+    acc = (a.float() @ b.float().t()) * 0.5 * cs + sh
+    val = torch.nn.functional.gelu(acc) * cs2
+    ref = torch.full((m, n), 7.0, device="cuda")
+    keep = perm >= 0
+    idx = perm[keep].long()
+    ref[idx] = val[keep] + resid[idx]
+    assert _rel(o32, ref) < 2e-5
+    assert _rel(o16, ref) < 1e-3
+
+
+def test_gemm_inplace_residual():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    m, n, k = 640, 256, 128
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = torch.randn(n, k, device="cuda", generator=g).half()
+    x = torch.randn(m, n, device="cuda", generator=g)
+    ref = x + a.float() @ b.float().t()
+    lib.gemm(a, b, resid=x, out_f32=x)
+    assert _rel(x, ref) < 2e-5
+
+
+def test_gemm_colstats():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    m, n, k = 3000, 200, 128
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.1).half()
+    sh = torch.randn(n, device="cuda", generator=g)
+    rm = torch.arange(m, device="cuda").int()
+    rm[5::9] = -1
+    s1 = torch.zeros(n, device="cuda")
+    s2 = torch.zeros(n, device="cuda")
+    o16 = torch.zeros(m, n, device="cuda").half()
+    lib.gemm(a, b, col_shift=sh, row_map=rm, out_f16=o16, col_sum=s1, col_sumsq=s2)
+    v = a.float() @ b.float().t() + sh
+    v = v[rm >= 0]
+    assert _rel(s1, v.sum(0)) < 1e-4
+    assert _rel(s2, (v * v).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (520, 392, 1000), (784, 200, 3000)])
+def test_gemm_mn_major(a_mn, b_mn, m, n, k):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    A = torch.randn(m, k, device="cuda", generator=g).half()
+    B = torch.randn(n, k, device="cuda", generator=g).half()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_f32=out)
+    assert _rel(out, A.float() @ B.float().t()) < 2e-5
+
+
+def test_gemm_split_k_and_row_offsets():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    m, n, k = 256, 192, 5000
+    A = torch.randn(k, m, device="cuda", generator=g).half()  # MN-major [K, M]
+    B = torch.randn(k, n, device="cuda", generator=g).half()
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(A, B, a_mn=True, b_mn=True, split_k=16, alpha=0.25, out_f32=out)
+    assert _rel(out, 0.25 * (A.float().t() @ B.float())) < 1e-4
+    # row offset on B: out[m, n] = sum_r A[r, m] * B[r + off, n], OOB rows are zero
+    for off in (-3, 70):
+        out.zero_()
+        lib.gemm(A, B, a_mn=True, b_mn=True, split_k=8, b_row_off=off, out_f32=out)
+        Bs = torch.zeros_like(B)
+        if off >= 0:
+            Bs[: k - off] = B[off:]
+        else:
+            Bs[-off:] = B[: k + off]
+        assert _rel(out, A.float().t() @ Bs.float()) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 14), (196, 208, 9), (128, 256, 28)])
+def test_gemm_conv3x3_taps(cin, cout, hw):
+    """3x3/s1/p1 conv as 9 shifted-row taps over a zero-bordered NHWC matrix vs F.conv2d."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(cin + hw)
+    bsz, H, W = 3, hw, hw + 2
+    Hp, Wp = H + 2, W + 2
+    ld = (cin + 7) // 8 * 8
+    x = torch.randn(bsz, cin, H, W, device="cuda", generator=g).half()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05).half()
+    xp = torch.zeros(bsz, Hp, Wp, ld, device="cuda", dtype=torch.half)
+    xp[:, 1:-1, 1:-1, :cin] = x.permute(0, 2, 3, 1)
+    a = xp.view(-1, ld)[:, :cin]
+    kc_pad = (cin + 63) // 64 * 64
+    wp = torch.zeros(cout, 9, kc_pad, device="cuda", dtype=torch.half)
+    wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    taps = [((dy - 1) * Wp + (dx - 1), 0) for dy in range(3) for dx in range(3)]
+    out = torch.zeros(bsz * Hp * Wp, cout, device="cuda")
+    lib.gemm(a, wp.view(cout, 9 * kc_pad), kc=cin, taps=taps, out_f32=out)
+    got = out.view(bsz, Hp, Wp, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), padding=1)
+    assert _rel(got, ref) < 2e-5
+
+
+def test_gemm_planes_stride2_conv():
+    """3x3/s2/p1 conv through 4 parity planes (space-to-depth split) and per-tap plane select."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bsz, cin, cout, H, W = 2, 64, 128, 28, 28
+    Ho, Wo = H // 2, W // 2
+    x = torch.randn(bsz, cin, H, W, device="cuda", generator=g).half()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05).half()
+    # plane (ph, pw)[b, a+1, c+1] = x[b, 2a+ph, 2c+pw]; row/col 0 are the zero border
+    planes = torch.zeros(4, bsz, Ho + 1, Wo + 1, cin, device="cuda", dtype=torch.half)
+    xn = x.permute(0, 2, 3, 1)
+    for ph in range(2):
+        for pw in range(2):
+            planes[ph * 2 + pw, :, 1:, 1:] = xn[:, ph::2, pw::2]
+    a = planes.view(4, -1, cin)
+    wp = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    taps = []
+    for r in range(3):
+        ph, da = (1, -1) if r == 0 else ((0, 0) if r == 1 else (1, 0))
+        for s in range(3):
+            pw, db = (1, -1) if s == 0 else ((0, 0) if s == 1 else (1, 0))
+            taps.append((da * (Wo + 1) + db, ph * 2 + pw))
+    rows = bsz * (Ho + 1) * (Wo + 1)
+    out = torch.zeros(rows, cout, device="cuda")
+    lib.gemm(a, wp, m=rows, kc=cin, taps=taps, a_planes=4, out_f32=out)
+    got = out.view(bsz, Ho + 1, Wo + 1, cout)[:, 1:, 1:].permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), stride=2, padding=1)
+    assert _rel(got, ref) < 2e-5
+
+
+def test_gemm_gelu_bwd_epilogue():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(31)
+    m, n, k = 512, 256, 128
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.1).half()
+    pre = torch.randn(m, n, device="cuda", generator=g).half()
+    o16 = torch.zeros(m, n, device="cuda").half()
+    lib.gemm(a, b, act=lib.ACT_GELU_BWD, aux=pre, out_f16=o16)
+    p = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p).sum().backward()
+    ref = (a.float() @ b.float().t()) * p.grad
+    assert _rel(o16, ref) < 1e-3
