@@ -1,0 +1,40 @@
+"""Model configurations used by the oracle-side tests and golden generator (test infrastructure).
+
+`REF_KWARGS[name]` are the kwargs passed to the reference's create_model; `cfg_of(name)` is the oracle
+cfg dict. The full-size entries restate the entrypoint defaults (fv.py:977-1166, fvar.py:1007-1019);
+the `tiny_*` entries are reduced-width models that exercise every code path in seconds on a CPU.
+"""
+from __future__ import annotations
+
+CASES = {
+    # name: (reference entrypoint, override kwargs, oracle cfg)
+    "fv0": ("faster_vit_0_224", {}, dict(
+        dim=64, in_dim=64, depths=[2, 3, 6, 5], num_heads=[2, 4, 8, 16], window_size=[7, 7, 7, 7],
+        ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, True, False], do_propagation=False)),
+    "fv4": ("faster_vit_4_224", {}, dict(
+        dim=196, in_dim=64, depths=[3, 3, 12, 5], num_heads=[4, 8, 16, 32], window_size=[7, 7, 7, 7],
+        ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, True, False], do_propagation=True)),
+    "ar0": ("faster_vit_0_any_res", dict(resolution=[576, 960], window_size=[7, 7, 12, 6], ct_size=2, dim=64), dict(
+        dim=64, in_dim=64, depths=[2, 3, 6, 5], num_heads=[2, 4, 8, 16], window_size=[7, 7, 12, 6],
+        ct_size=2, mlp_ratio=4, resolution=[576, 960], hat=[False, False, True, False],
+        do_propagation=False, any_res=True)),
+    # reduced models: fv0-like (no layer scale / propagation) and fv4-like (layer scale + propagation,
+    # head_dim 12 -> exercises non-power-of-two head dims like fv4's 49)
+    "tiny_a": ("faster_vit_0_224", dict(dim=32, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=32, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 7, 7],
+        ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, True, False], do_propagation=False)),
+    "tiny_b": ("faster_vit_4_224", dict(dim=24, in_dim=16, depths=[1, 2, 2, 2], num_heads=[1, 2, 8, 16]), dict(
+        dim=24, in_dim=16, depths=[1, 2, 2, 2], num_heads=[1, 2, 8, 16], window_size=[7, 7, 7, 7],
+        ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, True, False], do_propagation=True)),
+    # any-res reduced: non-square carrier grid (sr = [2, 3]) and padding to the window (30x42 -> 30x42,
+    # level 3: 15x21 -> 18x24 with window 6)
+    "tiny_ar": ("faster_vit_0_any_res", dict(resolution=[240, 336], window_size=[7, 7, 5, 6], ct_size=2, dim=16,
+                                             in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 5, 6],
+        ct_size=2, mlp_ratio=4, resolution=[240, 336], hat=[False, False, True, False],
+        do_propagation=False, any_res=True)),
+}
+
+
+def cfg_of(name: str) -> dict:
+    return dict(CASES[name][2])
