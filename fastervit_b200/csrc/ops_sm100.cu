@@ -1,0 +1,607 @@
+// HBM-bound kernels of the FasterViT forward path (everything that is not a GEMM): weight packing,
+// BN/layer-scale folding, the 3->C stem convolution, LayerNorm (+ positional-embedding add, gather),
+// carrier-token initialiser, positional MLPs / attention-bias table, carrier->window propagation,
+// head pooling. All are coalesced along the channel dimension (NHWC / token-major rows) with
+// vectorised 16-byte accesses where the shape allows. Contracts are in include/fvit.h.
+#include <cuda_fp16.h>
+
+#include "../../include/fvit.h"
+#include "common.h"
+
+namespace fvit {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------ weight packing
+// dst[r][c] (fp16, row stride ldd, zero padded to `cols_pad`) = src[r][c] (fp32, row stride lds)
+__global__ void cast_pad_kernel(const float* __restrict__ src, long long lds, __half* __restrict__ dst,
+                                long long ldd, int rows, int cols, int cols_pad) {
+  const long long total = (long long)rows * cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
+    dst[r * ldd + c] = __float2half_rn(c < cols ? src[r * lds + c] : 0.f);
+  }
+}
+
+// conv weight [Cout][Cin][3][3] fp32 -> [Cout][9][kc_pad] fp16 (tap-major, channel innermost)
+// transpose_io != 0 builds the data-gradient operand [Cin][9 (flipped)][co_pad] instead.
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __half* __restrict__ dst, int cout,
+                                    int cin, int kc_pad, int transpose_io) {
+  const int rows = transpose_io ? cin : cout;
+  const int inner = transpose_io ? cout : cin;
+  const long long total = (long long)rows * 9 * kc_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kc_pad);
+    const int tap = (int)((i / kc_pad) % 9);
+    const int r = (int)(i / ((long long)kc_pad * 9));
+    float v = 0.f;
+    if (c < inner) {
+      if (!transpose_io)
+        v = w[((long long)r * cin + c) * 9 + tap];
+      else
+        v = w[((long long)c * cin + r) * 9 + (8 - tap)];
+    }
+    dst[i] = __float2half_rn(v);
+  }
+}
+
+// Per-channel epilogue vectors:  s = bn ? w*rsqrt(var+eps) : 1 ; t = bn ? b - mean*s : 0 ;
+// t += bias*s ; then both *= layer_scale (if given).  y = acc*s + t reproduces
+// layer_scale * BN(acc + bias) (fv.py:504-510) or layer_scale * (acc + bias) (fv.py:690-691).
+__global__ void affine_fold_kernel(float* __restrict__ scale, float* __restrict__ shift, int n,
+                                   const float* bn_w, const float* bn_b, const float* bn_mean,
+                                   const float* bn_var, float eps, const float* bias,
+                                   const float* ls) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 1.f, t = 0.f;
+  if (bn_w) {
+    s = bn_w[i] * rsqrtf(bn_var[i] + eps);
+    t = bn_b[i] - bn_mean[i] * s;
+  }
+  if (bias) t += bias[i] * s;
+  if (ls) {
+    s *= ls[i];
+    t *= ls[i];
+  }
+  scale[i] = s;
+  shift[i] = t;
+}
+
+// ------------------------------------------------------------------------------ stem conv 3x3 s2
+// x fp32 [B,3,H,W] (arbitrary strides) -> y = relu(conv(x) * scale + shift) as fp16 rows of `cout`
+// channels written at out_row_map[b*Ho*Wo + oh*Wo + ow] (the parity-plane layout conv2 consumes).
+// One thread per (pixel, 8 output channels); weights [cout][27] live in shared memory.
+template <int CIN>
+__global__ void stem_conv_kernel(const float* __restrict__ x, long long sb, long long sc, long long sh,
+                                 long long sw, int B, int H, int W, const float* __restrict__ wgt,
+                                 int cout, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, int relu,
+                                 const int* __restrict__ out_row_map, __half* __restrict__ out,
+                                 long long ldo, float* __restrict__ col_sum,
+                                 float* __restrict__ col_sumsq) {
+  extern __shared__ float sw_[];  // [cout][CIN*9]
+  const int K = CIN * 9;
+  for (int i = threadIdx.x; i < cout * K; i += blockDim.x) sw_[i] = wgt[i];
+  __syncthreads();
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int groups = cout / 8;
+  const long long total = (long long)B * Ho * Wo * groups;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool active = i < total;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int g = 0;
+  long long pix = 0;
+  if (active) {
+    g = (int)(i % groups);
+    pix = i / groups;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((long long)Wo * Ho));
+    float in[CIN * 9];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ih = 2 * oh + r - 1, iw = 2 * ow + s - 1;
+          in[c * 9 + r * 3 + s] =
+              (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[b * sb + c * sc + ih * sh + iw * sw] : 0.f;
+        }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wr = sw_ + (g * 8 + j) * K;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < CIN * 9; ++k) a = fmaf(in[k], wr[k], a);
+      acc[j] = a;
+    }
+  }
+  if (col_sum) {
+    // train-mode BatchNorm statistics of the raw conv output: block-level reduction, then atomics
+    __shared__ float red[2][64];  // cout <= 64 per pass handled by groups*8 columns
+    for (int j = threadIdx.x; j < 2 * 64; j += blockDim.x) (&red[0][0])[j] = 0.f;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[0][(g * 8 + j) & 63], acc[j]);
+        atomicAdd(&red[1][(g * 8 + j) & 63], acc[j] * acc[j]);
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cout && j < 64; j += blockDim.x) {
+      atomicAdd(col_sum + j, red[0][j]);
+      atomicAdd(col_sumsq + j, red[1][j]);
+    }
+  }
+  if (active && out) {
+    const int orow = out_row_map ? out_row_map[pix] : (int)pix;
+    if (orow >= 0) {
+      __half2 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v0 = acc[2 * j], v1 = acc[2 * j + 1];
+        if (scale) {
+          v0 = v0 * scale[g * 8 + 2 * j] + shift[g * 8 + 2 * j];
+          v1 = v1 * scale[g * 8 + 2 * j + 1] + shift[g * 8 + 2 * j + 1];
+        }
+        if (relu) {
+          v0 = fmaxf(v0, 0.f);
+          v1 = fmaxf(v1, 0.f);
+        }
+        h[j] = __floats2half2_rn(v0, v1);
+      }
+      *reinterpret_cast<uint4*>(out + (long long)orow * ldo + g * 8) = *reinterpret_cast<uint4*>(h);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm forward
+// One warp per row. v = x[in_map ? in_map[r] : r] (+ add[(r % group) - skip] if (r % group) >= skip);
+// optionally written back as fp32 to wb[r]; y = (v - mean) * rstd * gamma + beta written as fp16 to
+// out[out_map ? out_map[r] : r]. Two-pass statistics in registers (biased variance, like
+// F.layer_norm). Saves mean / rstd when requested (backward).
+constexpr int LN_MAX_VEC = 13;  // C <= 32 * 4 * 13 = 1664
+__global__ void ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ in_map,
+                              int rows, int C, const float* __restrict__ add, int group, int skip,
+                              float* __restrict__ wb, long long ldwb, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, __half* __restrict__ out,
+                              long long ldo, const int* __restrict__ out_map,
+                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 2;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows;
+       r += gridDim.x * warps_per_block) {
+    const long long src = in_map ? in_map[r] : r;
+    const float4* xr = reinterpret_cast<const float4*>(x + src * ldx);
+    const float4* ar = nullptr;
+    if (add) {
+      const int t = r % group;
+      if (t >= skip) ar = reinterpret_cast<const float4*>(add + (long long)(t - skip) * C);
+    }
+    float4 v[LN_MAX_VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        float4 t4 = xr[i];
+        if (ar) {
+          const float4 a4 = ar[i];
+          t4.x += a4.x, t4.y += a4.y, t4.z += a4.z, t4.w += a4.w;
+        }
+        v[j] = t4;
+        s += t4.x + t4.y + t4.z + t4.w;
+      }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    if (wb) {
+      float4* wr = reinterpret_cast<float4*>(wb + (long long)r * ldwb);
+#pragma unroll
+      for (int j = 0; j < LN_MAX_VEC; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) wr[i] = v[j];
+      }
+    }
+    if (mean_out && lane == 0) {
+      mean_out[r] = mean;
+      rstd_out[r] = rstd;
+    }
+    const long long orow = out_map ? out_map[r] : r;
+    if (orow >= 0) {
+      __half* o = out + orow * ldo;
+      const float4* g4 = reinterpret_cast<const float4*>(gamma);
+      const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+      for (int j = 0; j < LN_MAX_VEC; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) {
+          const float4 g = g4[i], b = b4[i];
+          const __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g.x + b.x,
+                                               (v[j].y - mean) * rstd * g.y + b.y);
+          const __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g.z + b.z,
+                                               (v[j].w - mean) * rstd * g.w + b.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(o + 4 * i) = pk;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ attention core (SIMT)
+// One CTA per (group of S tokens, head): P = softmax(q k^T * scale + bias[h]) ; out = P v.
+// qkv fp16 [rows, 3C] (q | k | v, head-major inside each), out fp16 [rows, C]. fp32 math throughout.
+// Generic in S and head_dim; used for every attention shape until the tcgen05 path takes over the
+// hot shapes.
+__global__ void attn_core_simt_kernel(const __half* __restrict__ qkv, long long ldq, int S, int hd,
+                                      int heads, int C, const float* __restrict__ bias, float scale,
+                                      __half* __restrict__ out, long long ldo,
+                                      float* __restrict__ probs_out) {
+  extern __shared__ float sm[];
+  const int hdp = hd + 1;
+  float* sq = sm;                 // [S][hd+1]
+  float* sk = sq + S * hdp;       // [S][hd+1]
+  float* sv = sk + S * hdp;       // [S][hd+1]
+  float* sp = sv + S * hdp;       // [S][S+1]
+  const int g = blockIdx.x / heads, h = blockIdx.x % heads;
+  const long long row0 = (long long)g * S;
+  for (int i = threadIdx.x; i < S * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const __half* base = qkv + (row0 + t) * ldq + h * hd + d;
+    sq[t * hdp + d] = __half2float(base[0]) * scale;
+    sk[t * hdp + d] = __half2float(base[C]);
+    sv[t * hdp + d] = __half2float(base[2 * C]);
+  }
+  __syncthreads();
+  const float* bh = bias ? bias + (long long)h * S * S : nullptr;
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+    const int r = i / S, c = i % S;
+    float a = 0.f;
+    for (int d = 0; d < hd; ++d) a = fmaf(sq[r * hdp + d], sk[c * hdp + d], a);
+    sp[r * (S + 1) + c] = a + (bh ? bh[i] : 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < S; r += nwarps) {
+    float* pr = sp + r * (S + 1);
+    float m = -INFINITY;
+    for (int c = lane; c < S; c += 32) m = fmaxf(m, pr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < S; c += 32) {
+      const float e = __expf(pr[c] - m);
+      pr[c] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int c = lane; c < S; c += 32) pr[c] *= inv;
+  }
+  __syncthreads();
+  if (probs_out) {
+    float* po = probs_out + ((long long)g * heads + h) * S * S;
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) po[i] = sp[(i / S) * (S + 1) + (i % S)];
+  }
+  for (int i = threadIdx.x; i < S * hd; i += blockDim.x) {
+    const int r = i / hd, d = i % hd;
+    float a = 0.f;
+    for (int c = 0; c < S; ++c) a = fmaf(sp[r * (S + 1) + c], sv[c * hdp + d], a);
+    out[(row0 + r) * ldo + h * hd + d] = __float2half_rn(a);
+  }
+}
+
+// ------------------------------------------------------------------------------ positional MLPs
+// out[p][d] = sum_j relu(w0[j][0]*c[p][0] + w0[j][1]*c[p][1] + b0[j]) * w1[d][j]   (hidden = 512)
+// (cpb_mlp of PosEmbMLPSwinv1D / PosEmbMLPSwinv2D, fv.py:223-225, 322-324). One CTA per point p;
+// hidden activations in shared memory; one warp per output channel, lanes stride the hidden dim.
+__global__ void cpb_mlp_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w0,
+                               const float* __restrict__ b0, const float* __restrict__ w1, int D,
+                               float* __restrict__ out, float* __restrict__ hidden_out) {
+  __shared__ float hid[512];
+  const int p = blockIdx.x;
+  const float c0 = coords[2 * p], c1 = coords[2 * p + 1];
+  for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+    const float hv = fmaxf(fmaf(w0[2 * j], c0, fmaf(w0[2 * j + 1], c1, b0[j])), 0.f);
+    hid[j] = hv;
+    if (hidden_out) hidden_out[(long long)p * 512 + j] = hv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int d = warp; d < D; d += nwarps) {
+    const float* wr = w1 + (long long)d * 512;
+    float a = 0.f;
+#pragma unroll 4
+    for (int j = lane; j < 512; j += 32) a = fmaf(hid[j], wr[j], a);
+    a = warp_sum(a);
+    if (lane == 0) out[(long long)p * D + d] = a;
+  }
+}
+
+// bias[h][r][c] = (r >= ng && c >= ng) ? 16*sigmoid(table[index[(r-ng)*L + (c-ng)]][h]) : 0
+// with L = ws*ws local tokens and ng = S - L carrier tokens on the top/left (fv.py:276-299).
+__global__ void attn_bias_kernel(const float* __restrict__ table, const long long* __restrict__ index,
+                                 int heads, int S, int L, float* __restrict__ bias) {
+  const int ng = S - L;
+  const long long total = (long long)heads * S * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % S), r = (int)((i / S) % S), h = (int)(i / ((long long)S * S));
+    float v = 0.f;
+    if (r >= ng && c >= ng) {
+      const long long idx = index[(long long)(r - ng) * L + (c - ng)];
+      v = 16.f / (1.f + __expf(-table[idx * heads + h]));
+    }
+    bias[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------ carrier tokens
+// TokenInitializer (fv.py:733-738): ct = AvgPool_{kh x kw, stride sh x sw}(dwconv3x3(x) + b), written
+// to the carrier rows of the window-major token buffer. x is read through `pix_map` (pixel (b,h,w) of
+// the (padded) Hp x Wp map -> row of xs, or -1 for padding pixels which read as zero).
+__global__ void token_init_kernel(const float* __restrict__ xs, long long ldx,
+                                  const int* __restrict__ pix_map, int B, int Hp, int Wp, int C,
+                                  const float* __restrict__ w, const float* __restrict__ bias, int kh,
+                                  int kw, int sh, int sw, int oh, int ow,
+                                  const int* __restrict__ ct_row_map, float* __restrict__ out,
+                                  long long ldo) {
+  const long long total = (long long)B * oh * ow * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pos = i / C;
+    const int x0 = (int)(pos % ow), y0 = (int)((pos / ow) % oh), b = (int)(pos / ((long long)ow * oh));
+    float wl[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wl[t] = w[c * 9 + t];
+    float acc = 0.f;
+    for (int py = 0; py < kh; ++py)
+      for (int px = 0; px < kw; ++px) {
+        const int cy = y0 * sh + py, cx = x0 * sw + px;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int iy = cy + r - 1, ix = cx + s - 1;
+            if (iy >= 0 && iy < Hp && ix >= 0 && ix < Wp) {
+              const int row = pix_map[((long long)b * Hp + iy) * Wp + ix];
+              if (row >= 0) acc = fmaf(wl[r * 3 + s], xs[(long long)row * ldx + c], acc);
+            }
+          }
+      }
+    const float v = acc / (float)(kh * kw) + bias[c];
+    out[(long long)ct_row_map[pos] * ldo + c] = v;
+  }
+}
+
+// Propagation (fv.py:697-700): x[row] += gamma[c] * x[src_map[row]][c] for window-token rows
+// (src_map < 0: untouched). gamma == nullptr means 1.
+__global__ void propagate_kernel(float* __restrict__ xs, long long ldx, const int* __restrict__ src_map,
+                                 int rows, int C, const float* __restrict__ gamma) {
+  const int c4 = C >> 2;
+  const long long total = (long long)rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % c4);
+    const long long r = i / c4;
+    const int src = src_map[r];
+    if (src < 0) continue;
+    float4 v = reinterpret_cast<float4*>(xs + r * ldx)[j];
+    const float4 s = reinterpret_cast<const float4*>(xs + (long long)src * ldx)[j];
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gamma) g = reinterpret_cast<const float4*>(gamma)[j];
+    v.x = fmaf(g.x, s.x, v.x), v.y = fmaf(g.y, s.y, v.y), v.z = fmaf(g.z, s.z, v.z),
+    v.w = fmaf(g.w, s.w, v.w);
+    reinterpret_cast<float4*>(xs + r * ldx)[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------ head
+// pooled[b][c] = (mean_t x[row_map(b, t)][c]) * scale[c] + shift[c]  -> fp16  (BatchNorm2d folded
+// into the average pool, fv.py:953-958). One thread per (b, 4 channels).
+__global__ void pool_affine_kernel(const float* __restrict__ xs, long long ldx,
+                                   const int* __restrict__ row_map, int B, int T, int C,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   __half* __restrict__ out, long long ldo) {
+  const int c4 = C >> 2;
+  const long long total = (long long)B * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % c4);
+    const int b = (int)(i / c4);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const long long row = row_map ? row_map[(long long)b * T + t] : (long long)b * T + t;
+      const float4 v = reinterpret_cast<const float4*>(xs + row * ldx)[j];
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    const float inv = 1.f / T;
+    const float4 s = reinterpret_cast<const float4*>(scale)[j];
+    const float4 h = reinterpret_cast<const float4*>(shift)[j];
+    const __half2 h0 = __floats2half2_rn(a.x * inv * s.x + h.x, a.y * inv * s.y + h.y);
+    const __half2 h1 = __floats2half2_rn(a.z * inv * s.z + h.z, a.w * inv * s.w + h.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + (long long)b * ldo + 4 * j) = pk;
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace fvit
+
+using namespace fvit;
+
+extern "C" {
+
+int fvit_cast_pad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows,
+                      int32_t cols, int32_t cols_pad, void* stream) {
+  FVIT_CHECK(src && dst && rows > 0 && cols > 0 && cols_pad >= cols && ldd >= cols_pad,
+             "fvit_cast_pad_f16: bad arguments");
+  const long long total = (long long)rows * cols_pad;
+  cast_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, lds, (__half*)dst, ldd, rows, cols, cols_pad);
+  return post_launch("cast_pad_kernel");
+}
+
+int fvit_pack_conv3x3_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,
+                          int32_t transpose_io, void* stream) {
+  FVIT_CHECK(w && dst && cout > 0 && cin > 0, "fvit_pack_conv3x3_f16: bad arguments");
+  FVIT_CHECK(kc_pad >= (transpose_io ? cout : cin), "fvit_pack_conv3x3_f16: kc_pad too small");
+  const long long total = (long long)(transpose_io ? cin : cout) * 9 * kc_pad;
+  pack_conv3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, (__half*)dst, cout, cin, kc_pad, transpose_io);
+  return post_launch("pack_conv3x3_kernel");
+}
+
+int fvit_affine_fold(float* scale, float* shift, int32_t n, const float* bn_w, const float* bn_b,
+                     const float* bn_mean, const float* bn_var, float eps, const float* bias,
+                     const float* layer_scale, void* stream) {
+  FVIT_CHECK(scale && shift && n > 0, "fvit_affine_fold: bad arguments");
+  FVIT_CHECK(!bn_w || (bn_b && bn_mean && bn_var), "fvit_affine_fold: incomplete BN arguments");
+  affine_fold_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      scale, shift, n, bn_w, bn_b, bn_mean, bn_var, eps, bias, layer_scale);
+  return post_launch("affine_fold_kernel");
+}
+
+int fvit_stem_conv_fwd(const float* x, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B,
+                       int32_t cin, int32_t H, int32_t W, const float* wgt, int32_t cout,
+                       const float* scale, const float* shift, int32_t relu, const int32_t* out_row_map,
+                       void* out, int64_t ldo, float* col_sum, float* col_sumsq, void* stream) {
+  FVIT_CHECK(x && wgt && B > 0 && H > 0 && W > 0, "fvit_stem_conv_fwd: bad arguments");
+  FVIT_CHECK(cin == 3, "fvit_stem_conv_fwd: only in_chans == 3 is supported (got %d)", cin);
+  FVIT_CHECK(cout % 8 == 0 && cout <= 512, "fvit_stem_conv_fwd: cout=%d must be a multiple of 8", cout);
+  FVIT_CHECK(!col_sum || cout <= 64, "fvit_stem_conv_fwd: statistics need cout <= 64");
+  FVIT_CHECK(!out || ldo % 8 == 0, "fvit_stem_conv_fwd: ldo must be a multiple of 8");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)B * Ho * Wo * (cout / 8);
+  const int block = 128;
+  const long long grid = (total + block - 1) / block;
+  const size_t smem = (size_t)cout * 27 * sizeof(float);
+  if (smem > 48 * 1024)
+    FVIT_CUDA(cudaFuncSetAttribute(stem_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  stem_conv_kernel<3><<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
+      x, sb, sc, sh, sw, B, H, W, wgt, cout, scale, shift, relu, out_row_map, (__half*)out, ldo,
+      col_sum, col_sumsq);
+  return post_launch("stem_conv_kernel");
+}
+
+int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows, int32_t C,
+                const float* add, int32_t group, int32_t skip, float* wb, int64_t ldwb,
+                const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
+                const int32_t* out_map, float* mean_out, float* rstd_out, void* stream) {
+  FVIT_CHECK(x && gamma && beta && out && rows > 0, "fvit_ln_fwd: bad arguments");
+  FVIT_CHECK(C % 4 == 0 && C <= 32 * 4 * LN_MAX_VEC, "fvit_ln_fwd: C=%d unsupported", C);
+  FVIT_CHECK(ldx % 4 == 0 && ldo % 4 == 0 && (!wb || ldwb % 4 == 0), "fvit_ln_fwd: unaligned strides");
+  FVIT_CHECK(!add || group > 0, "fvit_ln_fwd: add needs group > 0");
+  const int block = 256, wpb = block / 32;
+  long long grid = ((long long)rows + wpb - 1) / wpb;
+  const long long cap = (long long)num_sms() * 8;
+  if (grid > cap) grid = cap;
+  ln_fwd_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(
+      x, ldx, in_map, rows, C, add, group > 0 ? group : 1, skip, wb, ldwb, gamma, beta, eps,
+      (__half*)out, ldo, out_map, mean_out, rstd_out);
+  return post_launch("ln_fwd_kernel");
+}
+
+int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads,
+                       int32_t head_dim, const float* bias, float scale, void* out, int64_t ldo,
+                       float* probs_out, void* stream) {
+  FVIT_CHECK(qkv && out && groups > 0 && S > 0 && heads > 0 && head_dim > 0,
+             "fvit_attn_core_fwd: bad arguments");
+  const int C = heads * head_dim;
+  const size_t smem = ((size_t)3 * S * (head_dim + 1) + (size_t)S * (S + 1)) * sizeof(float);
+  FVIT_CHECK(smem <= 227 * 1024, "fvit_attn_core_fwd: S=%d head_dim=%d needs %zu B of shared memory", S,
+             head_dim, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    FVIT_CUDA(cudaFuncSetAttribute(attn_core_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    configured = 227 * 1024;
+  }
+  const int block = S * S >= 4096 ? 256 : 128;
+  attn_core_simt_kernel<<<(unsigned)((long long)groups * heads), block, smem, (cudaStream_t)stream>>>(
+      (const __half*)qkv, ldq, S, head_dim, heads, C, bias, scale, (__half*)out, ldo, probs_out);
+  return post_launch("attn_core_simt_kernel");
+}
+
+int fvit_cpb_mlp_fwd(const float* coords, int32_t P, const float* w0, const float* b0, const float* w1,
+                     int32_t D, float* out, float* hidden_out, void* stream) {
+  FVIT_CHECK(coords && w0 && b0 && w1 && out && P > 0 && D > 0, "fvit_cpb_mlp_fwd: bad arguments");
+  cpb_mlp_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(coords, P, w0, b0, w1, D, out, hidden_out);
+  return post_launch("cpb_mlp_kernel");
+}
+
+int fvit_attn_bias_fwd(const float* table, const int64_t* index, int32_t heads, int32_t S, int32_t L,
+                       float* bias, void* stream) {
+  FVIT_CHECK(table && index && bias && heads > 0 && S >= L && L > 0, "fvit_attn_bias_fwd: bad arguments");
+  const long long total = (long long)heads * S * S;
+  attn_bias_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      table, (const long long*)index, heads, S, L, bias);
+  return post_launch("attn_bias_kernel");
+}
+
+int fvit_token_init_fwd(const float* xs, int64_t ldx, const int32_t* pix_map, int32_t B, int32_t Hp,
+                        int32_t Wp, int32_t C, const float* w, const float* bias, int32_t kh, int32_t kw,
+                        int32_t sh, int32_t sw, int32_t oh, int32_t ow, const int32_t* ct_row_map,
+                        float* out, int64_t ldo, void* stream) {
+  FVIT_CHECK(xs && pix_map && w && bias && ct_row_map && out, "fvit_token_init_fwd: null argument");
+  FVIT_CHECK((oh - 1) * sh + kh <= Hp && (ow - 1) * sw + kw <= Wp, "fvit_token_init_fwd: pool window out of range");
+  const long long total = (long long)B * oh * ow * C;
+  token_init_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      xs, ldx, pix_map, B, Hp, Wp, C, w, bias, kh, kw, sh, sw, oh, ow, ct_row_map, out, ldo);
+  return post_launch("token_init_kernel");
+}
+
+int fvit_propagate_fwd(float* xs, int64_t ldx, const int32_t* src_map, int32_t rows, int32_t C,
+                       const float* gamma, void* stream) {
+  FVIT_CHECK(xs && src_map && rows > 0 && C % 4 == 0 && ldx % 4 == 0, "fvit_propagate_fwd: bad arguments");
+  const long long total = (long long)rows * (C / 4);
+  propagate_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(xs, ldx, src_map, rows, C,
+                                                                           gamma);
+  return post_launch("propagate_kernel");
+}
+
+int fvit_pool_affine_fwd(const float* xs, int64_t ldx, const int32_t* row_map, int32_t B, int32_t T,
+                         int32_t C, const float* scale, const float* shift, void* out, int64_t ldo,
+                         void* stream) {
+  FVIT_CHECK(xs && scale && shift && out && B > 0 && T > 0 && C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0,
+             "fvit_pool_affine_fwd: bad arguments");
+  const long long total = (long long)B * (C / 4);
+  pool_affine_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(
+      xs, ldx, row_map, B, T, C, scale, shift, (__half*)out, ldo);
+  return post_launch("pool_affine_kernel");
+}
+
+}  // extern "C"

@@ -78,7 +78,20 @@ def _bind_ops(lib) -> None:
         fn.restype = C.c_int
 
 
-_OP_SIGS: dict[str, list] = {}
+_P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_OP_SIGS: dict[str, list] = {
+    "fvit_cast_pad_f16": [_P, _L, _P, _L, _I, _I, _I, _P],
+    "fvit_pack_conv3x3_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "fvit_affine_fold": [_P, _P, _I, _P, _P, _P, _P, _F, _P, _P, _P],
+    "fvit_stem_conv_fwd": [_P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P, _P, _P],
+    "fvit_ln_fwd": [_P, _L, _P, _I, _I, _P, _I, _I, _P, _L, _P, _P, _F, _P, _L, _P, _P, _P, _P],
+    "fvit_attn_core_fwd": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
+    "fvit_cpb_mlp_fwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P],
+    "fvit_attn_bias_fwd": [_P, _P, _I, _I, _I, _P, _P],
+    "fvit_token_init_fwd": [_P, _L, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
+    "fvit_propagate_fwd": [_P, _L, _P, _I, _I, _P, _P],
+    "fvit_pool_affine_fwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _L, _P],
+}
 
 
 def check(rc: int) -> None:
@@ -159,3 +172,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
         g.out_f16, g.ld_out_f16 = out_f16.data_ptr(), out_f16.stride(0)
     g.col_sum, g.col_sumsq = ptr(col_sum), ptr(col_sumsq)
     check(lib.fvit_gemm(C.byref(g), stream_ptr()))
+
+
+def call(name: str, *args) -> None:
+    """Invoke a non-GEMM entry point; the current torch CUDA stream is appended as last argument."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc != 0:
+        raise FvitError(f"{name}: {lib.fvit_last_error().decode()}")

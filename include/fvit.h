@@ -103,6 +103,80 @@ typedef struct fvit_gemm_args {
 
 int fvit_gemm(const fvit_gemm_args* args, void* stream);
 
+/* ---- weight preparation (fp32 nn.Parameter -> packed fp16 tensor-core operands) ---------------- */
+/* dst[r][0:cols_pad] = (half)src[r][0:cols], zero padded; nn.Linear weights [out, in] (fv.py:393-395,
+ * 545-547, 927) become K-major B operands with a 16-byte aligned row stride. */
+int fvit_cast_pad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows,
+                      int32_t cols, int32_t cols_pad, void* stream);
+/* nn.Conv2d weight [cout][cin][3][3] (fv.py:434, 461, 489, 492) -> [cout][9][kc_pad] fp16, tap-major;
+ * transpose_io != 0 builds the data-gradient operand [cin][9 flipped][kc_pad >= cout]. */
+int fvit_pack_conv3x3_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,
+                          int32_t transpose_io, void* stream);
+/* scale/shift so that acc*scale+shift == layer_scale * BN_eval(acc + bias) (fv.py:504-510) or
+ * layer_scale * (acc + bias) (fv.py:679-680, 690-691). Any of the BN / bias / layer_scale inputs may
+ * be NULL. */
+int fvit_affine_fold(float* scale, float* shift, int32_t n, const float* bn_w, const float* bn_b,
+                     const float* bn_mean, const float* bn_var, float eps, const float* bias,
+                     const float* layer_scale, void* stream);
+
+/* ---- PatchEmbed first convolution (fv.py:458-460): 3x3 stride 2 pad 1 on the fp32 NCHW image ----
+ * (element strides sb, sc, sh, sw), y = relu?(conv * scale + shift) as fp16 rows of `cout` channels at
+ * out_row_map[b*Ho*Wo + oh*Wo + ow]. With col_sum/col_sumsq: adds per-channel sum / sum of squares of
+ * the raw convolution (train-mode BatchNorm statistics); `out` may then be NULL. */
+int fvit_stem_conv_fwd(const float* x, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B,
+                       int32_t cin, int32_t H, int32_t W, const float* wgt, int32_t cout,
+                       const float* scale, const float* shift, int32_t relu, const int32_t* out_row_map,
+                       void* out, int64_t ldo, float* col_sum, float* col_sumsq, void* stream);
+
+/* ---- LayerNorm forward over the channel dim of token rows (nn.LayerNorm eps 1e-5 fv.py:615,631,
+ * 643-644, 690-691; timm LayerNorm2d eps 1e-6 fv.py:432,438), fused with the positional-embedding add
+ * of PosEmbMLPSwinv1D (fv.py:366, 665, 676), with row gather (window partition / ct_dewindow,
+ * fv.py:83-101) on the input and row scatter on the output.
+ *   v   = x[in_map ? in_map[r] : r] + ( (r % group) >= skip ? add[(r % group) - skip] : 0 )
+ *   wb[r] = v (optional fp32 write-back of the updated residual stream)
+ *   out[out_map ? out_map[r] : r] = (half)((v - mean) * rstd * gamma + beta)
+ * mean_out / rstd_out (optional) receive the row statistics for the backward pass. */
+int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows, int32_t C,
+                const float* add, int32_t group, int32_t skip, float* wb, int64_t ldwb,
+                const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
+                const int32_t* out_map, float* mean_out, float* rstd_out, void* stream);
+
+/* ---- attention core of WindowAttention.forward (fv.py:559-565) on a packed qkv matrix -------------
+ * qkv fp16 [groups*S, 3*heads*head_dim] (q | k | v); for every group of S consecutive tokens and every
+ * head: out = softmax(q k^T * scale + bias[head]) v, written fp16 to out[row, head*head_dim + d].
+ * bias fp32 [heads, S, S] or NULL. probs_out (optional, fp32 [groups, heads, S, S]) saves P. */
+int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads,
+                       int32_t head_dim, const float* bias, float scale, void* out, int64_t ldo,
+                       float* probs_out, void* stream);
+
+/* ---- positional MLPs (cpb_mlp: Linear(2,512)+ReLU+Linear(512,D, no bias); fv.py:223-225, 322-324) --
+ * out[p][d] for P coordinate pairs; hidden_out (optional, [P,512]) saves the ReLU output. */
+int fvit_cpb_mlp_fwd(const float* coords, int32_t P, const float* w0, const float* b0, const float* w1,
+                     int32_t D, float* out, float* hidden_out, void* stream);
+/* bias[h][r][c] = 16*sigmoid(table[index[(r-ng)*L + (c-ng)]][h]) for r,c >= ng = S-L, else 0
+ * (PosEmbMLPSwinv2D.forward fv.py:276-299). */
+int fvit_attn_bias_fwd(const float* table, const int64_t* index, int32_t heads, int32_t S, int32_t L,
+                       float* bias, void* stream);
+
+/* ---- TokenInitializer.forward (fv.py:733-738; fvar.py:729-750): depthwise 3x3 (+bias) then AvgPool
+ * (kh x kw, stride sh x sw) -> oh x ow carrier tokens per image, written to rows ct_row_map[...] of
+ * `out`. The feature map is read through pix_map[(b*Hp + y)*Wp + x] -> row of xs (-1: zero pixel). */
+int fvit_token_init_fwd(const float* xs, int64_t ldx, const int32_t* pix_map, int32_t B, int32_t Hp,
+                        int32_t Wp, int32_t C, const float* w, const float* bias, int32_t kh, int32_t kw,
+                        int32_t sh, int32_t sw, int32_t oh, int32_t ow, const int32_t* ct_row_map,
+                        float* out, int64_t ldo, void* stream);
+
+/* ---- carrier -> window propagation (fv.py:697-700): xs[r] += gamma * xs[src_map[r]] (src_map < 0:
+ * row untouched; gamma NULL = 1). */
+int fvit_propagate_fwd(float* xs, int64_t ldx, const int32_t* src_map, int32_t rows, int32_t C,
+                       const float* gamma, void* stream);
+
+/* ---- head (fv.py:953-958): BatchNorm2d folded into AdaptiveAvgPool2d(1):
+ * out[b][c] = (half)(mean_t xs[row_map[b*T + t]][c] * scale[c] + shift[c]) */
+int fvit_pool_affine_fwd(const float* xs, int64_t ldx, const int32_t* row_map, int32_t B, int32_t T,
+                         int32_t C, const float* scale, const float* shift, void* out, int64_t ldo,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif
