@@ -1,0 +1,541 @@
+"""Execution engine: turns a FasterViT module + input shape into a static plan of libfvit_sm100.so
+kernel launches over persistent device buffers, and runs it.
+
+Data layout in HBM (all activations are token-major / NHWC row matrices):
+  * conv levels (fv.py:502-512): zero-bordered maps, row = b*(H+2)*(W+2) + (y+1)*(W+2) + (x+1); a fp32
+    copy carries the residual stream, a fp16 copy is the tensor-core operand. A 3x3/s1 convolution is a
+    9-tap GEMM whose tap (dy,dx) shifts the A-operand rows by (dy-1)*(W+2)+(dx-1) (no im2col);
+  * stride-2 convolutions (fv.py:434, 461) read four parity planes plane[(y&1)*2+(x&1)][b][(y>>1)+1][(x>>1)+1]
+    with a zero top row / left column, which makes every tap a unit-stride shifted box as well;
+  * transformer levels (fv.py:662-701): one fp32 buffer xs[nW*S + B*n_ct, C]; window w owns rows
+    [w*S, (w+1)*S): its ct_size^2 carrier tokens first, then its ws*ws tokens (the `torch.cat` of
+    fv.py:687 materialised once); the tail B*n_ct rows hold the raster-ordered carrier tokens while
+    the carrier branch runs. window_partition / window_reverse / ct_dewindow / ct_window / cat / split
+    (fv.py:83-109, 687, 695) never move data: they are int32 row maps consumed by the LayerNorm
+    kernel (gather) and the GEMM epilogue (scatter).
+Tensor-core operands are fp16, accumulation fp32, residual stream / LayerNorm / softmax / BN fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+
+
+def _ru(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------------- index maps
+def _ct_dewindow_perm(cs: int, sr: list[int]) -> torch.Tensor:
+    """raster position r -> window-major carrier index it is read from; the literal index algebra of
+    ct_dewindow(ct, cs*sr[0], cs*sr[1], cs) (fv.py:96-101, call fv.py:673 / fvar.py:679)."""
+    Wd, Hd = cs * sr[0], cs * sr[1]
+    idx = torch.arange(Wd * Hd).view(1, Wd // cs, Hd // cs, cs, cs, 1)
+    return idx.permute(0, 5, 1, 3, 2, 4).reshape(Wd * Hd)
+
+
+def _ct_window_perm(cs: int, sr: list[int]) -> torch.Tensor:
+    """window-major slot q (= window*cs*cs + slot) -> raster position it receives; the index algebra of
+    ct_window(ct, cs*sr[0], cs*sr[1], cs).reshape(nW, cs*cs, C) (fv.py:104-109, 683-685)."""
+    Wd, Hd = cs * sr[0], cs * sr[1]
+    idx = torch.arange(Wd * Hd).view(1, Hd // cs, cs, Wd // cs, cs, 1)
+    return idx.permute(0, 1, 3, 2, 4, 5).reshape(Wd * Hd)
+
+
+class _Bufs:
+    """Device buffer factory: zero-initialised persistent tensors, named for debugging."""
+
+    def __init__(self, device):
+        self.device = device
+        self.named: dict[str, torch.Tensor] = {}
+        self.nbytes = 0
+
+    def new(self, name: str, shape, dtype) -> torch.Tensor:
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self.named[name] = t
+        self.nbytes += t.numel() * t.element_size()
+        return t
+
+    def i32(self, name: str, host: torch.Tensor) -> torch.Tensor:
+        t = host.to(torch.int32).contiguous().to(self.device)
+        self.named[name] = t
+        return t
+
+
+class Plan:
+    """Static launch list for one (batch, height, width, training) signature."""
+
+    def __init__(self, model, B: int, H: int, W: int, training: bool, device):
+        self.model, self.B, self.H, self.W, self.training, self.device = model, B, H, W, training, device
+        self.lib = L.load()
+        self.bufs = _Bufs(device)
+        self.prep_ops: list[tuple] = []   # weight preparation (fp32 params -> packed fp16 / folded vectors)
+        self.ops: list[tuple] = []        # the forward pass
+        self._gemm_keep: list = []        # keeps ctypes structs alive
+        self._x_args: list = []           # stem-conv calls that take the input pointer at run time
+        self._build()
+
+    # ---- op emitters --------------------------------------------------------------------------
+    def _op(self, target: list, name: str, *args) -> None:
+        target.append((getattr(self.lib, name), args, name))
+
+    def _gemm(self, *, a, a_rows, lda, b, ldb, m, n, kc, taps=None, a_planes=1, a_plane_stride=0,
+              b_rows=0, col_scale=None, col_shift=None, col_scale2=None, act=L.ACT_NONE, resid=None,
+              ld_resid=0, row_map=None, out_f32=None, ld_o32=0, out_f16=None, ld_o16=0,
+              col_sum=None, col_sumsq=None, alpha=1.0, tile_n=0) -> None:
+        g = L.GemmArgs()
+        g.a, g.a_rows, g.lda, g.a_plane_stride, g.a_planes = a, a_rows, lda, a_plane_stride, a_planes
+        g.b, g.b_rows, g.ldb = b, b_rows or n, ldb
+        g.m, g.n, g.kc = m, n, kc
+        taps = taps or [(0, 0)]
+        g.ntaps = len(taps)
+        for i, (s, p) in enumerate(taps):
+            g.tap_shift[i], g.tap_plane[i] = s, p
+        g.split_k, g.tile_n, g.alpha, g.act = 1, tile_n, alpha, act
+        g.col_scale, g.col_shift, g.col_scale2 = col_scale, col_shift, col_scale2
+        g.resid, g.ld_resid, g.row_map = resid, ld_resid, row_map
+        g.out_f32, g.ld_out_f32, g.out_f16, g.ld_out_f16 = out_f32, ld_o32, out_f16, ld_o16
+        g.col_sum, g.col_sumsq = col_sum, col_sumsq
+        self._gemm_keep.append(g)
+        self.ops.append((self.lib.fvit_gemm, (C.byref(g),), "fvit_gemm"))
+
+    # ---- weight preparation emitters ------------------------------------------------------------
+    def _pack_linear(self, name: str, lin: nn.Linear) -> tuple[torch.Tensor, int]:
+        n, k = lin.weight.shape
+        ld = _ru(k, 8)
+        w16 = self.bufs.new(name + ".w16", (n, ld), torch.float16)
+        self._op(self.prep_ops, "fvit_cast_pad_f16", lin.weight.data_ptr(), k, w16.data_ptr(), ld, n, k, ld)
+        return w16, ld
+
+    def _pack_conv(self, name: str, conv: nn.Conv2d) -> tuple[torch.Tensor, int]:
+        cout, cin = conv.weight.shape[:2]
+        kc_pad = _ru(cin, 64)
+        w16 = self.bufs.new(name + ".w16", (cout, 9 * kc_pad), torch.float16)
+        self._op(self.prep_ops, "fvit_pack_conv3x3_f16", conv.weight.data_ptr(), w16.data_ptr(), cout, cin,
+                 kc_pad, 0)
+        return w16, 9 * kc_pad
+
+    def _fold(self, name: str, n: int, bn: nn.BatchNorm2d | None = None, bias=None, ls=None):
+        """(scale, shift) device vectors for the GEMM epilogue; see fvit_affine_fold."""
+        sc = self.bufs.new(name + ".scale", (n,), torch.float32)
+        sh = self.bufs.new(name + ".shift", (n,), torch.float32)
+        p = lambda t: None if t is None else t.data_ptr()
+        self._op(self.prep_ops, "fvit_affine_fold", sc.data_ptr(), sh.data_ptr(), n,
+                 p(bn.weight) if bn is not None else None, p(bn.bias) if bn is not None else None,
+                 p(bn.running_mean) if bn is not None else None,
+                 p(bn.running_var) if bn is not None else None,
+                 float(bn.eps) if bn is not None else 0.0, p(bias), p(ls))
+        return sc, sh
+
+    # ---- plan construction ----------------------------------------------------------------------
+    def _build(self) -> None:
+        m, B = self.model, self.B
+        cfg = m.cfg
+        if self.training:
+            raise L.FvitError("training-mode forward/backward kernels are not built yet in this round; "
+                              "call model.eval() (there is no PyTorch fallback)")
+        dim, in_dim, depths = cfg["dim"], cfg["in_dim"], cfg["depths"]
+        nb = self.bufs
+        # ---------------- stem: conv1 (SIMT, fp32) -> parity planes -> conv2 (tensor cores) -> L0
+        H1, W1 = (self.H + 1) // 2, (self.W + 1) // 2     # after conv1
+        H0, W0 = (H1 + 1) // 2, (W1 + 1) // 2             # after conv2 = level-0 map
+        ld_in = _ru(in_dim, 8)
+        pl_rows = B * (H0 + 1) * (W0 + 1)
+        stem_planes = nb.new("stem.planes", (4 * pl_rows, ld_in), torch.float16)
+        bi, yi, xi = torch.meshgrid(torch.arange(B), torch.arange(H1), torch.arange(W1), indexing="ij")
+        plane = (yi & 1) * 2 + (xi & 1)
+        stem_map = nb.i32("stem.map", (plane * pl_rows + bi * (H0 + 1) * (W0 + 1)
+                                       + ((yi >> 1) + 1) * (W0 + 1) + (xi >> 1) + 1).reshape(-1))
+        pe = m.patch_embed.conv_down
+        s1, t1 = self._fold("stem.bn1", in_dim, pe[1])
+        self._x_args.append(dict(B=B, cin=cfg["in_chans"], H=self.H, W=self.W, wgt=pe[0].weight.data_ptr(),
+                                 cout=in_dim, scale=s1.data_ptr(), shift=t1.data_ptr(), relu=1,
+                                 row_map=stem_map.data_ptr(), out=stem_planes.data_ptr(), ldo=ld_in))
+        self.ops.append(("stem", len(self._x_args) - 1, "fvit_stem_conv_fwd"))
+
+        lvl = self._conv_level_buffers(0, dim, H0, W0)
+        w16, ldw = self._pack_conv("stem.conv2", pe[3])
+        s2, t2 = self._fold("stem.bn2", dim, pe[4])
+        self._gemm(a=stem_planes.data_ptr(), a_rows=pl_rows, lda=ld_in, a_planes=4,
+                   a_plane_stride=pl_rows * ld_in, b=w16.data_ptr(), ldb=ldw, m=pl_rows, n=dim, kc=in_dim,
+                   taps=self._s2_taps(W0), col_scale=s2.data_ptr(), col_shift=t2.data_ptr(), act=L.ACT_RELU,
+                   row_map=self._plane_to_padded_map("stem.to_l0", B, H0, W0).data_ptr(),
+                   out_f32=lvl["x32"].data_ptr(), ld_o32=lvl["C"], out_f16=lvl["x16"].data_ptr(),
+                   ld_o16=lvl["ld"])
+
+        # ---------------- levels
+        Hc, Wc, Cc = H0, W0, dim
+        for i, level in enumerate(m.levels):
+            if level.conv:
+                if i > 0:
+                    lvl = self._conv_level_buffers(i, Cc, Hc, Wc)
+                    self._emit_downsample_conv(i - 1, prev, lvl, to_conv=True)
+                self._emit_conv_blocks(i, level, lvl)
+                prev = dict(kind="conv", **lvl)
+            else:
+                tl = self._token_level_buffers(i, level, Cc, Hc, Wc)
+                self._emit_downsample_conv(i - 1, prev, tl, to_conv=False)
+                self._emit_token_level(i, level, tl)
+                prev = dict(kind="tok", **tl)
+            if level.downsample is not None:
+                Hc, Wc, Cc = (Hc + 1) // 2, (Wc + 1) // 2, Cc * 2
+        # ---------------- head: BN folded into the average pool, then the classifier GEMM
+        self.feat = prev
+        nf = m.num_features
+        sN, tN = self._fold("norm", nf, m.norm)
+        T = prev["H"] * prev["W"]
+        pooled = nb.new("head.pooled", (B, _ru(nf, 8)), torch.float16)
+        self._op(self.ops, "fvit_pool_affine_fwd", prev["xs"].data_ptr(), nf, prev["crop_map"].data_ptr(), B, T,
+                 nf, sN.data_ptr(), tN.data_ptr(), pooled.data_ptr(), pooled.stride(0))
+        if isinstance(m.head, nn.Linear):
+            hw16, ldh = self._pack_linear("head", m.head)
+            self.logits = nb.new("logits", (B, m.num_classes), torch.float32)
+            self._gemm(a=pooled.data_ptr(), a_rows=B, lda=pooled.stride(0), b=hw16.data_ptr(), ldb=ldh, m=B,
+                       n=m.num_classes, kc=nf, col_shift=m.head.bias.data_ptr(),
+                       out_f32=self.logits.data_ptr(), ld_o32=m.num_classes)
+        else:
+            self.logits = None
+            self.pooled = pooled
+
+    # ---- geometry helpers -----------------------------------------------------------------------
+    def _s2_taps(self, Wo: int) -> list[tuple[int, int]]:
+        """9 taps of a 3x3 stride-2 pad-1 convolution over the parity-plane layout: input row 2*oh+r-1
+        lives in plane parity (r+1)&1 at plane row oh + (r==0 ? -1 : 0) (+1 border offset cancels)."""
+        taps = []
+        for r in range(3):
+            ph, da = (1, -1) if r == 0 else ((0, 0) if r == 1 else (1, 0))
+            for s in range(3):
+                pw, db = (1, -1) if s == 0 else ((0, 0) if s == 1 else (1, 0))
+                taps.append((da * (Wo + 1) + db, ph * 2 + pw))
+        return taps
+
+    def _plane_to_padded_map(self, name: str, B: int, Ho: int, Wo: int) -> torch.Tensor:
+        """plane-space output row (b, a+1, c+1) -> zero-bordered level row; border rows -> -1."""
+        bi, ai, ci = torch.meshgrid(torch.arange(B), torch.arange(Ho + 1), torch.arange(Wo + 1), indexing="ij")
+        dst = bi * (Ho + 2) * (Wo + 2) + ai * (Wo + 2) + ci  # (a-1)+1 = a
+        dst = torch.where((ai >= 1) & (ci >= 1), dst, torch.full_like(dst, -1))
+        return self.bufs.i32(name, dst.reshape(-1))
+
+    def _conv_level_buffers(self, i: int, Cc: int, Hc: int, Wc: int) -> dict:
+        B, nb = self.B, self.bufs
+        rows = B * (Hc + 2) * (Wc + 2)
+        ld = _ru(Cc, 8)
+        bi, yi, xi = torch.meshgrid(torch.arange(B), torch.arange(Hc + 2), torch.arange(Wc + 2), indexing="ij")
+        inside = (yi >= 1) & (yi <= Hc) & (xi >= 1) & (xi <= Wc)
+        ident = torch.arange(rows).view(B, Hc + 2, Wc + 2)
+        interior = nb.i32(f"l{i}.interior", torch.where(inside, ident, torch.full_like(ident, -1)).reshape(-1))
+        pix = nb.i32(f"l{i}.pix", ident[:, 1:-1, 1:-1].reshape(-1))  # pixel (b,y,x) -> padded row
+        return dict(C=Cc, H=Hc, W=Wc, ld=ld, rows=rows, interior=interior, pix=pix,
+                    x32=nb.new(f"l{i}.x32", (rows, Cc), torch.float32),
+                    x16=nb.new(f"l{i}.x16", (rows, ld), torch.float16),
+                    h16=nb.new(f"l{i}.h16", (rows, ld), torch.float16))
+
+    # ---- conv levels ------------------------------------------------------------------------------
+    def _emit_conv_blocks(self, i: int, level, lv: dict) -> None:
+        Cc, Wp = lv["C"], lv["W"] + 2
+        taps = [((dy - 1) * Wp + (dx - 1), 0) for dy in range(3) for dx in range(3)]
+        for j, blk in enumerate(level.blocks):
+            nm = f"l{i}.b{j}"
+            w1, ld1 = self._pack_conv(nm + ".conv1", blk.conv1)
+            w2, ld2 = self._pack_conv(nm + ".conv2", blk.conv2)
+            s1, t1 = self._fold(nm + ".bn1", Cc, blk.norm1, bias=blk.conv1.bias)
+            s2, t2 = self._fold(nm + ".bn2", Cc, blk.norm2, bias=blk.conv2.bias, ls=getattr(blk, "gamma", None))
+            # h = GELU(BN(conv1(x)))                                        (fv.py:504-506)
+            self._gemm(a=lv["x16"].data_ptr(), a_rows=lv["rows"], lda=lv["ld"], b=w1.data_ptr(), ldb=ld1,
+                       m=lv["rows"], n=Cc, kc=Cc, taps=taps, col_scale=s1.data_ptr(), col_shift=t1.data_ptr(),
+                       act=L.ACT_GELU, row_map=lv["interior"].data_ptr(), out_f16=lv["h16"].data_ptr(),
+                       ld_o16=lv["ld"])
+            # x = x + gamma * BN(conv2(h))                                   (fv.py:507-511)
+            self._gemm(a=lv["h16"].data_ptr(), a_rows=lv["rows"], lda=lv["ld"], b=w2.data_ptr(), ldb=ld2,
+                       m=lv["rows"], n=Cc, kc=Cc, taps=taps, col_scale=s2.data_ptr(), col_shift=t2.data_ptr(),
+                       resid=lv["x32"].data_ptr(), ld_resid=Cc, row_map=lv["interior"].data_ptr(),
+                       out_f32=lv["x32"].data_ptr(), ld_o32=Cc, out_f16=lv["x16"].data_ptr(), ld_o16=lv["ld"])
+
+    def _emit_downsample_conv(self, i: int, src: dict, dst: dict, to_conv: bool) -> None:
+        """Downsample of level i (fv.py:437-440): channel LayerNorm (eps 1e-6) scattered into parity
+        planes, then the 3x3/s2 convolution as a 9-tap GEMM writing the next level's layout."""
+        B, nb = self.B, self.bufs
+        ds = self.model.levels[i].downsample
+        Cs, Hs, Ws = src["C"], src["H"], src["W"]
+        Ho, Wo = (Hs + 1) // 2, (Ws + 1) // 2
+        ld = _ru(Cs, 8)
+        pl_rows = B * (Ho + 1) * (Wo + 1)
+        planes = nb.new(f"ds{i}.planes", (4 * pl_rows, ld), torch.float16)
+        bi, yi, xi = torch.meshgrid(torch.arange(B), torch.arange(Hs), torch.arange(Ws), indexing="ij")
+        omap = nb.i32(f"ds{i}.omap", (((yi & 1) * 2 + (xi & 1)) * pl_rows + bi * (Ho + 1) * (Wo + 1)
+                                      + ((yi >> 1) + 1) * (Wo + 1) + (xi >> 1) + 1).reshape(-1))
+        src_rows = src["pix"] if src["kind"] == "conv" else src["crop_map"]
+        src_x = src["x32"] if src["kind"] == "conv" else src["xs"]
+        self._op(self.ops, "fvit_ln_fwd", src_x.data_ptr(), Cs, src_rows.data_ptr(), B * Hs * Ws, Cs,
+                 None, 1, 0, None, 0, ds.norm.weight.data_ptr(), ds.norm.bias.data_ptr(), float(ds.norm.eps),
+                 planes.data_ptr(), ld, omap.data_ptr(), None, None)
+        w16, ldw = self._pack_conv(f"ds{i}.conv", ds.reduction[0])
+        if to_conv:
+            rmap = self._plane_to_padded_map(f"ds{i}.rmap", B, Ho, Wo)
+            self._gemm(a=planes.data_ptr(), a_rows=pl_rows, lda=ld, a_planes=4, a_plane_stride=pl_rows * ld,
+                       b=w16.data_ptr(), ldb=ldw, m=pl_rows, n=2 * Cs, kc=Cs, taps=self._s2_taps(Wo),
+                       row_map=rmap.data_ptr(), out_f32=dst["x32"].data_ptr(), ld_o32=dst["C"],
+                       out_f16=dst["x16"].data_ptr(), ld_o16=dst["ld"])
+        else:
+            # plane-space row (b, a+1, c+1) -> token row of pixel (a, c) in the window-major buffer
+            pm = dst["pix_map_host"]  # [B, Hp, Wp]
+            full = torch.full((B, Ho + 1, Wo + 1), -1, dtype=torch.int64)
+            full[:, 1:, 1:] = pm[:, :Ho, :Wo]
+            rmap = nb.i32(f"ds{i}.rmap", full.reshape(-1))
+            self._gemm(a=planes.data_ptr(), a_rows=pl_rows, lda=ld, a_planes=4, a_plane_stride=pl_rows * ld,
+                       b=w16.data_ptr(), ldb=ldw, m=pl_rows, n=2 * Cs, kc=Cs, taps=self._s2_taps(Wo),
+                       row_map=rmap.data_ptr(), out_f32=dst["xs"].data_ptr(), ld_o32=dst["C"])
+
+    # ---- transformer levels -----------------------------------------------------------------------
+    def _token_level_buffers(self, i: int, level, Cc: int, Hc: int, Wc: int) -> dict:
+        B, nb = self.B, self.bufs
+        ws, cs = level.window_size, self.model.cfg["ct_size"]
+        Hp, Wp = _ru(Hc, ws), _ru(Wc, ws)
+        if not self.model.any_res and (Hp != Hc or Wp != Wc):
+            raise L.FvitError(f"level {i}: {Hc}x{Wc} map is not a multiple of window {ws} "
+                              "(use a *_any_res model for such resolutions)")
+        nwh, nww = Hp // ws, Wp // ws
+        has_ct = len(level.blocks) > 0 and level.blocks[0].has_carriers
+        sr = level.sr_ratio
+        if has_ct and (sr[0] != nwh or sr[1] != nww):
+            raise L.FvitError(f"level {i}: input gives {nwh}x{nww} windows but the model was built for {sr}")
+        ncw = cs * cs if has_ct else 0
+        S = ncw + ws * ws
+        nwin = nwh * nww
+        nW = B * nwin
+        n_ct = ncw * nwin
+        xs = nb.new(f"l{i}.xs", (nW * S + B * n_ct, Cc), torch.float32)
+        bi, yi, xi = torch.meshgrid(torch.arange(B), torch.arange(Hp), torch.arange(Wp), indexing="ij")
+        win = (bi * nwh + yi // ws) * nww + xi // ws
+        pix_map = win * S + ncw + (yi % ws) * ws + (xi % ws)          # [B, Hp, Wp] -> xs row
+        d = dict(C=Cc, H=Hc, W=Wc, Hp=Hp, Wp=Wp, ws=ws, cs=cs, S=S, ncw=ncw, nwin=nwin, nW=nW, n_ct=n_ct,
+                 xs=xs, pix_map_host=pix_map, padded=(Hp != Hc or Wp != Wc),
+                 pix_map=nb.i32(f"l{i}.pix_map", pix_map.reshape(-1)),
+                 crop_map=nb.i32(f"l{i}.crop_map", pix_map[:, :Hc, :Wc].reshape(-1)),
+                 xn16=nb.new(f"l{i}.xn16", (nW * S, Cc), torch.float16),
+                 qkv16=nb.new(f"l{i}.qkv16", (nW * S, 3 * Cc), torch.float16),
+                 ao16=nb.new(f"l{i}.ao16", (nW * S, Cc), torch.float16),
+                 h16=nb.new(f"l{i}.h16", (nW * S, int(Cc * self.model.cfg["mlp_ratio"])), torch.float16))
+        if has_ct:
+            ctr0 = nW * S
+            dew = _ct_dewindow_perm(cs, sr)     # raster r -> window-major index p
+            winp = _ct_window_perm(cs, sr)      # window-major slot q -> raster r
+            b_off = torch.arange(B).view(B, 1)
+            p = dew.view(1, -1)
+            d["ct_gather"] = nb.i32(f"l{i}.ct_gather", ((b_off * nwin + p // ncw) * S + p % ncw).reshape(-1))
+            # norm1 gather: carrier slots come from the raster buffer, window tokens stay in place
+            rows = torch.arange(nW * S).view(B, nwin, S).clone()
+            q = torch.arange(nwin * ncw).view(nwin, ncw)
+            rows[:, :, :ncw] = ctr0 + b_off.view(B, 1, 1) * n_ct + winp[q].view(1, nwin, ncw)
+            d["norm1_gather"] = nb.i32(f"l{i}.norm1_gather", rows.reshape(-1))
+            d["ctr0"] = ctr0
+            d["ctn16"] = nb.new(f"l{i}.ctn16", (B * n_ct, Cc), torch.float16)
+            d["ctqkv16"] = nb.new(f"l{i}.ctqkv16", (B * n_ct, 3 * Cc), torch.float16)
+            d["ctao16"] = nb.new(f"l{i}.ctao16", (B * n_ct, Cc), torch.float16)
+            d["cth16"] = nb.new(f"l{i}.cth16", (B * n_ct, int(Cc * self.model.cfg["mlp_ratio"])), torch.float16)
+            # tokenizer output (b, y0, x0) over the (cs*nwh) x (cs*nww) carrier grid -> xs row
+            oh, ow = cs * nwh, cs * nww
+            bt, y0, x0 = torch.meshgrid(torch.arange(B), torch.arange(oh), torch.arange(ow), indexing="ij")
+            wloc = (y0 // cs) * nww + x0 // cs
+            d["ct_rows"] = nb.i32(f"l{i}.ct_rows", ((bt * nwin + wloc) * S + (y0 % cs) * cs + x0 % cs).reshape(-1))
+            # propagation source (nearest-neighbour upsample cs -> ws, fv.py:656, 699-700)
+            r = torch.arange(nW * S)
+            t = r % S - ncw
+            src = (r // S) * S + ((t // ws) * cs // ws) * cs + (t % ws) * cs // ws
+            d["prop_src"] = nb.i32(f"l{i}.prop_src", torch.where(t >= 0, src, torch.full_like(src, -1)))
+        return d
+
+    def _emit_attention(self, nm: str, attn, rows: int, groups: int, S: int, xin, ld_in, qkv, ao, bias_buf) -> None:
+        """qkv GEMM (+bias) and the softmax(QK^T*scale + bias)V core (fv.py:559-565)."""
+        Cc = attn.qkv.in_features
+        wq, ldq = self._pack_linear(nm + ".qkv", attn.qkv)
+        self._gemm(a=xin.data_ptr(), a_rows=rows, lda=ld_in, b=wq.data_ptr(), ldb=ldq, m=rows, n=3 * Cc, kc=Cc,
+                   col_shift=attn.qkv.bias.data_ptr() if attn.qkv.bias is not None else None,
+                   out_f16=qkv.data_ptr(), ld_o16=3 * Cc)
+        self._op(self.ops, "fvit_attn_core_fwd", qkv.data_ptr(), 3 * Cc, groups, S, attn.num_heads, attn.head_dim,
+                 bias_buf.data_ptr(), float(attn.head_dim ** -0.5), ao.data_ptr(), Cc, None)
+
+    def _emit_bias(self, nm: str, rpb, S: int) -> torch.Tensor:
+        """PosEmbMLPSwinv2D (fv.py:276-307): table MLP + gather + 16*sigmoid, written straight into the
+        module's `relative_bias` buffer (which the reference also overwrites every forward)."""
+        P = rpb.relative_coords_table.shape[1] * rpb.relative_coords_table.shape[2]
+        table = self.bufs.new(nm + ".table", (P, rpb.num_heads), torch.float32)
+        if tuple(rpb.relative_bias.shape) != (1, rpb.num_heads, S, S):
+            rpb.relative_bias = torch.zeros(1, rpb.num_heads, S, S, device=self.device)
+        tgt = self.prep_ops  # batch independent: recomputed only when the weights change
+        self._op(tgt, "fvit_cpb_mlp_fwd", rpb.relative_coords_table.data_ptr(), P, rpb.cpb_mlp[0].weight.data_ptr(),
+                 rpb.cpb_mlp[0].bias.data_ptr(), rpb.cpb_mlp[2].weight.data_ptr(), rpb.num_heads,
+                 table.data_ptr(), None)
+        self._op(tgt, "fvit_attn_bias_fwd", table.data_ptr(), rpb.relative_position_index.data_ptr(),
+                 rpb.num_heads, S, rpb.window ** 2, rpb.relative_bias.data_ptr())
+        return rpb.relative_bias
+
+    def _emit_pos_embed(self, nm: str, tpe, n_side: int, Cc: int) -> torch.Tensor:
+        """PosEmbMLPSwinv1D rank 2 (fv.py:355-365): MLP over the centred n x n grid, written into the
+        module's `relative_bias` buffer; the add itself is fused into the following LayerNorm."""
+        r = torch.arange(n_side, dtype=torch.float32)
+        grid = torch.stack(torch.meshgrid(r, r, indexing="ij"))          # 2, n, n
+        grid = (grid - n_side // 2) / (n_side // 2)
+        coords = self.bufs.new(nm + ".coords", (n_side * n_side, 2), torch.float32)
+        coords.copy_(grid.flatten(1).t())
+        if tuple(tpe.relative_bias.shape) != (1, n_side * n_side, Cc):
+            tpe.relative_bias = torch.zeros(1, n_side * n_side, Cc, device=self.device)
+        self._op(self.prep_ops, "fvit_cpb_mlp_fwd", coords.data_ptr(), n_side * n_side,
+                 tpe.cpb_mlp[0].weight.data_ptr(), tpe.cpb_mlp[0].bias.data_ptr(),
+                 tpe.cpb_mlp[2].weight.data_ptr(), Cc, tpe.relative_bias.data_ptr(), None)
+        return tpe.relative_bias
+
+    def _emit_branch_out(self, nm: str, lin: nn.Linear, gamma, a, lda, rows, stream_buf, act=L.ACT_NONE,
+                         out16=None, ld16=0) -> None:
+        """x += gamma * (a @ W^T + b) in place on the fp32 residual stream (fv.py:679-680, 690-691)."""
+        n, k = lin.weight.shape
+        w16, ldw = self._pack_linear(nm, lin)
+        if isinstance(gamma, torch.Tensor):
+            sc, sh = self._fold(nm + ".ls", n, bias=lin.bias, ls=gamma)
+            cs_, sh_ = sc.data_ptr(), sh.data_ptr()
+        else:
+            cs_, sh_ = None, lin.bias.data_ptr()
+        self._gemm(a=a.data_ptr(), a_rows=rows, lda=lda, b=w16.data_ptr(), ldb=ldw, m=rows, n=n, kc=k,
+                   col_scale=cs_, col_shift=sh_, resid=stream_buf, ld_resid=n, out_f32=stream_buf, ld_o32=n)
+
+    def _emit_fc1(self, nm: str, lin: nn.Linear, a, lda, rows, out16) -> None:
+        n, k = lin.weight.shape
+        w16, ldw = self._pack_linear(nm, lin)
+        self._gemm(a=a.data_ptr(), a_rows=rows, lda=lda, b=w16.data_ptr(), ldb=ldw, m=rows, n=n, kc=k,
+                   col_shift=lin.bias.data_ptr(), act=L.ACT_GELU, out_f16=out16.data_ptr(), ld_o16=n)
+
+    def _emit_token_level(self, i: int, level, tl: dict) -> None:
+        B, Cc, S, ncw, ws = self.B, tl["C"], tl["S"], tl["ncw"], tl["ws"]
+        nW, n_ct = tl["nW"], tl["n_ct"]
+        xs = tl["xs"]
+        xs_ptr = xs.data_ptr()
+        has_ct = ncw > 0
+        if tl["padded"] or True:
+            # window-padding pixels are zero tokens at level entry (fvar.py:853-855); all other rows are
+            # fully overwritten by the downsample GEMM / tokenizer below
+            if tl["padded"]:
+                self.ops.append(("zero", xs, "memset"))
+        # (the downsample GEMM that fills the window tokens was emitted before this call)
+        if level.do_gt and has_ct:
+            tk = level.global_tokenizer
+            (kh, sh_, oh), (kw, sw_, ow) = tk.pool
+            self._op(self.ops, "fvit_token_init_fwd", xs_ptr, Cc, tl["pix_map"].data_ptr(), B, tl["Hp"], tl["Wp"],
+                     Cc, tk.pos_embed.weight.data_ptr(), tk.pos_embed.bias.data_ptr(), kh, kw, sh_, sw_, oh, ow,
+                     tl["ct_rows"].data_ptr(), xs_ptr, Cc)
+        for j, blk in enumerate(level.blocks):
+            nm = f"l{i}.b{j}"
+            pe = self._emit_pos_embed(nm + ".pe", blk.pos_embed, ws, Cc)
+            if has_ct:
+                ctr_ptr = xs_ptr + tl["ctr0"] * Cc * 4
+                rows_c = B * n_ct
+                hat_pe = None
+                if hasattr(blk, "hat_pos_embed"):
+                    hat_pe = self._emit_pos_embed(nm + ".hat_pe", blk.hat_pos_embed, int(n_ct ** 0.5), Cc)
+                # ct = dewindow(ct) + hat_pos_embed ; LN -> fp16                 (fv.py:673-679)
+                self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, tl["ct_gather"].data_ptr(), rows_c, Cc,
+                         hat_pe.data_ptr() if hat_pe is not None else None, n_ct, 0, ctr_ptr, Cc,
+                         blk.hat_norm1.weight.data_ptr(), blk.hat_norm1.bias.data_ptr(), float(blk.hat_norm1.eps),
+                         tl["ctn16"].data_ptr(), Cc, None, None, None)
+                hb = self._emit_bias(nm + ".hat_bias", blk.hat_attn.pos_emb_funct, n_ct)
+                self._emit_attention(nm + ".hat_attn", blk.hat_attn, rows_c, B, n_ct, tl["ctn16"], Cc,
+                                     tl["ctqkv16"], tl["ctao16"], hb)
+                self._emit_branch_out(nm + ".hat_proj", blk.hat_attn.proj, blk.gamma1, tl["ctao16"], Cc, rows_c,
+                                      ctr_ptr)
+                self._op(self.ops, "fvit_ln_fwd", ctr_ptr, Cc, None, rows_c, Cc, None, 1, 0, None, 0,
+                         blk.hat_norm2.weight.data_ptr(), blk.hat_norm2.bias.data_ptr(), float(blk.hat_norm2.eps),
+                         tl["ctn16"].data_ptr(), Cc, None, None, None)
+                self._emit_fc1(nm + ".hat_fc1", blk.hat_mlp.fc1, tl["ctn16"], Cc, rows_c, tl["cth16"])
+                self._emit_branch_out(nm + ".hat_fc2", blk.hat_mlp.fc2, blk.gamma2, tl["cth16"],
+                                      tl["cth16"].stride(0), rows_c, ctr_ptr)
+            # x = cat(ct_window(ct), x + pos_embed) ; LN(norm1) -> fp16          (fv.py:665, 683-690)
+            rows = nW * S
+            self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, tl["norm1_gather"].data_ptr() if has_ct else None, rows,
+                     Cc, pe.data_ptr(), S, ncw, xs_ptr, Cc, blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(),
+                     float(blk.norm1.eps), tl["xn16"].data_ptr(), Cc, None, None, None)
+            ab = self._emit_bias(nm + ".bias", blk.attn.pos_emb_funct, S)
+            self._emit_attention(nm + ".attn", blk.attn, rows, nW, S, tl["xn16"], Cc, tl["qkv16"], tl["ao16"], ab)
+            self._emit_branch_out(nm + ".proj", blk.attn.proj, blk.gamma3, tl["ao16"], Cc, rows, xs_ptr)
+            self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, None, rows, Cc, None, 1, 0, None, 0,
+                     blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr(), float(blk.norm2.eps),
+                     tl["xn16"].data_ptr(), Cc, None, None, None)
+            self._emit_fc1(nm + ".fc1", blk.mlp.fc1, tl["xn16"], Cc, rows, tl["h16"])
+            self._emit_branch_out(nm + ".fc2", blk.mlp.fc2, blk.gamma4, tl["h16"], tl["h16"].stride(0), rows, xs_ptr)
+            if has_ct and blk.last and blk.do_propagation:
+                g1 = blk.gamma1.data_ptr() if isinstance(blk.gamma1, torch.Tensor) else None
+                self._op(self.ops, "fvit_propagate_fwd", xs_ptr, Cc, tl["prop_src"].data_ptr(), rows, Cc, g1)
+
+    # ---- execution --------------------------------------------------------------------------------
+    def weights_key(self) -> tuple:
+        k = 0
+        for p in self.model.parameters():
+            k += p._version
+        for b_ in self.model.buffers():
+            k += b_._version
+        return (k,)
+
+    def run_ops(self, ops: list, x: torch.Tensor | None) -> None:
+        st = L.stream_ptr()
+        lib = self.lib
+        for fn, args, name in ops:
+            if fn == "stem":
+                a = self._x_args[args]
+                rc = lib.fvit_stem_conv_fwd(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
+                                            a["B"], a["cin"], a["H"], a["W"], a["wgt"], a["cout"], a["scale"],
+                                            a["shift"], a["relu"], a["row_map"], a["out"], a["ldo"], None, None, st)
+            elif fn == "zero":
+                args.zero_()
+                continue
+            else:
+                rc = fn(*args, st)
+            if rc != 0:
+                raise L.FvitError(f"{name}: {lib.fvit_last_error().decode()}")
+
+
+class Engine:
+    """Per-model cache of plans keyed by input signature; owns packed weights and workspaces."""
+
+    def __init__(self, model):
+        self.model = model
+        self.plans: dict = {}
+        self._prepped: dict = {}
+
+    def _plan(self, x: torch.Tensor) -> Plan:
+        if not x.is_cuda:
+            raise L.FvitError("FasterViT (fastervit_b200) runs on CUDA only: move the model and input to a "
+                              "B200 (`.cuda()`); there is no CPU / PyTorch fallback path")
+        if x.dim() != 4 or x.dtype != torch.float32:
+            raise L.FvitError(f"expected a float32 [B, C, H, W] tensor, got {tuple(x.shape)} {x.dtype}")
+        p0 = next(self.model.parameters())
+        if p0.device != x.device:
+            raise L.FvitError(f"model is on {p0.device} but the input is on {x.device}")
+        training = self.model.training
+        key = (tuple(x.shape), training, x.device.index)
+        plan = self.plans.get(key)
+        if plan is None:
+            with torch.cuda.device(x.device):
+                plan = Plan(self.model, x.shape[0], x.shape[2], x.shape[3], training, x.device)
+            self.plans[key] = plan
+        return plan
+
+    def forward(self, x: torch.Tensor, features_only: bool = False) -> torch.Tensor:
+        plan = self._plan(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()) and plan.training:
+            raise L.FvitError("backward kernels are not built yet in this round")
+        with torch.cuda.device(x.device):
+            wk = plan.weights_key()
+            if self._prepped.get(id(plan)) != wk:
+                plan.run_ops(plan.prep_ops, None)
+                self._prepped[id(plan)] = wk
+            plan.run_ops(plan.ops, x)
+        if features_only:
+            raise L.FvitError("forward_features is not wired yet; use forward()")
+        return plan.logits.clone()
+
+    def forward_head(self, feats: torch.Tensor) -> torch.Tensor:
+        raise L.FvitError("forward_head on external features is not wired yet; use forward()")

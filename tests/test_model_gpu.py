@@ -1,0 +1,56 @@
+"""GPU parity: FasterViT forward on the sm_100a kernels vs the golden logits produced by the unmodified
+reference in fp64 (tests/golden/*.pt, see oracle/make_golden.py). Tolerance: the north-star's
+"outputs within 1e-3 rel" measured as max|d|/max|ref| and as relative L2."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from pathlib import Path
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def _setup(case):
+    import fastervit_b200 as F
+    from oracle import fastervit_oracle as O
+    g = torch.load(GOLDEN / f"{case}.pt", weights_only=False)
+    model = F.create_model(g["entry"], drop_path_rate=0.0, **g["kwargs"]).eval()
+    O.synth_fill_(model.state_dict(), g["seeds"]["w"])
+    x = O.synth_input(g["eval"]["batch"], g["cfg"]["resolution"], g["seeds"]["x"], torch.float32)
+    return g, model.cuda(), x.cuda()
+
+
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "fv0", "fv4", "ar0"])
+def test_eval_logits_match_reference(case):
+    g, model, x = _setup(case)
+    with torch.no_grad():
+        out = model(x)
+    ref = g["eval"]["logits"].to(out.device)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    d = out.double() - ref
+    max_rel = (d.abs().max() / ref.abs().max()).item()
+    l2_rel = (d.norm() / ref.norm()).item()
+    print(f"{case}: max-rel {max_rel:.3e}  l2-rel {l2_rel:.3e}")
+    assert max_rel < 1e-3 and l2_rel < 1e-3
+    # the forward must be repeatable (persistent buffers are fully rewritten each call)
+    with torch.no_grad():
+        out2 = model(x)
+    assert torch.equal(out, out2)
+
+
+def test_cpu_input_raises():
+    import fastervit_b200 as F
+    model = F.create_model("faster_vit_0_224").eval()
+    with pytest.raises(Exception):
+        model(torch.zeros(1, 3, 224, 224))
+
+
+def test_batch_independence():
+    """Samples do not interact in eval mode: a batch of 3 equals three batches of 1."""
+    g, model, x = _setup("tiny_a")
+    x3 = torch.cat([x, x[:1] * 0.5], 0)
+    with torch.no_grad():
+        full = model(x3)
+        singles = torch.cat([model(x3[i:i + 1]) for i in range(3)], 0)
+    assert (full - singles).abs().max().item() <= 1e-5 * full.abs().max().item()
