@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""bench.py — images/sec of the FasterViT hot path on B200 (see the contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fv0_fwd] [--impl reference]
+
+One "step" = one pass of the hot path over one synthetic batch. Default workload = BASELINE.json
+configs[1]: faster_vit_0_224 forward-only, batch 256 per GPU (random-init weights, synthetic N(0,1)
+images). `value` is whole-job img/s with inputs resident in HBM; `e2e` is the same metric through the
+public API (create_model(...)(x)) with pinned-host inputs uploaded and logits downloaded every step.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port of
+fastervit/models/faster_vit.py — the Python reference cannot travel to the GPU box) on the host cores.
+Under torchrun (N > 1) every rank runs an independent replica on its own batch (the forward path has
+no exchange step; weak scaling) and the time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (entrypoint, create kwargs, per-GPU batch, resolution (H, W), mode)
+    "fv0_fwd": ("faster_vit_0_224", {}, 256, (224, 224), "fwd"),
+    "fv4_fwd": ("faster_vit_4_224", {}, 128, (224, 224), "fwd"),
+    "ar0_fwd": ("faster_vit_0_any_res", dict(resolution=[576, 960], window_size=[7, 7, 12, 6], ct_size=2, dim=64),
+                32, (576, 960), "fwd"),
+}
+ORACLE_CASE = {"fv0_fwd": "fv0", "fv4_fwd": "fv4", "ar0_fwd": "ar0"}
+# algorithmic forward GFLOP per image (measured on the reference with FlopCounterMode)
+ALG_GFLOP_FWD = {"fv0_fwd": 6.7237, "fv4_fwd": 85.3574, "ar0_fwd": 73.0828}
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tensor=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="measured")
+    return dict(tensor=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float = 20.0) -> dict:
+    """Time the CPU port of the reference path (oracle) with all host threads on a bounded sample."""
+    from oracle import fastervit_oracle as O
+    from oracle.configs import cfg_of
+    import fastervit_b200 as F
+    entry, kwargs, _, hw, _ = WORKLOADS[workload]
+    cfg = cfg_of(ORACLE_CASE[workload])
+    torch.manual_seed(0)
+    model = F.create_model(entry, drop_path_rate=0.0, **kwargs).eval()  # parameter container only
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = {"fv0_fwd": 16, "fv4_fwd": 4, "ar0_fwd": 2}[workload]
+    x = O.synth_input(bs, hw, 1)
+    with torch.no_grad():
+        for _ in range(max(1, warmup)):
+            O.forward(sd, cfg, x)
+        t0 = time.perf_counter()
+        n = 0
+        while n < steps and (n == 0 or time.perf_counter() - t0 < budget_s):
+            O.forward(sd, cfg, x)
+            n += 1
+        dt = time.perf_counter() - t0
+    return dict(value=bs * n / dt, unit="img/s", cores=cores, kind="port",
+                sample=f"{entry} eval forward (oracle port of the reference nn.Modules, fp32 torch CPU ops), "
+                       f"batch {bs} x {n} iterations in {dt:.1f}s, {cores} threads",
+                ms_per_step=1e3 * dt / n, steps_done=n, batch=bs)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="fv0_fwd", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-launch timing table (JSON) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    entry, kwargs, batch, hw, mode = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    config = {"workload": f"{entry} forward-only (eval), batch {batch}/GPU, 3x{hw[0]}x{hw[1]} synthetic N(0,1), "
+                          "random-init weights", "global_batch": batch * world, "parallelism": f"dp{world} replicas",
+              "l2": "inputs larger than L2 (rotating device batches; no explicit flush)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_rate(args.workload, args.steps, args.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": "images/sec", "value": r["value"], "unit": "img/s",
+                "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference)")
+    import fastervit_b200 as F
+    from fastervit_b200 import lib as L
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = F.create_model(entry, **kwargs).to(dev).eval()
+    nbuf = 2
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    xs = [torch.randn(batch, 3, hw[0], hw[1], device=dev, generator=g) for _ in range(nbuf)]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(xs[i % nbuf])
+        sync_all()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        L.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            out = model(xs[i % nbuf])
+        e1.record()
+        sync_all()
+        launches = L.launch_count()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = batch * world * args.steps / (ms_total / 1e3)
+
+    # ------------------------------------------------------------------ end to end (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        host_in = [torch.randn(batch, 3, hw[0], hw[1]).pin_memory() for _ in range(2)]
+        host_out = torch.empty(batch, model.num_classes).pin_memory()
+        dev_in = [torch.empty(batch, 3, hw[0], hw[1], device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        steps_e = max(3, min(args.steps, 10))
+
+        def e2e_loop(n):
+            # prefetch on a side stream (what timm's PrefetchLoader does for train.py / validate.py),
+            # forward on the current stream, logits back to pinned host memory every step
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            with torch.cuda.stream(copy_stream):
+                dev_in[0].copy_(host_in[0], non_blocking=True)
+                ready[0].record(copy_stream)
+            for i in range(n):
+                cur, nxt = i % 2, (i + 1) % 2
+                if i + 1 < n:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(done[nxt])
+                        dev_in[nxt].copy_(host_in[nxt], non_blocking=True)
+                        ready[nxt].record(copy_stream)
+                torch.cuda.current_stream().wait_event(ready[cur])
+                logits = model(dev_in[cur])
+                done[cur].record()
+                host_out.copy_(logits, non_blocking=True)
+            torch.cuda.synchronize()
+
+        with torch.no_grad():
+            e2e_loop(2)
+            sync_all()
+            t0 = time.perf_counter()
+            e2e_loop(steps_e)
+            dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": batch * world * steps_e / t.item(), "unit": "img/s",
+               "h2d_bytes_per_step": batch * 3 * hw[0] * hw[1] * 4, "d2h_bytes_per_step": batch * model.num_classes * 4,
+               "steps": steps_e, "note": "pinned host input uploaded on a prefetch stream, logits copied back, wall clock"}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    pk = peaks()
+    roofline = None
+    prof_table = None
+    if rank == 0:
+        plan = next(iter(model._engine.plans.values()))
+        with torch.no_grad():
+            plan.profile(xs[0])
+            prof = plan.profile(xs[1])
+        by = {}
+        for r in prof:
+            d = by.setdefault(r["name"], dict(ms=0.0, n=0, flops=0.0))
+            d["ms"] += r["ms"]
+            d["n"] += 1
+            d["flops"] += r["flops"]
+        tot = sum(d["ms"] for d in by.values())
+        gm = by.get("fvit_gemm")
+        prof_table = {k: dict(ms=round(v["ms"], 4), launches=v["n"], share=round(v["ms"] / tot, 4),
+                              gflop=round(v["flops"] / 1e9, 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
+        if gm:
+            ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
+            roofline = {"kernel": "gemm_tcgen05_kernel (fvit_gemm: conv taps + linear layers)", "bound": "tensor",
+                        "achieved": round(ach, 2), "peak": pk["tensor"], "unit": "TFLOP/s",
+                        "frac": round(ach / pk["tensor"], 4), "traffic": None,
+                        "peak_source": f"{pk['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
+                        "launches_per_step": gm["n"], "avg_launch_ms": round(gm["ms"] / gm["n"], 5),
+                        "alg_gflop_per_launch": round(gm["flops"] / gm["n"] / 1e9, 3),
+                        "share_of_step": round(gm["ms"] / tot, 4)}
+        if args.profile_out:
+            Path(args.profile_out).write_text(json.dumps({"per_kernel": prof_table, "launches": prof}, indent=1))
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1)
+    cpu = None
+    if rank == 0 and world == 1:
+        cpu = cpu_reference_rate(args.workload, steps=1000, warmup=1, budget_s=15.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        alg = ALG_GFLOP_FWD[args.workload] * 1e9
+        line = {"metric": "images/sec", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp16 operands, fp32 accumulate / residual / statistics", "data": "synthetic",
+                "config": config, "e2e": e2e, "gpu_launches": int(launches),
+                "launches_per_step": launches / args.steps, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "per_kernel": prof_table,
+                "model_tflops": round(value * alg / 1e12, 2),
+                "model_frac_of_tensor_peak": round(value / world * alg / 1e12 / pk["tensor"], 4)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

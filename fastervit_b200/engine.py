@@ -79,6 +79,7 @@ class Plan:
         self.ops: list[tuple] = []        # the forward pass
         self._gemm_keep: list = []        # keeps ctypes structs alive
         self._x_args: list = []           # stem-conv calls that take the input pointer at run time
+        self.op_flops: dict[int, float] = {}  # op index -> algorithmic FLOPs (GEMM launches)
         self._build()
 
     # ---- op emitters --------------------------------------------------------------------------
@@ -88,7 +89,9 @@ class Plan:
     def _gemm(self, *, a, a_rows, lda, b, ldb, m, n, kc, taps=None, a_planes=1, a_plane_stride=0,
               b_rows=0, col_scale=None, col_shift=None, col_scale2=None, act=L.ACT_NONE, resid=None,
               ld_resid=0, row_map=None, out_f32=None, ld_o32=0, out_f16=None, ld_o16=0,
-              col_sum=None, col_sumsq=None, alpha=1.0, tile_n=0) -> None:
+              col_sum=None, col_sumsq=None, alpha=1.0, tile_n=0, m_alg=None) -> None:
+        """Emit one fvit_gemm launch. m_alg = number of output rows that are real work (pixels / tokens,
+        without layout padding) for the algorithmic FLOP count 2*m_alg*n*kc*ntaps."""
         g = L.GemmArgs()
         g.a, g.a_rows, g.lda, g.a_plane_stride, g.a_planes = a, a_rows, lda, a_plane_stride, a_planes
         g.b, g.b_rows, g.ldb = b, b_rows or n, ldb
@@ -104,6 +107,7 @@ class Plan:
         g.col_sum, g.col_sumsq = col_sum, col_sumsq
         self._gemm_keep.append(g)
         self.ops.append((self.lib.fvit_gemm, (C.byref(g),), "fvit_gemm"))
+        self.op_flops[len(self.ops) - 1] = 2.0 * (m_alg if m_alg is not None else m) * n * kc * len(taps)
 
     # ---- weight preparation emitters ------------------------------------------------------------
     def _pack_linear(self, name: str, lin: nn.Linear) -> tuple[torch.Tensor, int]:
@@ -165,6 +169,7 @@ class Plan:
         self._gemm(a=stem_planes.data_ptr(), a_rows=pl_rows, lda=ld_in, a_planes=4,
                    a_plane_stride=pl_rows * ld_in, b=w16.data_ptr(), ldb=ldw, m=pl_rows, n=dim, kc=in_dim,
                    taps=self._s2_taps(W0), col_scale=s2.data_ptr(), col_shift=t2.data_ptr(), act=L.ACT_RELU,
+                   m_alg=B * H0 * W0,
                    row_map=self._plane_to_padded_map("stem.to_l0", B, H0, W0).data_ptr(),
                    out_f32=lvl["x32"].data_ptr(), ld_o32=lvl["C"], out_f16=lvl["x16"].data_ptr(),
                    ld_o16=lvl["ld"])
@@ -249,12 +254,12 @@ class Plan:
             # h = GELU(BN(conv1(x)))                                        (fv.py:504-506)
             self._gemm(a=lv["x16"].data_ptr(), a_rows=lv["rows"], lda=lv["ld"], b=w1.data_ptr(), ldb=ld1,
                        m=lv["rows"], n=Cc, kc=Cc, taps=taps, col_scale=s1.data_ptr(), col_shift=t1.data_ptr(),
-                       act=L.ACT_GELU, row_map=lv["interior"].data_ptr(), out_f16=lv["h16"].data_ptr(),
+                       m_alg=self.B * lv["H"] * lv["W"], act=L.ACT_GELU, row_map=lv["interior"].data_ptr(), out_f16=lv["h16"].data_ptr(),
                        ld_o16=lv["ld"])
             # x = x + gamma * BN(conv2(h))                                   (fv.py:507-511)
             self._gemm(a=lv["h16"].data_ptr(), a_rows=lv["rows"], lda=lv["ld"], b=w2.data_ptr(), ldb=ld2,
                        m=lv["rows"], n=Cc, kc=Cc, taps=taps, col_scale=s2.data_ptr(), col_shift=t2.data_ptr(),
-                       resid=lv["x32"].data_ptr(), ld_resid=Cc, row_map=lv["interior"].data_ptr(),
+                       m_alg=self.B * lv["H"] * lv["W"], resid=lv["x32"].data_ptr(), ld_resid=Cc, row_map=lv["interior"].data_ptr(),
                        out_f32=lv["x32"].data_ptr(), ld_o32=Cc, out_f16=lv["x16"].data_ptr(), ld_o16=lv["ld"])
 
     def _emit_downsample_conv(self, i: int, src: dict, dst: dict, to_conv: bool) -> None:
@@ -280,7 +285,7 @@ class Plan:
             rmap = self._plane_to_padded_map(f"ds{i}.rmap", B, Ho, Wo)
             self._gemm(a=planes.data_ptr(), a_rows=pl_rows, lda=ld, a_planes=4, a_plane_stride=pl_rows * ld,
                        b=w16.data_ptr(), ldb=ldw, m=pl_rows, n=2 * Cs, kc=Cs, taps=self._s2_taps(Wo),
-                       row_map=rmap.data_ptr(), out_f32=dst["x32"].data_ptr(), ld_o32=dst["C"],
+                       m_alg=B * Ho * Wo, row_map=rmap.data_ptr(), out_f32=dst["x32"].data_ptr(), ld_o32=dst["C"],
                        out_f16=dst["x16"].data_ptr(), ld_o16=dst["ld"])
         else:
             # plane-space row (b, a+1, c+1) -> token row of pixel (a, c) in the window-major buffer
@@ -290,7 +295,7 @@ class Plan:
             rmap = nb.i32(f"ds{i}.rmap", full.reshape(-1))
             self._gemm(a=planes.data_ptr(), a_rows=pl_rows, lda=ld, a_planes=4, a_plane_stride=pl_rows * ld,
                        b=w16.data_ptr(), ldb=ldw, m=pl_rows, n=2 * Cs, kc=Cs, taps=self._s2_taps(Wo),
-                       row_map=rmap.data_ptr(), out_f32=dst["xs"].data_ptr(), ld_o32=dst["C"])
+                       m_alg=B * Ho * Wo, row_map=rmap.data_ptr(), out_f32=dst["xs"].data_ptr(), ld_o32=dst["C"])
 
     # ---- transformer levels -----------------------------------------------------------------------
     def _token_level_buffers(self, i: int, level, Cc: int, Hc: int, Wc: int) -> dict:
@@ -495,6 +500,22 @@ class Plan:
                 rc = fn(*args, st)
             if rc != 0:
                 raise L.FvitError(f"{name}: {lib.fvit_last_error().decode()}")
+
+
+    def profile(self, x: torch.Tensor) -> list[dict]:
+        """Time every launch of one forward with CUDA events on the current stream (the GPU is kept busy
+        by a spin kernel while the launches are enqueued, so the intervals are back-to-back device
+        time, not host enqueue latency). Returns [{name, ms, flops}] in launch order."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(4e8))
+        evs[0].record()
+        for i, op in enumerate(self.ops):
+            self.run_ops([op], x)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        return [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=self.op_flops.get(i, 0.0))
+                for i, op in enumerate(self.ops)]
 
 
 class Engine:

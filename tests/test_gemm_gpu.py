@@ -168,7 +168,8 @@ def test_gemm_conv3x3_taps(cin, cout, hw):
     out = torch.zeros(bsz * Hp * Wp, cout, device="cuda")
     lib.gemm(a, wp.view(cout, 9 * kc_pad), kc=cin, taps=taps, out_f32=out)
     got = out.view(bsz, Hp, Wp, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
-    ref = torch.nn.functional.conv2d(x.float(), w.float(), padding=1)
+    # CPU reference: keeps cuDNN (slow to cold-load on a fresh box) out of the test
+    ref = torch.nn.functional.conv2d(x.float().cpu(), w.float().cpu(), padding=1).cuda()
     assert _rel(got, ref) < 2e-5
 
 
@@ -198,7 +199,7 @@ def test_gemm_planes_stride2_conv():
     out = torch.zeros(rows, cout, device="cuda")
     lib.gemm(a, wp, m=rows, kc=cin, taps=taps, a_planes=4, out_f32=out)
     got = out.view(bsz, Ho + 1, Wo + 1, cout)[:, 1:, 1:].permute(0, 3, 1, 2)
-    ref = torch.nn.functional.conv2d(x.float(), w.float(), stride=2, padding=1)
+    ref = torch.nn.functional.conv2d(x.float().cpu(), w.float().cpu(), stride=2, padding=1).cuda()
     assert _rel(got, ref) < 2e-5
 
 
