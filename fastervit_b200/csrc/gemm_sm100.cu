@@ -36,6 +36,8 @@ constexpr int ACC_STRIDE = 256;  // TMEM column stride between the two accumulat
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem base, placed after the stage ring
 constexpr int SMEM_ALIGN_SLACK = 1024;
+constexpr int STG_LD = 36;  // floats per staging row: 32 + 4 pad -> conflict-free float4 access both ways
+constexpr int SMEM_STG_BYTES = 4 * 32 * STG_LD * 4;  // one 32x32 fp32 staging tile per epilogue warp
 
 struct GemmParams {
   int m, n;
@@ -91,6 +93,27 @@ __device__ __forceinline__ uint32_t pack2_16(float a, float b, int bf16) {
   }
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ float4 ld_vec4_guard(const float* p, int valid, float fill) {
+  if (valid >= 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(fill, fill, fill, fill);
+  if (valid > 0) r.x = __ldg(p);
+  if (valid > 1) r.y = __ldg(p + 1);
+  if (valid > 2) r.z = __ldg(p + 2);
+  if (valid > 3) r.w = __ldg(p + 3);
+  return r;
+}
+__device__ __forceinline__ void unpack4_16(uint2 pk, int bf16, float (&a)[4]) {
+  if (bf16) {
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+    a[0] = __low2float(lo), a[1] = __high2float(lo), a[2] = __low2float(hi), a[3] = __high2float(hi);
+  } else {
+    const __half2 lo = *reinterpret_cast<const __half2*>(&pk.x);
+    const __half2 hi = *reinterpret_cast<const __half2*>(&pk.y);
+    a[0] = __low2float(lo), a[1] = __high2float(lo), a[2] = __low2float(hi), a[3] = __high2float(hi);
+  }
 }
 
 // Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving).
@@ -244,152 +267,168 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ===================================================================== epilogue warps
+    // Each warp owns one 32-lane TMEM quadrant (32 rows of the tile). Per 32-column chunk it pulls the
+    // accumulators row-per-thread with tcgen05.ld, transposes them through a padded shared-memory
+    // staging tile and then works "coalesced": one instruction covers 4 rows x 128 contiguous bytes
+    // (8 lanes x float4 per row), so residual loads and fp32 / fp16 stores are full-line accesses.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    float* stg = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES) + quad * (32 * STG_LD);
+    const int sub = lane >> 3;   // row within a 4-row group
+    const int c4 = lane & 7;     // which float4 of the 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool splitk = p.atomic_out != 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int t = w / p.split_k;
       const int tn = t % p.tiles_n;
       const int tm = t / p.tiles_n;
-      const int row = tm * BM + quad * 32 + lane;
+      const int row_base = tm * BM + quad * 32;
       const int n0 = tn * p.tile_n;
-      long long orow = -1;
-      if (row < p.m) orow = p.row_map ? (long long)p.row_map[row] : (long long)row;
-      const bool valid = orow >= 0;
+      const int n_end = min(p.n, n0 + p.tile_n);
+      // output row of tile row (row_base + lane); other rows are fetched by shuffle
+      long long my_orow = -1;
+      if (row_base + lane < p.m)
+        my_orow = p.row_map ? (long long)p.row_map[row_base + lane] : (long long)(row_base + lane);
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
 
-      for (int c0 = 0; c0 < p.tile_n; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c0, raw);
-        tmem_ld_wait();
+      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
         const int nbase = n0 + c0;
-        if (nbase >= p.n) continue;  // warp-uniform
-        const bool full16 = nbase + 16 <= p.n;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-
-        if (splitk) {
-          if (valid) {
-            float* o = p.out_f32 + orow * p.ld_o32 + nbase;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nbase + i < p.n) atomicAdd(o + i, v[i]);
-          }
-          __syncwarp();
-          continue;
-        }
-
-        if (p.col_scale) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full16 || nbase + i < p.n) v[i] *= __ldg(p.col_scale + nbase + i);
-        }
-        if (p.col_shift) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full16 || nbase + i < p.n) v[i] += __ldg(p.col_shift + nbase + i);
-        }
-        if (p.col_sum) {
-          float s1[16], s2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x = valid ? v[i] : 0.f;
-            s1[i] = x;
-            s2[i] = x * x;
-          }
-          warp_colsum16(s1, lane);
-          warp_colsum16(s2, lane);
-          if ((lane & 1) == 0) {
-            const int c = nbase + colsum16_owner_col(lane);
-            if (c < p.n) {
-              atomicAdd(p.col_sum + c, s1[0]);
-              atomicAdd(p.col_sumsq + c, s2[0]);
-            }
-          }
-        }
-        if (valid) {  // lane-divergent region: no warp-collective ops inside
-        if (p.act == FVIT_ACT_RELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else if (p.act == FVIT_ACT_GELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-        } else if (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) {
-          const long long abase = (long long)row * p.ld_aux + nbase;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (full16 || nbase + i < p.n) {
-              const float a = load16_as_float(p.aux, abase + i, p.bf16);
-              v[i] *= (p.act == FVIT_ACT_GELU_BWD) ? gelu_erf_grad(a) : (a > 0.f ? 1.f : 0.f);
-            }
-          }
-        }
-        if (p.col_scale2) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full16 || nbase + i < p.n) v[i] *= __ldg(p.col_scale2 + nbase + i);
-        }
-        if (p.resid) {
-          const float* r = p.resid + orow * p.ld_resid + nbase;
-          if (full16 && p.vec_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 rv = *reinterpret_cast<const float4*>(r + 4 * q);
-              v[4 * q + 0] += rv.x;
-              v[4 * q + 1] += rv.y;
-              v[4 * q + 2] += rv.z;
-              v[4 * q + 3] += rv.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nbase + i < p.n) v[i] += r[i];
-          }
-        }
-        if (p.out_f32) {
-          float* o = p.out_f32 + orow * p.ld_o32 + nbase;
-          if (full16 && p.vec_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(o + 4 * q) =
-                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nbase + i < p.n) o[i] = v[i];
-          }
-        }
-        if (p.out_f16) {
-          uint16_t* o = reinterpret_cast<uint16_t*>(p.out_f16) + orow * p.ld_o16 + nbase;
-          if (full16 && p.vec_ok) {
-            uint4 w0, w1;
-            w0.x = pack2_16(v[0], v[1], p.bf16);
-            w0.y = pack2_16(v[2], v[3], p.bf16);
-            w0.z = pack2_16(v[4], v[5], p.bf16);
-            w0.w = pack2_16(v[6], v[7], p.bf16);
-            w1.x = pack2_16(v[8], v[9], p.bf16);
-            w1.y = pack2_16(v[10], v[11], p.bf16);
-            w1.z = pack2_16(v[12], v[13], p.bf16);
-            w1.w = pack2_16(v[14], v[15], p.bf16);
-            *reinterpret_cast<uint4*>(o) = w0;
-            *reinterpret_cast<uint4*>(o + 8) = w1;
-          } else {
+        if (nbase >= p.n) break;  // warp-uniform
+        {
+          uint32_t raw[32];
+          if (c0 + 32 <= p.tile_n) {
+            tmem_ld32(taddr + c0, raw);
+          } else {  // tile_n is a multiple of 16: last half chunk
+            uint32_t lo[16];
+            tmem_ld16(taddr + c0, lo);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              if (nbase + i < p.n) {
-                const uint32_t pk = pack2_16(v[i], 0.f, p.bf16);
-                o[i] = (uint16_t)(pk & 0xFFFF);
-              }
+              raw[i] = lo[i];
+              raw[16 + i] = 0u;
+            }
+          }
+          tmem_ld_wait();
+          float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            srow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                  __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+        }
+        __syncwarp();
+        const int col = nbase + 4 * c4;            // first of this lane's 4 columns
+        const bool cfull = col + 4 <= n_end;        // all 4 columns valid
+        const bool cany = col < n_end;
+        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f),
+               cs2 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (cany) {
+          if (p.col_scale) cs = ld_vec4_guard(p.col_scale + col, n_end - col, 1.f);
+          if (p.col_shift) sh = ld_vec4_guard(p.col_shift + col, n_end - col, 0.f);
+          if (p.col_scale2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
+        }
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int k = 0; k < 8; ++k) {
+          const int rl = 4 * k + sub;  // row within the warp's 32
+          const long long orow = __shfl_sync(0xffffffffu, my_orow, rl);
+          const bool ok = cany && orow >= 0;
+          float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + 4 * c4);
+          v.x *= p.alpha, v.y *= p.alpha, v.z *= p.alpha, v.w *= p.alpha;
+          if (p.atomic_out) {
+            if (ok) {
+              float* o = p.out_f32 + orow * p.ld_o32 + col;
+              atomicAdd(o, v.x);
+              if (col + 1 < n_end) atomicAdd(o + 1, v.y);
+              if (col + 2 < n_end) atomicAdd(o + 2, v.z);
+              if (col + 3 < n_end) atomicAdd(o + 3, v.w);
+            }
+            continue;
+          }
+          v.x = fmaf(v.x, cs.x, sh.x), v.y = fmaf(v.y, cs.y, sh.y), v.z = fmaf(v.z, cs.z, sh.z),
+          v.w = fmaf(v.w, cs.w, sh.w);
+          if (p.col_sum && ok) {
+            s1.x += v.x, s1.y += v.y, s1.z += v.z, s1.w += v.w;
+            s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
+          }
+          if (!ok) continue;  // no warp-collective ops below this point inside the k loop
+          if (p.act == FVIT_ACT_RELU) {
+            v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+          } else if (p.act == FVIT_ACT_GELU) {
+            v.x = gelu_erf(v.x), v.y = gelu_erf(v.y), v.z = gelu_erf(v.z), v.w = gelu_erf(v.w);
+          } else if (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) {
+            const long long ab = (long long)(row_base + rl) * p.ld_aux + col;
+            float a[4];
+            if (cfull && p.vec_ok) {
+              const uint2 pk = *reinterpret_cast<const uint2*>(
+                  reinterpret_cast<const uint16_t*>(p.aux) + ab);
+              unpack4_16(pk, p.bf16, a);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a[i] = col + i < n_end ? load16_as_float(p.aux, ab + i, p.bf16) : 0.f;
+            }
+            if (p.act == FVIT_ACT_GELU_BWD) {
+              v.x *= gelu_erf_grad(a[0]), v.y *= gelu_erf_grad(a[1]), v.z *= gelu_erf_grad(a[2]),
+              v.w *= gelu_erf_grad(a[3]);
+            } else {
+              v.x = a[0] > 0.f ? v.x : 0.f, v.y = a[1] > 0.f ? v.y : 0.f, v.z = a[2] > 0.f ? v.z : 0.f,
+              v.w = a[3] > 0.f ? v.w : 0.f;
+            }
+          }
+          v.x *= cs2.x, v.y *= cs2.y, v.z *= cs2.z, v.w *= cs2.w;
+          if (p.resid) {
+            const float* r = p.resid + orow * p.ld_resid + col;
+            if (cfull && p.vec_ok) {
+              const float4 rv = *reinterpret_cast<const float4*>(r);
+              v.x += rv.x, v.y += rv.y, v.z += rv.z, v.w += rv.w;
+            } else {
+              v.x += r[0];
+              if (col + 1 < n_end) v.y += r[1];
+              if (col + 2 < n_end) v.z += r[2];
+              if (col + 3 < n_end) v.w += r[3];
+            }
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + orow * p.ld_o32 + col;
+            if (cfull && p.vec_ok) {
+              *reinterpret_cast<float4*>(o) = v;
+            } else {
+              o[0] = v.x;
+              if (col + 1 < n_end) o[1] = v.y;
+              if (col + 2 < n_end) o[2] = v.z;
+              if (col + 3 < n_end) o[3] = v.w;
+            }
+          }
+          if (p.out_f16) {
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out_f16) + orow * p.ld_o16 + col;
+            const uint32_t lo = pack2_16(v.x, v.y, p.bf16), hi = pack2_16(v.z, v.w, p.bf16);
+            if (cfull && p.vec_ok) {
+              *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
+            } else {
+              o[0] = (uint16_t)(lo & 0xFFFF);
+              if (col + 1 < n_end) o[1] = (uint16_t)(lo >> 16);
+              if (col + 2 < n_end) o[2] = (uint16_t)(hi & 0xFFFF);
+              if (col + 3 < n_end) o[3] = (uint16_t)(hi >> 16);
             }
           }
         }
-        }  // valid
-        __syncwarp();  // reconverge before the next .sync.aligned TMEM load
+        __syncwarp();
+        if (p.col_sum && !p.atomic_out) {
+          // lanes sharing c4 (lane, lane^8, lane^16, lane^24) hold partial sums of the same 4 columns
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o), s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o), s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o), s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o), s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+          }
+          if (sub == 0 && cany) {
+            atomicAdd(p.col_sum + col, s1.x), atomicAdd(p.col_sumsq + col, s2.x);
+            if (col + 1 < n_end) atomicAdd(p.col_sum + col + 1, s1.y), atomicAdd(p.col_sumsq + col + 1, s2.y);
+            if (col + 2 < n_end) atomicAdd(p.col_sum + col + 2, s1.z), atomicAdd(p.col_sumsq + col + 2, s2.z);
+            if (col + 3 < n_end) atomicAdd(p.col_sum + col + 3, s1.w), atomicAdd(p.col_sumsq + col + 3, s2.w);
+          }
+        }
       }
       // hand the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -517,7 +556,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (p.split_k < 1) p.split_k = 1;
   p.atomic_out = split_k > 1 ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + tile_n * BK * 2;
-  int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK) / stage_bytes;
+  int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK - SMEM_STG_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   FVIT_CHECK(stages >= 2, "fvit_gemm: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -551,6 +590,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
     vec = vec && (a->ld_out_f16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->out_f16) & 15) == 0);
   if (a->resid)
     vec = vec && (a->ld_resid % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->resid) & 15) == 0);
+  if (a->aux)
+    vec = vec && (a->ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->aux) & 7) == 0);
   p.vec_ok = vec ? 1 : 0;
   CUtensorMap tma, tmb;
   int rc;
@@ -574,7 +615,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   }
   if (rc) return rc;
 
-  const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK;
+  const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
     FVIT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

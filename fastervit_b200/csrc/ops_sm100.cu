@@ -77,25 +77,35 @@ __global__ void affine_fold_kernel(float* __restrict__ scale, float* __restrict_
 // ------------------------------------------------------------------------------ stem conv 3x3 s2
 // x fp32 [B,3,H,W] (arbitrary strides) -> y = relu(conv(x) * scale + shift) as fp16 rows of `cout`
 // channels written at out_row_map[b*Ho*Wo + oh*Wo + ow] (the parity-plane layout conv2 consumes).
-// One thread per (pixel, 8 output channels); weights [cout][27] live in shared memory.
+// One thread per (pixel, 16 output channels): the 27 taps sit in registers, weights are read from
+// shared memory as [27][cout] float4 broadcasts (one LDS.128 per 4 FMAs), and the cout/16 threads
+// of a pixel write one contiguous 2*cout-byte row. fp32 math (K = 27 is too thin for tensor cores;
+// the kernel is HBM/LSU bound: 3*H*W*4 B in, cout*H*W/2 B out per image).
 template <int CIN>
-__global__ void stem_conv_kernel(const float* __restrict__ x, long long sb, long long sc, long long sh,
-                                 long long sw, int B, int H, int W, const float* __restrict__ wgt,
-                                 int cout, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, int relu,
-                                 const int* __restrict__ out_row_map, __half* __restrict__ out,
-                                 long long ldo, float* __restrict__ col_sum,
-                                 float* __restrict__ col_sumsq) {
-  extern __shared__ float sw_[];  // [cout][CIN*9]
-  const int K = CIN * 9;
-  for (int i = threadIdx.x; i < cout * K; i += blockDim.x) sw_[i] = wgt[i];
+__global__ void __launch_bounds__(256)
+    stem_conv_kernel(const float* __restrict__ x, long long sb, long long sc, long long sh, long long sw,
+                     int B, int H, int W, const float* __restrict__ wgt, int cout,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                     const int* __restrict__ out_row_map, __half* __restrict__ out, long long ldo,
+                     float* __restrict__ col_sum, float* __restrict__ col_sumsq) {
+  extern __shared__ float sw_[];  // [CIN*9][cout] then (statistics) [2][cout]
+  constexpr int K = CIN * 9;
+  for (int i = threadIdx.x; i < cout * K; i += blockDim.x) {
+    const int co = i / K, k = i % K;
+    sw_[k * cout + co] = wgt[i];
+  }
+  float* red = sw_ + K * cout;
+  if (col_sum)
+    for (int i = threadIdx.x; i < 2 * cout; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const int groups = cout / 8;
+  const int groups = cout / 16;
   const long long total = (long long)B * Ho * Wo * groups;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool active = i < total;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   int g = 0;
   long long pix = 0;
   if (active) {
@@ -104,7 +114,7 @@ __global__ void stem_conv_kernel(const float* __restrict__ x, long long sb, long
     const int ow = (int)(pix % Wo);
     const int oh = (int)((pix / Wo) % Ho);
     const int b = (int)(pix / ((long long)Wo * Ho));
-    float in[CIN * 9];
+    float in[K];
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
 #pragma unroll
@@ -113,53 +123,57 @@ __global__ void stem_conv_kernel(const float* __restrict__ x, long long sb, long
         for (int s = 0; s < 3; ++s) {
           const int ih = 2 * oh + r - 1, iw = 2 * ow + s - 1;
           in[c * 9 + r * 3 + s] =
-              (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[b * sb + c * sc + ih * sh + iw * sw] : 0.f;
+              (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + b * sb + c * sc + ih * sh + iw * sw) : 0.f;
         }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float* wr = sw_ + (g * 8 + j) * K;
-      float a = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(sw_ + k * cout + g * 16);
 #pragma unroll
-      for (int k = 0; k < CIN * 9; ++k) a = fmaf(in[k], wr[k], a);
-      acc[j] = a;
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = wr[q];
+        acc[4 * q + 0] = fmaf(in[k], w4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(in[k], w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(in[k], w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(in[k], w4.w, acc[4 * q + 3]);
+      }
     }
   }
   if (col_sum) {
     // train-mode BatchNorm statistics of the raw conv output: block-level reduction, then atomics
-    __shared__ float red[2][64];  // cout <= 64 per pass handled by groups*8 columns
-    for (int j = threadIdx.x; j < 2 * 64; j += blockDim.x) (&red[0][0])[j] = 0.f;
-    __syncthreads();
     if (active) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[0][(g * 8 + j) & 63], acc[j]);
-        atomicAdd(&red[1][(g * 8 + j) & 63], acc[j] * acc[j]);
+      for (int j = 0; j < 16; ++j) {
+        atomicAdd(&red[g * 16 + j], acc[j]);
+        atomicAdd(&red[cout + g * 16 + j], acc[j] * acc[j]);
       }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < cout && j < 64; j += blockDim.x) {
-      atomicAdd(col_sum + j, red[0][j]);
-      atomicAdd(col_sumsq + j, red[1][j]);
+    for (int j = threadIdx.x; j < cout; j += blockDim.x) {
+      atomicAdd(col_sum + j, red[j]);
+      atomicAdd(col_sumsq + j, red[cout + j]);
     }
   }
   if (active && out) {
     const int orow = out_row_map ? out_row_map[pix] : (int)pix;
     if (orow >= 0) {
-      __half2 h[4];
+      uint32_t pk[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         float v0 = acc[2 * j], v1 = acc[2 * j + 1];
         if (scale) {
-          v0 = v0 * scale[g * 8 + 2 * j] + shift[g * 8 + 2 * j];
-          v1 = v1 * scale[g * 8 + 2 * j + 1] + shift[g * 8 + 2 * j + 1];
+          v0 = fmaf(v0, __ldg(scale + g * 16 + 2 * j), __ldg(shift + g * 16 + 2 * j));
+          v1 = fmaf(v1, __ldg(scale + g * 16 + 2 * j + 1), __ldg(shift + g * 16 + 2 * j + 1));
         }
         if (relu) {
           v0 = fmaxf(v0, 0.f);
           v1 = fmaxf(v1, 0.f);
         }
-        h[j] = __floats2half2_rn(v0, v1);
+        const __half2 h = __floats2half2_rn(v0, v1);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
       }
-      *reinterpret_cast<uint4*>(out + (long long)orow * ldo + g * 8) = *reinterpret_cast<uint4*>(h);
+      uint4* o = reinterpret_cast<uint4*>(out + (long long)orow * ldo + g * 16);
+      o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
   }
 }
@@ -169,30 +183,34 @@ __global__ void stem_conv_kernel(const float* __restrict__ x, long long sb, long
 // optionally written back as fp32 to wb[r]; y = (v - mean) * rstd * gamma + beta written as fp16 to
 // out[out_map ? out_map[r] : r]. Two-pass statistics in registers (biased variance, like
 // F.layer_norm). Saves mean / rstd when requested (backward).
-constexpr int LN_MAX_VEC = 13;  // C <= 32 * 4 * 13 = 1664
-__global__ void ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ in_map,
-                              int rows, int C, const float* __restrict__ add, int group, int skip,
-                              float* __restrict__ wb, long long ldwb, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float eps, __half* __restrict__ out,
-                              long long ldo, const int* __restrict__ out_map,
-                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int warps_per_block = blockDim.x >> 5;
+// LPR lanes cooperate on one row (32 / LPR rows per warp), each lane holding up to MAXV float4.
+template <int LPR, int MAXV>
+__global__ void __launch_bounds__(256)
+    ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ in_map, int rows,
+                  int C, const float* __restrict__ add, int group, int skip, float* __restrict__ wb,
+                  long long ldwb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, __half* __restrict__ out, long long ldo, const int* __restrict__ out_map,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
+  const int sl = lane % LPR;     // lane within the row group
   const int nvec = C >> 2;
-  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows;
-       r += gridDim.x * warps_per_block) {
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long r = warp_global * RPW + lane / LPR;
+  const bool active = r < rows;
+  float4 v[MAXV];
+  float s = 0.f;
+  if (active) {
     const long long src = in_map ? in_map[r] : r;
     const float4* xr = reinterpret_cast<const float4*>(x + src * ldx);
     const float4* ar = nullptr;
     if (add) {
-      const int t = r % group;
+      const int t = (int)(r % group);
       if (t >= skip) ar = reinterpret_cast<const float4*>(add + (long long)(t - skip) * C);
     }
-    float4 v[LN_MAX_VEC];
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_VEC; ++j) {
-      const int i = lane + 32 * j;
+    for (int j = 0; j < MAXV; ++j) {
+      const int i = sl + LPR * j;
       if (i < nvec) {
         float4 t4 = xr[i];
         if (ar) {
@@ -203,48 +221,55 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, long long ldx, const 
         s += t4.x + t4.y + t4.z + t4.w;
       }
     }
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
+  }
 #pragma unroll
-    for (int j = 0; j < LN_MAX_VEC; ++j) {
-      const int i = lane + 32 * j;
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int i = sl + LPR * j;
       if (i < nvec) {
         const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
         q += a * a + b * b + c * c + d * d;
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
-    if (wb) {
-      float4* wr = reinterpret_cast<float4*>(wb + (long long)r * ldwb);
+  }
 #pragma unroll
-      for (int j = 0; j < LN_MAX_VEC; ++j) {
-        const int i = lane + 32 * j;
-        if (i < nvec) wr[i] = v[j];
-      }
-    }
-    if (mean_out && lane == 0) {
-      mean_out[r] = mean;
-      rstd_out[r] = rstd;
-    }
-    const long long orow = out_map ? out_map[r] : r;
-    if (orow >= 0) {
-      __half* o = out + orow * ldo;
-      const float4* g4 = reinterpret_cast<const float4*>(gamma);
-      const float4* b4 = reinterpret_cast<const float4*>(beta);
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (!active) return;
+  const float rstd = rsqrtf(q / C + eps);
+  if (wb) {
+    float4* wr = reinterpret_cast<float4*>(wb + r * ldwb);
 #pragma unroll
-      for (int j = 0; j < LN_MAX_VEC; ++j) {
-        const int i = lane + 32 * j;
-        if (i < nvec) {
-          const float4 g = g4[i], b = b4[i];
-          const __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g.x + b.x,
-                                               (v[j].y - mean) * rstd * g.y + b.y);
-          const __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g.z + b.z,
-                                               (v[j].w - mean) * rstd * g.w + b.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(o + 4 * i) = pk;
-        }
+    for (int j = 0; j < MAXV; ++j) {
+      const int i = sl + LPR * j;
+      if (i < nvec) wr[i] = v[j];
+    }
+  }
+  if (mean_out && sl == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+  }
+  const long long orow = out_map ? out_map[r] : r;
+  if (orow >= 0) {
+    __half* o = out + orow * ldo;
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int i = sl + LPR * j;
+      if (i < nvec) {
+        const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+        const __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g.x + b.x,
+                                             (v[j].y - mean) * rstd * g.y + b.y);
+        const __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g.z + b.z,
+                                             (v[j].w - mean) * rstd * g.w + b.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(o + 4 * i) = pk;
       }
     }
   }
@@ -500,14 +525,14 @@ int fvit_stem_conv_fwd(const float* x, int64_t sb, int64_t sc, int64_t sh, int64
                        void* out, int64_t ldo, float* col_sum, float* col_sumsq, void* stream) {
   FVIT_CHECK(x && wgt && B > 0 && H > 0 && W > 0, "fvit_stem_conv_fwd: bad arguments");
   FVIT_CHECK(cin == 3, "fvit_stem_conv_fwd: only in_chans == 3 is supported (got %d)", cin);
-  FVIT_CHECK(cout % 8 == 0 && cout <= 512, "fvit_stem_conv_fwd: cout=%d must be a multiple of 8", cout);
-  FVIT_CHECK(!col_sum || cout <= 64, "fvit_stem_conv_fwd: statistics need cout <= 64");
+  FVIT_CHECK(cout % 16 == 0 && cout <= 512, "fvit_stem_conv_fwd: cout=%d must be a multiple of 16", cout);
   FVIT_CHECK(!out || ldo % 8 == 0, "fvit_stem_conv_fwd: ldo must be a multiple of 8");
+  FVIT_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "fvit_stem_conv_fwd: statistics come in pairs");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long total = (long long)B * Ho * Wo * (cout / 8);
-  const int block = 128;
+  const long long total = (long long)B * Ho * Wo * (cout / 16);
+  const int block = 256;
   const long long grid = (total + block - 1) / block;
-  const size_t smem = (size_t)cout * 27 * sizeof(float);
+  const size_t smem = (size_t)cout * (27 + 2) * sizeof(float);
   if (smem > 48 * 1024)
     FVIT_CUDA(cudaFuncSetAttribute(stem_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
@@ -522,16 +547,27 @@ int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows
                 const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
                 const int32_t* out_map, float* mean_out, float* rstd_out, void* stream) {
   FVIT_CHECK(x && gamma && beta && out && rows > 0, "fvit_ln_fwd: bad arguments");
-  FVIT_CHECK(C % 4 == 0 && C <= 32 * 4 * LN_MAX_VEC, "fvit_ln_fwd: C=%d unsupported", C);
+  FVIT_CHECK(C % 4 == 0 && C <= 32 * 4 * 16, "fvit_ln_fwd: C=%d unsupported", C);
   FVIT_CHECK(ldx % 4 == 0 && ldo % 4 == 0 && (!wb || ldwb % 4 == 0), "fvit_ln_fwd: unaligned strides");
   FVIT_CHECK(!add || group > 0, "fvit_ln_fwd: add needs group > 0");
+  const int nvec = C / 4;
   const int block = 256, wpb = block / 32;
-  long long grid = ((long long)rows + wpb - 1) / wpb;
-  const long long cap = (long long)num_sms() * 8;
-  if (grid > cap) grid = cap;
-  ln_fwd_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(
-      x, ldx, in_map, rows, C, add, group > 0 ? group : 1, skip, wb, ldwb, gamma, beta, eps,
-      (__half*)out, ldo, out_map, mean_out, rstd_out);
+  const int grp = group > 0 ? group : 1;
+#define FVIT_LN_LAUNCH(LPR, MAXV)                                                                   \
+  do {                                                                                              \
+    const long long warps = ((long long)rows + (32 / LPR) - 1) / (32 / LPR);                        \
+    const long long grid = (warps + wpb - 1) / wpb;                                                 \
+    ln_fwd_kernel<LPR, MAXV><<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(                   \
+        x, ldx, in_map, rows, C, add, grp, skip, wb, ldwb, gamma, beta, eps, (__half*)out, ldo,     \
+        out_map, mean_out, rstd_out);                                                               \
+  } while (0)
+  if (nvec <= 16) FVIT_LN_LAUNCH(8, 2);
+  else if (nvec <= 32) FVIT_LN_LAUNCH(8, 4);
+  else if (nvec <= 64) FVIT_LN_LAUNCH(16, 4);
+  else if (nvec <= 128) FVIT_LN_LAUNCH(32, 4);
+  else if (nvec <= 256) FVIT_LN_LAUNCH(32, 8);
+  else FVIT_LN_LAUNCH(32, 16);
+#undef FVIT_LN_LAUNCH
   return post_launch("ln_fwd_kernel");
 }
 

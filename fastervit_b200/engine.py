@@ -185,6 +185,11 @@ class Plan:
                 prev = dict(kind="conv", **lvl)
             else:
                 tl = self._token_level_buffers(i, level, Cc, Hc, Wc)
+                if tl["padded"]:
+                    # window-padding pixels enter the level as zero tokens (fvar.py:853-855) and are
+                    # modified in place by the blocks, so they are re-zeroed every forward; all other
+                    # rows are fully overwritten by the downsample GEMM / tokenizer
+                    self.ops.append(("zero", tl["xs"], "memset"))
                 self._emit_downsample_conv(i - 1, prev, tl, to_conv=False)
                 self._emit_token_level(i, level, tl)
                 prev = dict(kind="tok", **tl)
@@ -421,11 +426,6 @@ class Plan:
         xs = tl["xs"]
         xs_ptr = xs.data_ptr()
         has_ct = ncw > 0
-        if tl["padded"] or True:
-            # window-padding pixels are zero tokens at level entry (fvar.py:853-855); all other rows are
-            # fully overwritten by the downsample GEMM / tokenizer below
-            if tl["padded"]:
-                self.ops.append(("zero", xs, "memset"))
         # (the downsample GEMM that fills the window tokens was emitted before this call)
         if level.do_gt and has_ct:
             tk = level.global_tokenizer
