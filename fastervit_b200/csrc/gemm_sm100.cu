@@ -6,9 +6,9 @@
 //                 N = tile_n (runtime, multiple of 16), K=16 per instruction, fp32 accumulators in
 //                 TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the
 //                 main loop of tile i+1
-//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32b x 16 columns), fused scale/shift/activation/
-//                 layer-scale/residual, optional per-column statistics, row-map scatter, vectorised
-//                 global stores
+//   warps 2..9  : epilogue — tcgen05.ld (32 lanes x 32b x 32 columns), shared-memory transpose, fused
+//                 scale/shift/activation/layer-scale/residual, optional per-column statistics,
+//                 row-map scatter, coalesced 16-byte global accesses
 //
 // The A operand of K-block kb is the 2-D box at row (m0 + tap_shift[tap]) of plane tap_plane[tap]:
 // with 9 taps this is an im2col-free 3x3 convolution over a zero-bordered NHWC activation matrix
@@ -28,7 +28,7 @@ namespace fvit {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B: one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int TMEM_COLS = 512;
@@ -37,7 +37,7 @@ constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem base, placed after the stage ring
 constexpr int SMEM_ALIGN_SLACK = 1024;
 constexpr int STG_LD = 36;  // floats per staging row: 32 + 4 pad -> conflict-free float4 access both ways
-constexpr int SMEM_STG_BYTES = 4 * 32 * STG_LD * 4;  // one 32x32 fp32 staging tile per epilogue warp
+constexpr int SMEM_STG_BYTES = 8 * 32 * STG_LD * 4;  // one 32x32 fp32 staging tile per epilogue warp
 
 struct GemmParams {
   int m, n;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], 8);
     }
     fence_mbar_init();
   }
@@ -267,14 +267,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ===================================================================== epilogue warps
-    // Each warp owns one 32-lane TMEM quadrant (32 rows of the tile). Per 32-column chunk it pulls the
-    // accumulators row-per-thread with tcgen05.ld, transposes them through a padded shared-memory
-    // staging tile and then works "coalesced": one instruction covers 4 rows x 128 contiguous bytes
-    // (8 lanes x float4 per row), so residual loads and fp32 / fp16 stores are full-line accesses.
+    // 8 warps: warp w owns TMEM lane quadrant (w & 3) (32 rows of the tile) and every second
+    // 32-column chunk ((w - 2) >> 2 selects even / odd chunks). Per chunk a warp
+    //   1. issues its residual / aux global loads (addresses do not depend on the accumulator),
+    //   2. pulls the accumulators row-per-thread with tcgen05.ld and transposes them through a padded
+    //      shared-memory staging tile,
+    //   3. works "coalesced": one instruction covers 4 rows x 128 contiguous bytes (8 lanes x float4
+    //      per row), so residual loads and fp32 / fp16 stores are full-line accesses.
+    // The epilogue is bound by global-memory latency, hence the loads hoisted ahead of the TMEM read
+    // and the 256 threads: ~32 KB of residual reads are in flight per SM.
+    const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    float* stg = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES) + quad * (32 * STG_LD);
+    const int chunk_par = ew >> 2;
+    float* stg = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES) + ew * (32 * STG_LD);
     const int sub = lane >> 3;   // row within a 4-row group
     const int c4 = lane & 7;     // which float4 of the 32-column chunk
+    const bool use_resid = p.resid != nullptr && !p.atomic_out;
+    const bool use_aux = (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) && !p.atomic_out;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -284,18 +293,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int row_base = tm * BM + quad * 32;
       const int n0 = tn * p.tile_n;
       const int n_end = min(p.n, n0 + p.tile_n);
-      // output row of tile row (row_base + lane); other rows are fetched by shuffle
-      long long my_orow = -1;
-      if (row_base + lane < p.m)
-        my_orow = p.row_map ? (long long)p.row_map[row_base + lane] : (long long)(row_base + lane);
+      // output rows of the 8 tile rows this lane touches (4k + sub), fetched once per tile
+      long long orow[8];
+      {
+        long long my_orow = -1;
+        if (row_base + lane < p.m)
+          my_orow = p.row_map ? (long long)p.row_map[row_base + lane] : (long long)(row_base + lane);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) orow[k] = __shfl_sync(0xffffffffu, my_orow, 4 * k + sub);
+      }
 
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
+      bool waited = false;
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
 
-      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
+      for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 64) {
         const int nbase = n0 + c0;
         if (nbase >= p.n) break;  // warp-uniform
+        const int col = nbase + 4 * c4;            // first of this lane's 4 columns
+        const bool cfull = col + 4 <= n_end;        // all 4 columns valid
+        const bool cany = col < n_end;
+        // ---- 1. global loads first
+        float4 rv[8];
+        uint2 av[8];
+        if (use_resid) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cany && orow[k] >= 0) {
+              const float* r = p.resid + orow[k] * p.ld_resid + col;
+              if (cfull && p.vec_ok) {
+                rv[k] = *reinterpret_cast<const float4*>(r);
+              } else {
+                rv[k].x = r[0];
+                if (col + 1 < n_end) rv[k].y = r[1];
+                if (col + 2 < n_end) rv[k].z = r[2];
+                if (col + 3 < n_end) rv[k].w = r[3];
+              }
+            }
+          }
+        }
+        if (use_aux) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            av[k] = make_uint2(0u, 0u);
+            if (cany && orow[k] >= 0) {
+              const long long ab = (long long)(row_base + 4 * k + sub) * p.ld_aux + col;
+              const uint16_t* ap = reinterpret_cast<const uint16_t*>(p.aux) + ab;
+              if (cfull && p.vec_ok) {
+                av[k] = *reinterpret_cast<const uint2*>(ap);
+              } else {
+                uint32_t e[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col + i < n_end) e[i] = ap[i];
+                av[k] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+              }
+            }
+          }
+        }
+        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f),
+               cs2 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (cany) {
+          if (p.col_scale) cs = ld_vec4_guard(p.col_scale + col, n_end - col, 1.f);
+          if (p.col_shift) sh = ld_vec4_guard(p.col_shift + col, n_end - col, 0.f);
+          if (p.col_scale2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
+        }
+        // ---- 2. accumulators: TMEM -> registers -> staging tile
+        if (!waited) {
+          mbar_wait(&acc_full[acc], acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
         {
           uint32_t raw[32];
           if (c0 + 32 <= p.tile_n) {
@@ -317,27 +385,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                   __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
         }
         __syncwarp();
-        const int col = nbase + 4 * c4;            // first of this lane's 4 columns
-        const bool cfull = col + 4 <= n_end;        // all 4 columns valid
-        const bool cany = col < n_end;
-        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f),
-               cs2 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (cany) {
-          if (p.col_scale) cs = ld_vec4_guard(p.col_scale + col, n_end - col, 1.f);
-          if (p.col_shift) sh = ld_vec4_guard(p.col_shift + col, n_end - col, 0.f);
-          if (p.col_scale2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
-        }
+        // ---- 3. coalesced epilogue math + stores
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+#pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int rl = 4 * k + sub;  // row within the warp's 32
-          const long long orow = __shfl_sync(0xffffffffu, my_orow, rl);
-          const bool ok = cany && orow >= 0;
+          const bool ok = cany && orow[k] >= 0;
           float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + 4 * c4);
           v.x *= p.alpha, v.y *= p.alpha, v.z *= p.alpha, v.w *= p.alpha;
           if (p.atomic_out) {
             if (ok) {
-              float* o = p.out_f32 + orow * p.ld_o32 + col;
+              float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
               atomicAdd(o, v.x);
               if (col + 1 < n_end) atomicAdd(o + 1, v.y);
               if (col + 2 < n_end) atomicAdd(o + 2, v.z);
@@ -351,22 +409,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             s1.x += v.x, s1.y += v.y, s1.z += v.z, s1.w += v.w;
             s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
           }
-          if (!ok) continue;  // no warp-collective ops below this point inside the k loop
+          if (!ok) continue;
           if (p.act == FVIT_ACT_RELU) {
             v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
           } else if (p.act == FVIT_ACT_GELU) {
             v.x = gelu_erf(v.x), v.y = gelu_erf(v.y), v.z = gelu_erf(v.z), v.w = gelu_erf(v.w);
-          } else if (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) {
-            const long long ab = (long long)(row_base + rl) * p.ld_aux + col;
+          } else if (use_aux) {
             float a[4];
-            if (cfull && p.vec_ok) {
-              const uint2 pk = *reinterpret_cast<const uint2*>(
-                  reinterpret_cast<const uint16_t*>(p.aux) + ab);
-              unpack4_16(pk, p.bf16, a);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) a[i] = col + i < n_end ? load16_as_float(p.aux, ab + i, p.bf16) : 0.f;
-            }
+            unpack4_16(av[k], p.bf16, a);
             if (p.act == FVIT_ACT_GELU_BWD) {
               v.x *= gelu_erf_grad(a[0]), v.y *= gelu_erf_grad(a[1]), v.z *= gelu_erf_grad(a[2]),
               v.w *= gelu_erf_grad(a[3]);
@@ -376,20 +426,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
           v.x *= cs2.x, v.y *= cs2.y, v.z *= cs2.z, v.w *= cs2.w;
-          if (p.resid) {
-            const float* r = p.resid + orow * p.ld_resid + col;
-            if (cfull && p.vec_ok) {
-              const float4 rv = *reinterpret_cast<const float4*>(r);
-              v.x += rv.x, v.y += rv.y, v.z += rv.z, v.w += rv.w;
-            } else {
-              v.x += r[0];
-              if (col + 1 < n_end) v.y += r[1];
-              if (col + 2 < n_end) v.z += r[2];
-              if (col + 3 < n_end) v.w += r[3];
-            }
-          }
+          if (use_resid) v.x += rv[k].x, v.y += rv[k].y, v.z += rv[k].z, v.w += rv[k].w;
           if (p.out_f32) {
-            float* o = p.out_f32 + orow * p.ld_o32 + col;
+            float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
             if (cfull && p.vec_ok) {
               *reinterpret_cast<float4*>(o) = v;
             } else {
@@ -400,7 +439,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
           if (p.out_f16) {
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.out_f16) + orow * p.ld_o16 + col;
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out_f16) + orow[k] * p.ld_o16 + col;
             const uint32_t lo = pack2_16(v.x, v.y, p.bf16), hi = pack2_16(v.z, v.w, p.bf16);
             if (cfull && p.vec_ok) {
               *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
@@ -429,6 +468,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (col + 3 < n_end) atomicAdd(p.col_sum + col + 3, s1.w), atomicAdd(p.col_sumsq + col + 3, s2.w);
           }
         }
+      }
+      if (!waited) {  // this warp had no chunk in the tile: still consume the phase
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
       }
       // hand the accumulator stage back to the MMA warp
       tc_fence_before();

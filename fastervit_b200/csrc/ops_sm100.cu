@@ -51,6 +51,39 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __half* __restr
   }
 }
 
+// Head-padded packing for the tensor-core attention path: blocks of `hd` rows (pad_rows) and/or
+// columns (pad_cols) of the fp32 source are spread to blocks of `hdp` >= hd with zero fill, e.g. the
+// qkv weight [3*h*hd, C] -> [3*h*hdp, C] and the proj weight [C, h*hd] -> [C, h*hdp].
+__global__ void cast_headpad_kernel(const float* __restrict__ src, long long lds, __half* __restrict__ dst,
+                                    long long ldd, int rows_dst, int cols_dst, int hd, int hdp,
+                                    int pad_rows, int pad_cols) {
+  const long long total = (long long)rows_dst * cols_dst;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_dst), c = (int)(i % cols_dst);
+    int sr = r, sc = c;
+    bool ok = true;
+    if (pad_rows) {
+      const int d = r % hdp;
+      ok = ok && d < hd;
+      sr = (r / hdp) * hd + d;
+    }
+    if (pad_cols) {
+      const int d = c % hdp;
+      ok = ok && d < hd;
+      sc = (c / hdp) * hd + d;
+    }
+    dst[r * ldd + c] = __float2half_rn(ok ? src[sr * lds + sc] : 0.f);
+  }
+}
+__global__ void vec_headpad_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_dst, int hd,
+                                   int hdp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dst) return;
+  const int d = i % hdp;
+  dst[i] = d < hd ? src[(i / hdp) * hd + d] : 0.f;
+}
+
 // Per-channel epilogue vectors:  s = bn ? w*rsqrt(var+eps) : 1 ; t = bn ? b - mean*s : 0 ;
 // t += bias*s ; then both *= layer_scale (if given).  y = acc*s + t reproduces
 // layer_scale * BN(acc + bias) (fv.py:504-510) or layer_scale * (acc + bias) (fv.py:690-691).
@@ -497,6 +530,23 @@ int fvit_cast_pad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int
   cast_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       src, lds, (__half*)dst, ldd, rows, cols, cols_pad);
   return post_launch("cast_pad_kernel");
+}
+
+int fvit_cast_headpad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows_dst,
+                          int32_t cols_dst, int32_t hd, int32_t hdp, int32_t pad_rows, int32_t pad_cols,
+                          void* stream) {
+  FVIT_CHECK(src && dst && rows_dst > 0 && cols_dst > 0 && hd > 0 && hdp >= hd && ldd >= cols_dst,
+             "fvit_cast_headpad_f16: bad arguments");
+  const long long total = (long long)rows_dst * cols_dst;
+  cast_headpad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, lds, (__half*)dst, ldd, rows_dst, cols_dst, hd, hdp, pad_rows, pad_cols);
+  return post_launch("cast_headpad_kernel");
+}
+
+int fvit_vec_headpad_f32(const float* src, float* dst, int32_t n_dst, int32_t hd, int32_t hdp, void* stream) {
+  FVIT_CHECK(src && dst && n_dst > 0 && hd > 0 && hdp >= hd, "fvit_vec_headpad_f32: bad arguments");
+  vec_headpad_kernel<<<ceil_div(n_dst, 128), 128, 0, (cudaStream_t)stream>>>(src, dst, n_dst, hd, hdp);
+  return post_launch("vec_headpad_kernel");
 }
 
 int fvit_pack_conv3x3_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,

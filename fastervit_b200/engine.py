@@ -321,6 +321,9 @@ class Plan:
         nW = B * nwin
         n_ct = ncw * nwin
         xs = nb.new(f"l{i}.xs", (nW * S + B * n_ct, Cc), torch.float32)
+        heads = level.blocks[0].attn.num_heads
+        hdp = self._head_pad(Cc // heads)
+        Cp = heads * hdp  # channel count with every head zero-padded to hdp (tensor-core attention)
         bi, yi, xi = torch.meshgrid(torch.arange(B), torch.arange(Hp), torch.arange(Wp), indexing="ij")
         win = (bi * nwh + yi // ws) * nww + xi // ws
         pix_map = win * S + ncw + (yi % ws) * ws + (xi % ws)          # [B, Hp, Wp] -> xs row
@@ -329,8 +332,8 @@ class Plan:
                  pix_map=nb.i32(f"l{i}.pix_map", pix_map.reshape(-1)),
                  crop_map=nb.i32(f"l{i}.crop_map", pix_map[:, :Hc, :Wc].reshape(-1)),
                  xn16=nb.new(f"l{i}.xn16", (nW * S, Cc), torch.float16),
-                 qkv16=nb.new(f"l{i}.qkv16", (nW * S, 3 * Cc), torch.float16),
-                 ao16=nb.new(f"l{i}.ao16", (nW * S, Cc), torch.float16),
+                 qkv16=nb.new(f"l{i}.qkv16", (nW * S, 3 * Cp), torch.float16),
+                 ao16=nb.new(f"l{i}.ao16", (nW * S, Cp), torch.float16),
                  h16=nb.new(f"l{i}.h16", (nW * S, int(Cc * self.model.cfg["mlp_ratio"])), torch.float16))
         if has_ct:
             ctr0 = nW * S
@@ -346,8 +349,8 @@ class Plan:
             d["norm1_gather"] = nb.i32(f"l{i}.norm1_gather", rows.reshape(-1))
             d["ctr0"] = ctr0
             d["ctn16"] = nb.new(f"l{i}.ctn16", (B * n_ct, Cc), torch.float16)
-            d["ctqkv16"] = nb.new(f"l{i}.ctqkv16", (B * n_ct, 3 * Cc), torch.float16)
-            d["ctao16"] = nb.new(f"l{i}.ctao16", (B * n_ct, Cc), torch.float16)
+            d["ctqkv16"] = nb.new(f"l{i}.ctqkv16", (B * n_ct, 3 * Cp), torch.float16)
+            d["ctao16"] = nb.new(f"l{i}.ctao16", (B * n_ct, Cp), torch.float16)
             d["cth16"] = nb.new(f"l{i}.cth16", (B * n_ct, int(Cc * self.model.cfg["mlp_ratio"])), torch.float16)
             # tokenizer output (b, y0, x0) over the (cs*nwh) x (cs*nww) carrier grid -> xs row
             oh, ow = cs * nwh, cs * nww
@@ -361,15 +364,65 @@ class Plan:
             d["prop_src"] = nb.i32(f"l{i}.prop_src", torch.where(t >= 0, src, torch.full_like(src, -1)))
         return d
 
-    def _emit_attention(self, nm: str, attn, rows: int, groups: int, S: int, xin, ld_in, qkv, ao, bias_buf) -> None:
-        """qkv GEMM (+bias) and the softmax(QK^T*scale + bias)V core (fv.py:559-565)."""
-        Cc = attn.qkv.in_features
-        wq, ldq = self._pack_linear(nm + ".qkv", attn.qkv)
-        self._gemm(a=xin.data_ptr(), a_rows=rows, lda=ld_in, b=wq.data_ptr(), ldb=ldq, m=rows, n=3 * Cc, kc=Cc,
-                   col_shift=attn.qkv.bias.data_ptr() if attn.qkv.bias is not None else None,
-                   out_f16=qkv.data_ptr(), ld_o16=3 * Cc)
-        self._op(self.ops, "fvit_attn_core_fwd", qkv.data_ptr(), 3 * Cc, groups, S, attn.num_heads, attn.head_dim,
-                 bias_buf.data_ptr(), float(attn.head_dim ** -0.5), ao.data_ptr(), Cc, None)
+    @staticmethod
+    def _head_pad(hd: int) -> int:
+        """Padded head dim of the tensor-core attention kernel (TMA boxes need 16-byte rows; the
+        kernel is instantiated for 32 and 64). Larger heads use the generic SIMT core unpadded."""
+        return 32 if hd <= 32 else (64 if hd <= 64 else hd)
+
+    def _emit_attention(self, nm: str, attn, gamma, rows: int, groups: int, S: int, xin, ld_in, qkv, ao,
+                        bias_buf, stream_buf) -> None:
+        """x += gamma * proj(softmax(q k^T * scale + bias) v) with q,k,v = qkv(xin)  (fv.py:557-568).
+        Three launches: qkv GEMM (+bias), attention core, proj GEMM (+bias, layer-scale, residual)."""
+        Cc, h, hd = attn.qkv.in_features, attn.num_heads, attn.head_dim
+        hdp = self._head_pad(hd)
+        use_tc = S <= 128 and hdp <= 64
+        if not use_tc:
+            hdp = hd
+        Cp = h * hdp
+        qb = attn.qkv.bias
+        if hdp == hd:
+            wq, ldq = self._pack_linear(nm + ".qkv", attn.qkv)
+            qb_ptr = qb.data_ptr() if qb is not None else None
+        else:
+            ldq = _ru(Cc, 8)
+            wq = self.bufs.new(nm + ".qkv.w16", (3 * Cp, ldq), torch.float16)
+            self._op(self.prep_ops, "fvit_cast_headpad_f16", attn.qkv.weight.data_ptr(), Cc, wq.data_ptr(), ldq,
+                     3 * Cp, Cc, hd, hdp, 1, 0)
+            qb_ptr = None
+            if qb is not None:
+                qbp = self.bufs.new(nm + ".qkv.bias_pad", (3 * Cp,), torch.float32)
+                self._op(self.prep_ops, "fvit_vec_headpad_f32", qb.data_ptr(), qbp.data_ptr(), 3 * Cp, hd, hdp)
+                qb_ptr = qbp.data_ptr()
+        self._gemm(a=xin.data_ptr(), a_rows=rows, lda=ld_in, b=wq.data_ptr(), ldb=ldq, m=rows, n=3 * Cp, kc=Cc,
+                   col_shift=qb_ptr, out_f16=qkv.data_ptr(), ld_o16=3 * Cp)
+        self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc  # algorithmic (un-padded heads)
+        scale = float(hd ** -0.5)
+        if use_tc:
+            self._op(self.ops, "fvit_attn_tc_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hdp,
+                     bias_buf.data_ptr(), scale, ao.data_ptr(), Cp)
+        else:
+            self._op(self.ops, "fvit_attn_core_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hd,
+                     bias_buf.data_ptr(), scale, ao.data_ptr(), Cp, None)
+        self.op_flops[len(self.ops) - 1] = 4.0 * groups * h * S * S * hd
+        # proj: K dimension is the (head-padded) attention output
+        lin = attn.proj
+        n = lin.weight.shape[0]
+        if hdp == hd:
+            wp, ldp = self._pack_linear(nm + ".proj", lin)
+        else:
+            ldp = Cp
+            wp = self.bufs.new(nm + ".proj.w16", (n, Cp), torch.float16)
+            self._op(self.prep_ops, "fvit_cast_headpad_f16", lin.weight.data_ptr(), Cc, wp.data_ptr(), Cp, n, Cp,
+                     hd, hdp, 0, 1)
+        if isinstance(gamma, torch.Tensor):
+            sc, sh = self._fold(nm + ".proj.ls", n, bias=lin.bias, ls=gamma)
+            cs_, sh_ = sc.data_ptr(), sh.data_ptr()
+        else:
+            cs_, sh_ = None, lin.bias.data_ptr()
+        self._gemm(a=ao.data_ptr(), a_rows=rows, lda=Cp, b=wp.data_ptr(), ldb=ldp, m=rows, n=n, kc=Cp,
+                   col_scale=cs_, col_shift=sh_, resid=stream_buf, ld_resid=n, out_f32=stream_buf, ld_o32=n)
+        self.op_flops[len(self.ops) - 1] = 2.0 * rows * n * Cc
 
     def _emit_bias(self, nm: str, rpb, S: int) -> torch.Tensor:
         """PosEmbMLPSwinv2D (fv.py:276-307): table MLP + gather + 16*sigmoid, written straight into the
@@ -448,10 +501,8 @@ class Plan:
                          blk.hat_norm1.weight.data_ptr(), blk.hat_norm1.bias.data_ptr(), float(blk.hat_norm1.eps),
                          tl["ctn16"].data_ptr(), Cc, None, None, None)
                 hb = self._emit_bias(nm + ".hat_bias", blk.hat_attn.pos_emb_funct, n_ct)
-                self._emit_attention(nm + ".hat_attn", blk.hat_attn, rows_c, B, n_ct, tl["ctn16"], Cc,
-                                     tl["ctqkv16"], tl["ctao16"], hb)
-                self._emit_branch_out(nm + ".hat_proj", blk.hat_attn.proj, blk.gamma1, tl["ctao16"], Cc, rows_c,
-                                      ctr_ptr)
+                self._emit_attention(nm + ".hat_attn", blk.hat_attn, blk.gamma1, rows_c, B, n_ct, tl["ctn16"], Cc,
+                                     tl["ctqkv16"], tl["ctao16"], hb, ctr_ptr)
                 self._op(self.ops, "fvit_ln_fwd", ctr_ptr, Cc, None, rows_c, Cc, None, 1, 0, None, 0,
                          blk.hat_norm2.weight.data_ptr(), blk.hat_norm2.bias.data_ptr(), float(blk.hat_norm2.eps),
                          tl["ctn16"].data_ptr(), Cc, None, None, None)
@@ -464,8 +515,8 @@ class Plan:
                      Cc, pe.data_ptr(), S, ncw, xs_ptr, Cc, blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(),
                      float(blk.norm1.eps), tl["xn16"].data_ptr(), Cc, None, None, None)
             ab = self._emit_bias(nm + ".bias", blk.attn.pos_emb_funct, S)
-            self._emit_attention(nm + ".attn", blk.attn, rows, nW, S, tl["xn16"], Cc, tl["qkv16"], tl["ao16"], ab)
-            self._emit_branch_out(nm + ".proj", blk.attn.proj, blk.gamma3, tl["ao16"], Cc, rows, xs_ptr)
+            self._emit_attention(nm + ".attn", blk.attn, blk.gamma3, rows, nW, S, tl["xn16"], Cc, tl["qkv16"],
+                                 tl["ao16"], ab, xs_ptr)
             self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, None, rows, Cc, None, 1, 0, None, 0,
                      blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr(), float(blk.norm2.eps),
                      tl["xn16"].data_ptr(), Cc, None, None, None)

@@ -86,6 +86,9 @@ _OP_SIGS: dict[str, list] = {
     "fvit_stem_conv_fwd": [_P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P, _P, _P],
     "fvit_ln_fwd": [_P, _L, _P, _I, _I, _P, _I, _I, _P, _L, _P, _P, _F, _P, _L, _P, _P, _P, _P],
     "fvit_attn_core_fwd": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
+    "fvit_attn_tc_fwd": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _L, _P],
+    "fvit_cast_headpad_f16": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P],
+    "fvit_vec_headpad_f32": [_P, _P, _I, _I, _I, _P],
     "fvit_cpb_mlp_fwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P],
     "fvit_attn_bias_fwd": [_P, _P, _I, _I, _I, _P, _P],
     "fvit_token_init_fwd": [_P, _L, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],

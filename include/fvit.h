@@ -108,6 +108,13 @@ int fvit_gemm(const fvit_gemm_args* args, void* stream);
  * 545-547, 927) become K-major B operands with a 16-byte aligned row stride. */
 int fvit_cast_pad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows,
                       int32_t cols, int32_t cols_pad, void* stream);
+/* head-padded variants for the tensor-core attention path: blocks of `hd` rows / columns become
+ * blocks of `hdp` (zero filled), so every head slice of q, k, v and of the attention output is a
+ * 16-byte aligned TMA box (fv4: head_dim 49 -> 64). */
+int fvit_cast_headpad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t rows_dst,
+                          int32_t cols_dst, int32_t hd, int32_t hdp, int32_t pad_rows, int32_t pad_cols,
+                          void* stream);
+int fvit_vec_headpad_f32(const float* src, float* dst, int32_t n_dst, int32_t hd, int32_t hdp, void* stream);
 /* nn.Conv2d weight [cout][cin][3][3] (fv.py:434, 461, 489, 492) -> [cout][9][kc_pad] fp16, tap-major;
  * transpose_io != 0 builds the data-gradient operand [cin][9 flipped][kc_pad >= cout]. */
 int fvit_pack_conv3x3_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,
@@ -148,6 +155,13 @@ int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows
 int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads,
                        int32_t head_dim, const float* bias, float scale, void* out, int64_t ldo,
                        float* probs_out, void* stream);
+
+/* Tensor-core version of the same attention core (tcgen05: S = QK^T and O = PV with fp32 accumulators
+ * in tensor memory, TMA-staged head slices, per-row softmax by the epilogue warps; scores and
+ * probabilities never leave the SM). qkv fp16 [groups*S, 3*heads*hdp] with head_dim zero-padded to
+ * hdp in {32, 64}; out fp16 [groups*S, heads*hdp]; S <= 128. bias fp32 [heads, S, S] or NULL. */
+int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
+                     const float* bias, float scale, void* out, int64_t ldo, void* stream);
 
 /* ---- positional MLPs (cpb_mlp: Linear(2,512)+ReLU+Linear(512,D, no bias); fv.py:223-225, 322-324) --
  * out[p][d] for P coordinate pairs; hidden_out (optional, [P,512]) saves the ReLU output. */

@@ -1,0 +1,58 @@
+"""GPU parity of the attention cores (tcgen05 fvit_attn_tc_fwd and the generic SIMT fvit_attn_core_fwd)
+against fp32 torch math on the same fp16 q, k, v. Tolerance 2e-3 max-rel: P is rounded to fp16 before
+the PV product in the tensor-core kernel (same as the reference under fp16 autocast)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, groups, S, heads, hd, hdp, bias, scale):
+    q, k, v = qkv.float().view(groups, S, 3, heads, hdp)[..., :hd].permute(2, 0, 3, 1, 4)
+    attn = (q @ k.transpose(-2, -1)) * scale
+    if bias is not None:
+        attn = attn + bias[None]
+    p = attn.softmax(-1)
+    o = (p @ v).permute(0, 2, 1, 3)  # groups, S, heads, hd
+    out = torch.zeros(groups, S, heads, hdp, device=qkv.device)
+    out[..., :hd] = o
+    return out.reshape(groups * S, heads * hdp)
+
+
+@pytest.mark.parametrize("S,heads,hd,groups", [(53, 8, 32, 37), (49, 16, 32, 20), (16, 8, 32, 11), (53, 16, 49, 9),
+                                               (60, 8, 32, 5), (36, 16, 32, 31), (128, 2, 64, 3), (64, 4, 24, 6),
+                                               (53, 8, 32, 1024)])
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_attn_tc_matches_torch(S, heads, hd, groups, with_bias):
+    from fastervit_b200 import lib
+    lib.load()
+    hdp = 32 if hd <= 32 else 64
+    g = torch.Generator(device="cuda").manual_seed(S * 131 + heads)
+    qkv = torch.zeros(groups * S, 3, heads, hdp, device="cuda")
+    qkv[..., :hd] = torch.randn(groups * S, 3, heads, hd, device="cuda", generator=g)
+    qkv = qkv.reshape(groups * S, 3 * heads * hdp).half()
+    bias = (torch.randn(heads, S, S, device="cuda", generator=g) * 2 + 4) if with_bias else None
+    out = torch.full((groups * S, heads * hdp), float("nan"), device="cuda", dtype=torch.half)
+    scale = hd ** -0.5
+    lib.call("fvit_attn_tc_fwd", qkv.data_ptr(), qkv.stride(0), groups, S, heads, hdp,
+             bias.data_ptr() if with_bias else None, scale, out.data_ptr(), out.stride(0))
+    ref = _ref(qkv, groups, S, heads, hd, hdp, bias, scale)
+    err = ((out.float() - ref).abs().max() / ref.abs().max()).item()
+    assert torch.isfinite(out.float()).all()
+    assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("S,heads,hd,groups", [(53, 8, 32, 7), (148, 8, 32, 3), (53, 4, 49, 5)])
+def test_attn_simt_matches_torch(S, heads, hd, groups):
+    from fastervit_b200 import lib
+    lib.load()
+    g = torch.Generator(device="cuda").manual_seed(S + hd)
+    qkv = torch.randn(groups * S, 3 * heads * hd, device="cuda", generator=g).half()
+    bias = torch.randn(heads, S, S, device="cuda", generator=g) * 2 + 4
+    out = torch.zeros(groups * S, heads * hd, device="cuda", dtype=torch.half)
+    scale = hd ** -0.5
+    lib.call("fvit_attn_core_fwd", qkv.data_ptr(), qkv.stride(0), groups, S, heads, hd, bias.data_ptr(), scale,
+             out.data_ptr(), out.stride(0), None)
+    ref = _ref(qkv, groups, S, heads, hd, hd, bias, scale)
+    err = ((out.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-3, err
