@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        const int tile = w / p.heads, head = w % p.heads;
+        const int head = w / p.tiles, tile = w % p.tiles;  // head-major: bias is re-staged rarely
         mbar_wait(&qkv_empty[st], ph ^ 1);
         uint8_t* base = smem + st * SM::STAGE_BYTES;
         mbar_expect_tx(&qkv_full[st], SM::STAGE_BYTES);
@@ -165,18 +165,34 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
             make_uint4(0, 0, 0, 0);
     }
     int it = 0;
+    int staged_head = -1;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      const int tile = w / p.heads, head = w % p.heads;
+      const int head = w / p.tiles, tile = w % p.tiles;
       const bool row_ok = gi < p.gpt && (tile * p.gpt + gi) < p.groups;
-      // stage this head's bias (pre-multiplied by log2 e) in shared memory
-      named_bar_sync(1, 128);  // previous item's readers are done
-      if (p.bias) {
+      // stage this head's bias (pre-multiplied by log2 e) in shared memory when the head changes;
+      // loads are issued in batches of 8 so their latencies overlap
+      if (p.bias && head != staged_head) {
+        named_bar_sync(1, 128);  // previous head's readers are done
         const float* bsrc = p.bias + (long long)head * S * S;
-        for (int i = tid; i < S * S; i += 128) bias_s[i] = __ldg(bsrc + i) * 1.4426950408889634f;
+        const int n = S * S;
+        for (int i0 = tid; i0 < n; i0 += 128 * 8) {
+          float tmp[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 128;
+            tmp[u] = i < n ? __ldg(bsrc + i) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 128;
+            if (i < n) bias_s[i] = tmp[u] * 1.4426950408889634f;
+          }
+        }
+        named_bar_sync(1, 128);
+        staged_head = head;
       }
-      named_bar_sync(1, 128);
 
       mbar_wait(&s_full[st], ph);
       tc_fence_after();

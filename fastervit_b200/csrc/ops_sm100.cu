@@ -211,6 +211,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// im2col of the 3x3 / stride-2 / pad-1 stem convolution: out[pixel][c*9 + r*3 + s] = (half)x[b][c][2oh+r-1][2ow+s-1]
+// (zero outside the image, zero in columns >= 9*CIN). One thread per output pixel writes one `ldo`-wide
+// fp16 row with 16-byte stores; the GEMM kernel then runs the 27-deep contraction on tensor cores.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+    stem_im2col_kernel(const float* __restrict__ x, long long sb, long long sc, long long sh, long long sw,
+                       int B, int H, int W, __half* __restrict__ out, int ldo) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const unsigned total = (unsigned)B * Ho * Wo;
+  const unsigned pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int ow = pix % Wo;
+  const int oh = (pix / Wo) % Ho;
+  const int b = pix / ((unsigned)Wo * Ho);
+  constexpr int K = CIN * 9;
+  constexpr int KP = (K + 7) / 8 * 8;
+  __half v[KP];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ih = 2 * oh + r - 1, iw = 2 * ow + s - 1;
+        const float f = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + b * sb + c * sc + ih * sh + iw * sw) : 0.f;
+        v[c * 9 + r * 3 + s] = __float2half_rn(f);
+      }
+#pragma unroll
+  for (int k = K; k < KP; ++k) v[k] = __float2half_rn(0.f);
+  uint4* o = reinterpret_cast<uint4*>(out + (long long)pix * ldo);
+#pragma unroll
+  for (int q = 0; q < KP / 8; ++q) o[q] = *reinterpret_cast<const uint4*>(&v[q * 8]);
+  for (int q = KP / 8; q < ldo / 8; ++q) o[q] = make_uint4(0, 0, 0, 0);
+}
+
 // ------------------------------------------------------------------------------ LayerNorm forward
 // One warp per row. v = x[in_map ? in_map[r] : r] (+ add[(r % group) - skip] if (r % group) >= skip);
 // optionally written back as fp32 to wb[r]; y = (v - mean) * rstd * gamma + beta written as fp16 to
@@ -590,6 +625,19 @@ int fvit_stem_conv_fwd(const float* x, int64_t sb, int64_t sc, int64_t sh, int64
       x, sb, sc, sh, sw, B, H, W, wgt, cout, scale, shift, relu, out_row_map, (__half*)out, ldo,
       col_sum, col_sumsq);
   return post_launch("stem_conv_kernel");
+}
+
+int fvit_stem_im2col(const float* x, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B, int32_t cin,
+                     int32_t H, int32_t W, void* out, int32_t ldo, void* stream) {
+  FVIT_CHECK(x && out && B > 0 && H > 0 && W > 0, "fvit_stem_im2col: bad arguments");
+  FVIT_CHECK(cin == 3, "fvit_stem_im2col: only in_chans == 3 is supported (got %d)", cin);
+  FVIT_CHECK(ldo % 8 == 0 && ldo >= 32, "fvit_stem_im2col: ldo=%d must be a multiple of 8 and >= 32", ldo);
+  FVIT_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0, "fvit_stem_im2col: out must be 16-byte aligned");
+  const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
+  FVIT_CHECK(total < (1ll << 31), "fvit_stem_im2col: too many pixels");
+  stem_im2col_kernel<3><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, sb, sc, sh, sw, B, H, W, (__half*)out, ldo);
+  return post_launch("stem_im2col_kernel");
 }
 
 int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows, int32_t C,

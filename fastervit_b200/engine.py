@@ -70,6 +70,7 @@ class _Bufs:
 
 class Plan:
     """Static launch list for one (batch, height, width, training) signature."""
+    STEM_LD = 64  # fp16 row width of the stem im2col matrix (27 taps, zero padded to one 128-byte row)
 
     def __init__(self, model, B: int, H: int, W: int, training: bool, device):
         self.model, self.B, self.H, self.W, self.training, self.device = model, B, H, W, training, device
@@ -158,10 +159,19 @@ class Plan:
                                        + ((yi >> 1) + 1) * (W0 + 1) + (xi >> 1) + 1).reshape(-1))
         pe = m.patch_embed.conv_down
         s1, t1 = self._fold("stem.bn1", in_dim, pe[1])
-        self._x_args.append(dict(B=B, cin=cfg["in_chans"], H=self.H, W=self.W, wgt=pe[0].weight.data_ptr(),
-                                 cout=in_dim, scale=s1.data_ptr(), shift=t1.data_ptr(), relu=1,
-                                 row_map=stem_map.data_ptr(), out=stem_planes.data_ptr(), ldo=ld_in))
-        self.ops.append(("stem", len(self._x_args) - 1, "fvit_stem_conv_fwd"))
+        # conv1 (fv.py:458-460) on tensor cores: im2col rows [pixel, 27 -> STEM_LD] (one HBM-bound
+        # kernel), then a single-K-block GEMM with the BN + ReLU epilogue scattering into the planes
+        col16 = nb.new("stem.col16", (B * H1 * W1, self.STEM_LD), torch.float16)
+        self._x_args.append(dict(B=B, cin=cfg["in_chans"], H=self.H, W=self.W, out=col16.data_ptr(),
+                                 ldo=self.STEM_LD))
+        self.ops.append(("im2col", len(self._x_args) - 1, "fvit_stem_im2col"))
+        w1 = nb.new("stem.conv1.w16", (in_dim, self.STEM_LD), torch.float16)
+        self._op(self.prep_ops, "fvit_cast_pad_f16", pe[0].weight.data_ptr(), 27, w1.data_ptr(), self.STEM_LD,
+                 in_dim, 27, 32)
+        self._gemm(a=col16.data_ptr(), a_rows=B * H1 * W1, lda=self.STEM_LD, b=w1.data_ptr(), ldb=self.STEM_LD,
+                   m=B * H1 * W1, n=in_dim, kc=32, col_scale=s1.data_ptr(), col_shift=t1.data_ptr(),
+                   act=L.ACT_RELU, row_map=stem_map.data_ptr(), out_f16=stem_planes.data_ptr(), ld_o16=ld_in)
+        self.op_flops[len(self.ops) - 1] = 2.0 * B * H1 * W1 * in_dim * 27
 
         lvl = self._conv_level_buffers(0, dim, H0, W0)
         w16, ldw = self._pack_conv("stem.conv2", pe[3])
@@ -539,11 +549,10 @@ class Plan:
         st = L.stream_ptr()
         lib = self.lib
         for fn, args, name in ops:
-            if fn == "stem":
+            if fn == "im2col":
                 a = self._x_args[args]
-                rc = lib.fvit_stem_conv_fwd(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
-                                            a["B"], a["cin"], a["H"], a["W"], a["wgt"], a["cout"], a["scale"],
-                                            a["shift"], a["relu"], a["row_map"], a["out"], a["ldo"], None, None, st)
+                rc = lib.fvit_stem_im2col(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
+                                          a["B"], a["cin"], a["H"], a["W"], a["out"], a["ldo"], st)
             elif fn == "zero":
                 args.zero_()
                 continue

@@ -135,6 +135,12 @@ int fvit_stem_conv_fwd(const float* x, int64_t sb, int64_t sc, int64_t sh, int64
                        const float* scale, const float* shift, int32_t relu, const int32_t* out_row_map,
                        void* out, int64_t ldo, float* col_sum, float* col_sumsq, void* stream);
 
+/* im2col of the same convolution for the tensor-core path: out[pixel][c*9 + r*3 + s] = (half) input tap
+ * (zero outside the image and in the padding columns up to ldo); the 27-deep contraction then runs as a
+ * plain fvit_gemm with the BatchNorm/ReLU epilogue. */
+int fvit_stem_im2col(const float* x, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B, int32_t cin,
+                     int32_t H, int32_t W, void* out, int32_t ldo, void* stream);
+
 /* ---- LayerNorm forward over the channel dim of token rows (nn.LayerNorm eps 1e-5 fv.py:615,631,
  * 643-644, 690-691; timm LayerNorm2d eps 1e-6 fv.py:432,438), fused with the positional-embedding add
  * of PosEmbMLPSwinv1D (fv.py:366, 665, 676), with row gather (window partition / ct_dewindow,

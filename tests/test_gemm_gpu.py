@@ -18,7 +18,7 @@ def _rel(a, b):
     return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20)).item()
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (300, 200, 136), (4096, 768, 256), (1000, 1000, 520),
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (1000, 64, 32), (520, 48, 16), (300, 200, 136), (4096, 768, 256), (1000, 1000, 520),
                                    (128 * 200 + 5, 512, 192), (53 * 64, 2352, 784)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_gemm_nt_plain(m, n, k, dtype):
