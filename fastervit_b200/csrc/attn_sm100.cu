@@ -29,6 +29,7 @@ constexpr int AT_ROWS = 128;
 
 struct AttnParams {
   int groups, S, heads, gpt, tiles;
+  int slot;  // rows per window slot inside the 128-row tile: smallest of {16, 32, 64, 128} >= S
   int rows_total;
   float scale_log2e;
   const float* bias;  // [heads, S, S] or null
@@ -38,10 +39,11 @@ struct AttnParams {
 
 template <int HDP>
 struct AttnSmem {
+  static constexpr int NST = HDP == 32 ? 2 : 1;              // Q/K/V ring depth (2 CTAs per SM either way)
   static constexpr int TILE_BYTES = AT_ROWS * HDP * 2;       // one of Q / K / V
   static constexpr int STAGE_BYTES = 3 * TILE_BYTES;
   static constexpr int P_BYTES = AT_ROWS * 128 * 2;          // 128 x 128 fp16, two 64-wide K atoms
-  static constexpr int P_OFF = 2 * STAGE_BYTES;
+  static constexpr int P_OFF = NST * STAGE_BYTES;
   static constexpr int BIAS_OFF = P_OFF + P_BYTES;
 };
 
@@ -49,10 +51,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Window w of a tile lives in rows [w*slot, w*slot + S) of the 128-row operand tiles (slot = 16/32/64/
+// 128), so a query row only ever meets the keys of its own slot: the S x S diagonal blocks of the
+// 128 x 128 score matrix. Rows >= S of a slot hold the first rows of the next window (harmless:
+// masked as keys, not written as queries).
 template <int HDP>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ AttnParams p) {
   using SM = AttnSmem<HDP>;
+  constexpr int NST = SM::NST;
   constexpr uint32_t SWZ = HDP == 64 ? SWZ_128B : SWZ_64B;
   constexpr uint32_t ROW_BYTES = HDP * 2;            // bytes per smem row of Q / K / V
   constexpr uint32_t SBO_QKV = 8 * ROW_BYTES;        // 8-row group stride
@@ -82,30 +89,36 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // two score stages of 128 fp32 columns; O (HDP columns) overwrites the stage it was computed from
   const uint32_t tmem_S[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tmem_O = tmem_base + 256;
 
   const int items = p.tiles * p.heads;
+  const int nslots = AT_ROWS / p.slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int st = it % NST;
+        const uint32_t ph = (it / NST) & 1;
         const int head = w / p.tiles, tile = w % p.tiles;  // head-major: bias is re-staged rarely
         mbar_wait(&qkv_empty[st], ph ^ 1);
         uint8_t* base = smem + st * SM::STAGE_BYTES;
         mbar_expect_tx(&qkv_full[st], SM::STAGE_BYTES);
-        const int row0 = tile * p.gpt * S;
-        tma_load_2d(base, &tmap_qkv, &qkv_full[st], head * HDP, row0);
-        tma_load_2d(base + SM::TILE_BYTES, &tmap_qkv, &qkv_full[st], (p.heads + head) * HDP, row0);
-        tma_load_2d(base + 2 * SM::TILE_BYTES, &tmap_qkv, &qkv_full[st], (2 * p.heads + head) * HDP, row0);
+        for (int sl = 0; sl < nslots; ++sl) {
+          // window (tile*gpt + sl) -> rows [sl*slot, (sl+1)*slot) of the three operand tiles; windows
+          // past the end give out-of-range rows, which TMA zero-fills
+          const int row0 = (tile * p.gpt + sl) * S;
+          uint8_t* dst = base + sl * p.slot * ROW_BYTES;
+          tma_load_2d(dst, &tmap_qkv, &qkv_full[st], head * HDP, row0);
+          tma_load_2d(dst + SM::TILE_BYTES, &tmap_qkv, &qkv_full[st], (p.heads + head) * HDP, row0);
+          tma_load_2d(dst + 2 * SM::TILE_BYTES, &tmap_qkv, &qkv_full[st], (2 * p.heads + head) * HDP, row0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -114,25 +127,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       const uint32_t idesc2 = make_idesc_f16(128, HDP, 0, 1);  // B = V, MN-major
       const uint32_t sP = smem_u32(smem + SM::P_OFF);
       auto issue_pv = [&](int j) {
-        // O = P V for item j (local index): waits for the softmax warps' P
+        // O = P V for item j (local index): waits for the softmax warps' P; O lands on S stage j&1
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t sV = smem_u32(smem + (j & 1) * SM::STAGE_BYTES + 2 * SM::TILE_BYTES);
+        const uint32_t sV = smem_u32(smem + (j % NST) * SM::STAGE_BYTES + 2 * SM::TILE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 128 keys in steps of 16
           const uint64_t ad = make_smem_desc(sP + (ks >> 2) * (AT_ROWS * 128) + (ks & 3) * 32, 16, 1024, SWZ_128B);
           const uint64_t bd = make_smem_desc(sV + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
-          umma_f16_ss(tmem_O, ad, bd, idesc2, ks > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_S[j & 1], ad, bd, idesc2, ks > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
-        umma_commit(&qkv_empty[j & 1]);
+        umma_commit(&qkv_empty[j % NST]);
       };
       int it = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int st = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        const int ss = it & 1;
         mbar_wait(&qkv_full[st], ph);
-        mbar_wait(&s_empty[st], ph ^ 1);
+        mbar_wait(&s_empty[ss], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sQ = smem_u32(smem + st * SM::STAGE_BYTES);
         const uint32_t sK = sQ + SM::TILE_BYTES;
@@ -140,37 +154,46 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         for (int k = 0; k < HDP / 16; ++k) {
           const uint64_t ad = make_smem_desc(sQ + k * 32, 16, SBO_QKV, SWZ);
           const uint64_t bd = make_smem_desc(sK + k * 32, 16, SBO_QKV, SWZ);
-          umma_f16_ss(tmem_S[st], ad, bd, idesc1, k > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_S[ss], ad, bd, idesc1, k > 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[st]);
-        if (it > 0) issue_pv(it - 1);
+        umma_commit(&s_full[ss]);
+        if (NST == 1) {
+          // single operand stage: the next item's loads need this item's P V to retire first
+          issue_pv(it);
+        } else if (it > 0) {
+          issue_pv(it - 1);
+        }
       }
-      if (it > 0) issue_pv(it - 1);
+      if (NST == 2 && it > 0) issue_pv(it - 1);
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue warps
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // row in tile
+    const int r = quad * 32 + lane;    // row in tile
     const int tid = threadIdx.x - 64;  // 0..127 among the softmax threads
-    const int gi = r / S;
-    const int lo = gi * S, hi = lo + S;  // this row's key range inside the tile
-    const int wlo = ((quad * 32) / S) * S;
-    const int whi = min(128, ((quad * 32 + 31) / S) * S + S);  // union of the warp's key ranges
+    const int slot = p.slot;
+    const int sl = r / slot;           // window slot of this row
+    const int j = r - sl * slot;       // token index inside the window
+    const int lo = sl * slot;          // first key column of the window
+    // key columns of the warp's rows: slots are >= 32 rows or the warp spans 32/slot whole slots
+    const int wlo = slot >= 32 ? lo : quad * 32;
+    const int wn = slot >= 32 ? S : 32;            // columns to visit starting at wlo
+    const int nch = (wn + 31) / 32;
     uint8_t* sP = smem + SM::P_OFF;
-    // columns outside [wlo, whi) are never written by this warp's rows again: zero them once
-    for (int j = 0; j < 16; ++j) {
-      const int c = j * 8;
-      if (c + 8 <= wlo || c >= whi)
+    // columns outside [wlo, wlo + 32*nch) are never written by this warp's rows: zero them once
+    for (int c = 0; c < 128; c += 8) {
+      if (c + 8 <= wlo || c >= wlo + 32 * nch)
         *reinterpret_cast<uint4*>(sP + (c >> 6) * (AT_ROWS * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4)) =
             make_uint4(0, 0, 0, 0);
     }
     int it = 0;
     int staged_head = -1;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-      const int st = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const int ss = it & 1;
+      const uint32_t sph = (it >> 1) & 1;
       const int head = w / p.tiles, tile = w % p.tiles;
-      const bool row_ok = gi < p.gpt && (tile * p.gpt + gi) < p.groups;
+      const int grp = tile * p.gpt + sl;
+      const bool row_ok = j < S && sl < p.gpt && grp < p.groups;
       // stage this head's bias (pre-multiplied by log2 e) in shared memory when the head changes;
       // loads are issued in batches of 8 so their latencies overlap
       if (p.bias && head != staged_head) {
@@ -194,83 +217,79 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         staged_head = head;
       }
 
-      mbar_wait(&s_full[st], ph);
+      mbar_wait(&s_full[ss], sph);
       tc_fence_after();
-      const uint32_t ts = tmem_S[st] + ((uint32_t)(quad * 32) << 16);
-      const float* brow = bias_s + (r - lo) * S - lo;  // brow[c] for c in [lo, hi)
-      // pass 1: row maximum
+      const uint32_t ts = tmem_S[ss] + ((uint32_t)(quad * 32) << 16);
+      // brow[c - lo] = bias of (this row, key c); rows that are not real queries read row 0 (unused)
+      const float* brow = bias_s + (row_ok ? j : 0) * S;
+      const bool use_bias = p.bias != nullptr;
+      // pass 1: row maximum over the window's keys
       float mx = -INFINITY;
-      for (int c0 = (wlo / 32) * 32; c0 < whi; c0 += 32) {
+      for (int ch = 0; ch < nch; ++ch) {
+        const int c0 = wlo + 32 * ch;
         uint32_t raw[32];
         tmem_ld32(ts + c0, raw);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c >= lo && c < hi) {
-              float s = __uint_as_float(raw[j]) * p.scale_log2e;
-              if (p.bias) s += brow[c];
-              mx = fmaxf(mx, s);
-            }
-          }
+        for (int u = 0; u < 32; ++u) {
+          const int kk = c0 + u - lo;               // key index inside the window
+          const bool in = kk >= 0 && kk < S;
+          const float b = use_bias ? brow[in ? kk : 0] : 0.f;
+          const float sc = fmaf(__uint_as_float(raw[u]), p.scale_log2e, b);
+          mx = fmaxf(mx, in ? sc : -INFINITY);
         }
       }
+      if (!row_ok) mx = 0.f;
       // pass 2: probabilities (unnormalised) -> fp16 operand tile, row sum
       float sum = 0.f;
-      for (int c0 = (wlo / 32) * 32; c0 < whi; c0 += 32) {
+      for (int ch = 0; ch < nch; ++ch) {
+        const int c0 = wlo + 32 * ch;
         uint32_t raw[32];
         tmem_ld32(ts + c0, raw);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int u = 0; u < 32; u += 2) {
           float e[2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = c0 + j + u;
-            float v = 0.f;
-            if (row_ok && c >= lo && c < hi) {
-              float s = __uint_as_float(raw[j + u]) * p.scale_log2e;
-              if (p.bias) s += brow[c];
-              v = exp2f(s - mx);
-            }
-            e[u] = v;
+          for (int t = 0; t < 2; ++t) {
+            const int kk = c0 + u + t - lo;
+            const bool in = row_ok && kk >= 0 && kk < S;
+            const float b = use_bias ? brow[in ? kk : 0] : 0.f;
+            const float sc = fmaf(__uint_as_float(raw[u + t]), p.scale_log2e, b - mx);
+            e[t] = in ? exp2f(sc) : 0.f;
           }
           const __half2 h = __floats2half2_rn(e[0], e[1]);
           // accumulate what the tensor core will actually multiply (fp16-rounded probabilities)
           sum += __low2float(h) + __high2float(h);
-          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = c0 + q * 8;
-          *reinterpret_cast<uint4*>(sP + (c >> 6) * (AT_ROWS * 128) + r * 128 +
-                                    ((((c & 63) >> 3) ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          if (c < 128)
+            *reinterpret_cast<uint4*>(sP + (c >> 6) * (AT_ROWS * 128) + r * 128 +
+                                      ((((c & 63) >> 3) ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
-      // P is complete for this warp's rows: publish to the async proxy, release S, signal the MMA warp
+      // P is complete for this warp's rows: publish to the async proxy and signal the MMA warp
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(p_full);
-        mbar_arrive(&s_empty[st]);
-      }
-      // O epilogue
+      if (lane == 0) mbar_arrive(p_full);
+      // O epilogue (O overwrote the score stage)
       mbar_wait(o_full, it & 1);
       tc_fence_after();
-      const uint32_t to = tmem_O + ((uint32_t)(quad * 32) << 16);
       const float inv = row_ok ? 1.f / sum : 0.f;
-      const long long grow = (long long)tile * p.gpt * S + r;
+      const long long grow = (long long)grp * S + j;
       __half* orow = p.out + grow * p.ldo + head * HDP;
 #pragma unroll
       for (int c0 = 0; c0 < HDP; c0 += 32) {
         uint32_t raw[32];
-        tmem_ld32(to + c0, raw);
+        tmem_ld32(ts + c0, raw);
         tmem_ld_wait();
-        if (row_ok && grow < p.rows_total) {
+        if (row_ok) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint32_t o4[4];
@@ -284,14 +303,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           }
         }
       }
-      tc_fence_before();  // O reads retire before this thread's next p_full arrive
+      // scores and O of this stage are consumed: hand the TMEM stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[ss]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -328,7 +350,8 @@ extern "C" int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, in
   p.groups = groups;
   p.S = S;
   p.heads = heads;
-  p.gpt = AT_ROWS / S;
+  p.slot = S <= 16 ? 16 : (S <= 32 ? 32 : (S <= 64 ? 64 : 128));
+  p.gpt = AT_ROWS / p.slot;
   p.tiles = (groups + p.gpt - 1) / p.gpt;
   p.rows_total = groups * S;
   p.scale_log2e = scale * 1.4426950408889634f;
@@ -338,7 +361,7 @@ extern "C" int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, in
   CUtensorMap tm;
   {
     const uint64_t key = reinterpret_cast<uint64_t>(qkv) ^ ((uint64_t)ldq << 40) ^ ((uint64_t)p.rows_total << 8) ^
-                         (uint64_t)hdp ^ ((uint64_t)heads << 52);
+                         (uint64_t)hdp ^ ((uint64_t)heads << 52) ^ ((uint64_t)p.slot << 30);
     std::lock_guard<std::mutex> g(g_at_mu);
     auto it = g_at_cache.find(key);
     if (it != g_at_cache.end()) {
@@ -346,7 +369,7 @@ extern "C" int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, in
     } else {
       uint64_t dims[2] = {(uint64_t)(3 * heads * hdp), (uint64_t)p.rows_total};
       uint64_t strides[1] = {(uint64_t)ldq * 2};
-      uint32_t box[2] = {(uint32_t)hdp, AT_ROWS};
+      uint32_t box[2] = {(uint32_t)hdp, (uint32_t)p.slot};
       int rc = encode_tmap_16bit(&tm, qkv, 2, dims, strides, box,
                                  hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
@@ -355,7 +378,7 @@ extern "C" int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, in
     }
   }
   const size_t smem = 1024 + (hdp == 64 ? AttnSmem<64>::BIAS_OFF : AttnSmem<32>::BIAS_OFF) +
-                      ((size_t)S * S * 4 + 15) / 16 * 16 + 256;
+                      ((size_t)S * S * 4 + 15) / 16 * 16 + 128;
   FVIT_CHECK(smem <= 227 * 1024, "fvit_attn_tc_fwd: needs %zu B of shared memory", smem);
   if (hdp == 64) return launch_attn<64>(tm, p, smem, (cudaStream_t)stream);
   return launch_attn<32>(tm, p, smem, (cudaStream_t)stream);

@@ -32,7 +32,7 @@ constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;  // TMEM column stride between the two accumulator stages
+constexpr int MAX_ACC = 8;  // accumulator stages in TMEM: 512 / (64 | 128 | 256 columns)
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem base, placed after the stage ring
 constexpr int SMEM_ALIGN_SLACK = 1024;
@@ -49,6 +49,7 @@ struct GemmParams {
   int tiles_m, tiles_n, split_k;
   int atomic_out;  // split-K style accumulation: atomicAdd(alpha * acc) into out_f32
   int stages;
+  int acc_stride, nacc;  // TMEM columns per accumulator stage and number of stages
   uint32_t idesc;
   int tap_shift[16];
   int tap_plane[16];
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc_full = empty_bar + MAX_STAGES;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + MAX_ACC;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + MAX_ACC);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.nacc; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 8);
     }
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int kb1 = (int)((long long)p.num_kb * (split + 1) / p.split_k);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
         umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
+        if (++acc == p.nacc) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
 
       bool waited = false;
-      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16);
 
       for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 64) {
         const int nbase = n0 + c0;
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) {
+      if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -603,6 +604,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   FVIT_CHECK(stages >= 2, "fvit_gemm: not enough shared memory for 2 stages");
   p.stages = stages;
+  p.acc_stride = tile_n <= 64 ? 64 : (tile_n <= 128 ? 128 : 256);
+  p.nacc = TMEM_COLS / p.acc_stride;
   p.idesc = make_idesc_f16(BM, tile_n, p.a_mn, p.b_mn, a->bf16 ? 1u : 0u);
   for (int i = 0; i < 16; ++i) {
     p.tap_shift[i] = i < a->ntaps ? a->tap_shift[i] : 0;

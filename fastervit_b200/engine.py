@@ -70,7 +70,7 @@ class _Bufs:
 
 class Plan:
     """Static launch list for one (batch, height, width, training) signature."""
-    STEM_LD = 64  # fp16 row width of the stem im2col matrix (27 taps, zero padded to one 128-byte row)
+    STEM_LD = 32  # fp16 row width of the stem im2col matrix (27 taps zero padded to 32; TMA zero-fills the rest of the K block)
 
     def __init__(self, model, B: int, H: int, W: int, training: bool, device):
         self.model, self.B, self.H, self.W, self.training, self.device = model, B, H, W, training, device
