@@ -139,6 +139,10 @@ __device__ __forceinline__ int colsum16_owner_col(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// Epilogue specialisation: GENERIC = every option decided at run time (backward modes, statistics,
+// split-K atomics); otherwise ACT / RESID / O32 / O16 are compile-time and the unused paths vanish
+// (the epilogue is instruction-issue bound, so this is worth ~2.5x on short-K tiles).
+template <bool GENERIC, int ACT, bool RESID, bool O32, bool O16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const __grid_constant__ CUtensorMap tmap_b,
@@ -283,8 +287,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float* stg = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES) + ew * (32 * STG_LD);
     const int sub = lane >> 3;   // row within a 4-row group
     const int c4 = lane & 7;     // which float4 of the 32-column chunk
-    const bool use_resid = p.resid != nullptr && !p.atomic_out;
-    const bool use_aux = (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) && !p.atomic_out;
+    const bool atomic_out = GENERIC && p.atomic_out;
+    const bool use_resid = GENERIC ? (p.resid != nullptr && !p.atomic_out) : RESID;
+    const bool use_aux = GENERIC && (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) && !p.atomic_out;
+    const int act = GENERIC ? p.act : ACT;
+    const bool out32 = GENERIC ? (p.out_f32 != nullptr) : O32;
+    const bool out16 = GENERIC ? (p.out_f16 != nullptr) : O16;
+    const bool stats = GENERIC && p.col_sum != nullptr && !p.atomic_out;
+    const bool has_cs2 = GENERIC && p.col_scale2 != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -357,8 +367,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (cany) {
           if (p.col_scale) cs = ld_vec4_guard(p.col_scale + col, n_end - col, 1.f);
           if (p.col_shift) sh = ld_vec4_guard(p.col_shift + col, n_end - col, 0.f);
-          if (p.col_scale2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
+          if (has_cs2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
         }
+        cs.x *= p.alpha, cs.y *= p.alpha, cs.z *= p.alpha, cs.w *= p.alpha;  // fold alpha
         // ---- 2. accumulators: TMEM -> registers -> staging tile
         if (!waited) {
           mbar_wait(&acc_full[acc], acc_phase);
@@ -393,8 +404,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const int rl = 4 * k + sub;  // row within the warp's 32
           const bool ok = cany && orow[k] >= 0;
           float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + 4 * c4);
-          v.x *= p.alpha, v.y *= p.alpha, v.z *= p.alpha, v.w *= p.alpha;
-          if (p.atomic_out) {
+          if (atomic_out) {
+            v.x *= p.alpha, v.y *= p.alpha, v.z *= p.alpha, v.w *= p.alpha;
             if (ok) {
               float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
               atomicAdd(o, v.x);
@@ -406,19 +417,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           v.x = fmaf(v.x, cs.x, sh.x), v.y = fmaf(v.y, cs.y, sh.y), v.z = fmaf(v.z, cs.z, sh.z),
           v.w = fmaf(v.w, cs.w, sh.w);
-          if (p.col_sum && ok) {
+          if (stats && ok) {
             s1.x += v.x, s1.y += v.y, s1.z += v.z, s1.w += v.w;
             s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
           }
           if (!ok) continue;
-          if (p.act == FVIT_ACT_RELU) {
+          if (act == FVIT_ACT_RELU) {
             v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
-          } else if (p.act == FVIT_ACT_GELU) {
+          } else if (act == FVIT_ACT_GELU) {
             v.x = gelu_erf(v.x), v.y = gelu_erf(v.y), v.z = gelu_erf(v.z), v.w = gelu_erf(v.w);
           } else if (use_aux) {
             float a[4];
             unpack4_16(av[k], p.bf16, a);
-            if (p.act == FVIT_ACT_GELU_BWD) {
+            if (act == FVIT_ACT_GELU_BWD) {
               v.x *= gelu_erf_grad(a[0]), v.y *= gelu_erf_grad(a[1]), v.z *= gelu_erf_grad(a[2]),
               v.w *= gelu_erf_grad(a[3]);
             } else {
@@ -426,9 +437,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               v.w = a[3] > 0.f ? v.w : 0.f;
             }
           }
-          v.x *= cs2.x, v.y *= cs2.y, v.z *= cs2.z, v.w *= cs2.w;
+          if (has_cs2) v.x *= cs2.x, v.y *= cs2.y, v.z *= cs2.z, v.w *= cs2.w;
           if (use_resid) v.x += rv[k].x, v.y += rv[k].y, v.z += rv[k].z, v.w += rv[k].w;
-          if (p.out_f32) {
+          if (out32) {
             float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
             if (cfull && p.vec_ok) {
               *reinterpret_cast<float4*>(o) = v;
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if (col + 3 < n_end) o[3] = v.w;
             }
           }
-          if (p.out_f16) {
+          if (out16) {
             uint16_t* o = reinterpret_cast<uint16_t*>(p.out_f16) + orow[k] * p.ld_o16 + col;
             const uint32_t lo = pack2_16(v.x, v.y, p.bf16), hi = pack2_16(v.z, v.w, p.bf16);
             if (cfull && p.vec_ok) {
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
         __syncwarp();
-        if (p.col_sum && !p.atomic_out) {
+        if (stats) {
           // lanes sharing c4 (lane, lane^8, lane^16, lane^24) hold partial sums of the same 4 columns
 #pragma unroll
           for (int o = 8; o <= 16; o <<= 1) {
@@ -662,14 +673,32 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (rc) return rc;
 
   const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVIT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   SMEM_BUDGET));
-    attr_set = true;
-  }
   const long long work = (long long)p.tiles_m * p.tiles_n * p.split_k;
   const int grid = (int)(work < sms ? work : sms);
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tma, tmb, p);
-  return post_launch("gemm_tcgen05_kernel");
+  const bool generic = p.atomic_out || a->col_sum || a->col_scale2 || a->aux || a->act > FVIT_ACT_GELU;
+  const bool resid = a->resid != nullptr, o32 = a->out_f32 != nullptr, o16 = a->out_f16 != nullptr;
+#define FVIT_GEMM_LAUNCH(GEN, ACTV, RES, O32V, O16V)                                                   \
+  do {                                                                                                 \
+    auto kfn = gemm_tcgen05_kernel<GEN, ACTV, RES, O32V, O16V>;                                        \
+    static bool attr_set = false;                                                                      \
+    if (!attr_set) {                                                                                   \
+      FVIT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));  \
+      attr_set = true;                                                                                 \
+    }                                                                                                  \
+    kfn<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tma, tmb, p);                        \
+    return post_launch("gemm_tcgen05_kernel");                                                         \
+  } while (0)
+  if (!generic) {
+    const int act = a->act;
+    if (act == FVIT_ACT_NONE && !resid && !o32 && o16) FVIT_GEMM_LAUNCH(false, 0, false, false, true);   // qkv
+    if (act == FVIT_ACT_GELU && !resid && !o32 && o16) FVIT_GEMM_LAUNCH(false, 2, false, false, true);   // fc1, conv1
+    if (act == FVIT_ACT_RELU && !resid && !o32 && o16) FVIT_GEMM_LAUNCH(false, 1, false, false, true);   // stem conv1
+    if (act == FVIT_ACT_RELU && !resid && o32 && o16) FVIT_GEMM_LAUNCH(false, 1, false, true, true);     // stem conv2
+    if (act == FVIT_ACT_NONE && resid && o32 && !o16) FVIT_GEMM_LAUNCH(false, 0, true, true, false);     // proj, fc2
+    if (act == FVIT_ACT_NONE && resid && o32 && o16) FVIT_GEMM_LAUNCH(false, 0, true, true, true);       // conv2
+    if (act == FVIT_ACT_NONE && !resid && o32 && !o16) FVIT_GEMM_LAUNCH(false, 0, false, true, false);   // downsample, head
+    if (act == FVIT_ACT_NONE && !resid && o32 && o16) FVIT_GEMM_LAUNCH(false, 0, false, true, true);     // downsample -> conv level
+  }
+  FVIT_GEMM_LAUNCH(true, 0, false, false, false);
+#undef FVIT_GEMM_LAUNCH
 }
