@@ -72,6 +72,10 @@ struct GemmParams {
   long long ld_o16;
   float* col_sum;
   float* col_sumsq;
+  const float* alpha_ptr;   // optional device scalar multiplied into alpha
+  const float* row_scale;   // optional fp32 [m] factor applied with col_scale2 (after act)
+  void* out_pre16;          // optional fp16 copy of the value before col_scale2 / row_scale / resid
+  long long ld_pre16;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -295,6 +299,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool out16 = GENERIC ? (p.out_f16 != nullptr) : O16;
     const bool stats = GENERIC && p.col_sum != nullptr && !p.atomic_out;
     const bool has_cs2 = GENERIC && p.col_scale2 != nullptr;
+    const bool has_rs = GENERIC && p.row_scale != nullptr;
+    const bool has_pre = GENERIC && p.out_pre16 != nullptr;
+    const float alpha = (GENERIC && p.alpha_ptr) ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (p.col_shift) sh = ld_vec4_guard(p.col_shift + col, n_end - col, 0.f);
           if (has_cs2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
         }
-        cs.x *= p.alpha, cs.y *= p.alpha, cs.z *= p.alpha, cs.w *= p.alpha;  // fold alpha
+        cs.x *= alpha, cs.y *= alpha, cs.z *= alpha, cs.w *= alpha;  // fold alpha
         // ---- 2. accumulators: TMEM -> registers -> staging tile
         if (!waited) {
           mbar_wait(&acc_full[acc], acc_phase);
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const bool ok = cany && orow[k] >= 0;
           float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + 4 * c4);
           if (atomic_out) {
-            v.x *= p.alpha, v.y *= p.alpha, v.z *= p.alpha, v.w *= p.alpha;
+            v.x *= alpha, v.y *= alpha, v.z *= alpha, v.w *= alpha;
             if (ok) {
               float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
               atomicAdd(o, v.x);
@@ -422,6 +429,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
           }
           if (!ok) continue;
+          if (has_pre) {
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out_pre16) + (long long)(row_base + rl) * p.ld_pre16 + col;
+            const uint32_t lo = pack2_16(v.x, v.y, p.bf16), hi = pack2_16(v.z, v.w, p.bf16);
+            if (cfull && p.vec_ok) {
+              *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
+            } else {
+              o[0] = (uint16_t)(lo & 0xFFFF);
+              if (col + 1 < n_end) o[1] = (uint16_t)(lo >> 16);
+              if (col + 2 < n_end) o[2] = (uint16_t)(hi & 0xFFFF);
+              if (col + 3 < n_end) o[3] = (uint16_t)(hi >> 16);
+            }
+          }
           if (act == FVIT_ACT_RELU) {
             v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
           } else if (act == FVIT_ACT_GELU) {
@@ -438,6 +457,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
           if (has_cs2) v.x *= cs2.x, v.y *= cs2.y, v.z *= cs2.z, v.w *= cs2.w;
+          if (has_rs) {
+            const float rs = __ldg(p.row_scale + row_base + rl);
+            v.x *= rs, v.y *= rs, v.z *= rs, v.w *= rs;
+          }
           if (use_resid) v.x += rv[k].x, v.y += rv[k].y, v.z += rv[k].z, v.w += rv[k].w;
           if (out32) {
             float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
@@ -578,7 +601,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   FVIT_CHECK(a->a && a->b, "fvit_gemm: null operand");
   FVIT_CHECK(a->lda % 8 == 0 && a->ldb % 8 == 0, "fvit_gemm: lda/ldb must be multiples of 8");
   FVIT_CHECK(!(a->a_mn_major && a->ntaps != 1), "fvit_gemm: taps need a K-major A operand");
-  FVIT_CHECK(a->out_f32 || a->out_f16, "fvit_gemm: no output");
+  FVIT_CHECK(a->out_f32 || a->out_f16 || a->out_pre16, "fvit_gemm: no output");
   const int split_k = a->split_k > 1 ? a->split_k : 1;
   if (split_k > 1)
     FVIT_CHECK(a->out_f32 && !a->out_f16 && !a->col_sum, "fvit_gemm: split_k needs out_f32 only");
@@ -639,6 +662,10 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.ld_o16 = a->ld_out_f16;
   p.col_sum = a->col_sum;
   p.col_sumsq = a->col_sumsq;
+  p.alpha_ptr = a->alpha_ptr;
+  p.row_scale = a->row_scale;
+  p.out_pre16 = a->out_pre16;
+  p.ld_pre16 = a->ld_out_pre16;
   // vector path: every touched row segment must be 16-byte aligned
   bool vec = true;
   if (a->out_f32)
@@ -647,6 +674,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
     vec = vec && (a->ld_out_f16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->out_f16) & 15) == 0);
   if (a->resid)
     vec = vec && (a->ld_resid % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->resid) & 15) == 0);
+  if (a->out_pre16)
+    vec = vec && (a->ld_out_pre16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->out_pre16) & 7) == 0);
   if (a->aux)
     vec = vec && (a->ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->aux) & 7) == 0);
   p.vec_ok = vec ? 1 : 0;
@@ -675,7 +704,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES;
   const long long work = (long long)p.tiles_m * p.tiles_n * p.split_k;
   const int grid = (int)(work < sms ? work : sms);
-  const bool generic = p.atomic_out || a->col_sum || a->col_scale2 || a->aux || a->act > FVIT_ACT_GELU;
+  const bool generic = p.atomic_out || a->col_sum || a->col_scale2 || a->aux || a->act > FVIT_ACT_GELU ||
+                       a->alpha_ptr || a->row_scale || a->out_pre16;
   const bool resid = a->resid != nullptr, o32 = a->out_f32 != nullptr, o16 = a->out_f16 != nullptr;
 #define FVIT_GEMM_LAUNCH(GEN, ACTV, RES, O32V, O16V)                                                   \
   do {                                                                                                 \

@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(256)
                   int C, const float* __restrict__ add, int group, int skip, float* __restrict__ wb,
                   long long ldwb, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, __half* __restrict__ out, long long ldo, const int* __restrict__ out_map,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, __half* __restrict__ xhat_out,
+                  long long ldxh) {
   constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
   const int sl = lane % LPR;     // lane within the row group
@@ -319,6 +320,21 @@ __global__ void __launch_bounds__(256)
   if (mean_out && sl == 0) {
     mean_out[r] = mean;
     rstd_out[r] = rstd;
+  }
+  if (xhat_out) {  // normalised (pre-affine) value, saved for the backward pass
+    __half* o = xhat_out + r * ldxh;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int i = sl + LPR * j;
+      if (i < nvec) {
+        const __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd, (v[j].y - mean) * rstd);
+        const __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd, (v[j].w - mean) * rstd);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(o + 4 * i) = pk;
+      }
+    }
   }
   const long long orow = out_map ? out_map[r] : r;
   if (orow >= 0) {
@@ -643,8 +659,10 @@ int fvit_stem_im2col(const float* x, int64_t sb, int64_t sc, int64_t sh, int64_t
 int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows, int32_t C,
                 const float* add, int32_t group, int32_t skip, float* wb, int64_t ldwb,
                 const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
-                const int32_t* out_map, float* mean_out, float* rstd_out, void* stream) {
+                const int32_t* out_map, float* mean_out, float* rstd_out, void* xhat_out, int64_t ldxh,
+                void* stream) {
   FVIT_CHECK(x && gamma && beta && out && rows > 0, "fvit_ln_fwd: bad arguments");
+  FVIT_CHECK(!xhat_out || ldxh % 4 == 0, "fvit_ln_fwd: xhat stride must be a multiple of 4");
   FVIT_CHECK(C % 4 == 0 && C <= 32 * 4 * 16, "fvit_ln_fwd: C=%d unsupported", C);
   FVIT_CHECK(ldx % 4 == 0 && ldo % 4 == 0 && (!wb || ldwb % 4 == 0), "fvit_ln_fwd: unaligned strides");
   FVIT_CHECK(!add || group > 0, "fvit_ln_fwd: add needs group > 0");
@@ -657,7 +675,7 @@ int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows
     const long long grid = (warps + wpb - 1) / wpb;                                                 \
     ln_fwd_kernel<LPR, MAXV><<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(                   \
         x, ldx, in_map, rows, C, add, grp, skip, wb, ldwb, gamma, beta, eps, (__half*)out, ldo,     \
-        out_map, mean_out, rstd_out);                                                               \
+        out_map, mean_out, rstd_out, (__half*)xhat_out, ldxh);                                      \
   } while (0)
   if (nvec <= 16) FVIT_LN_LAUNCH(8, 2);
   else if (nvec <= 32) FVIT_LN_LAUNCH(8, 4);

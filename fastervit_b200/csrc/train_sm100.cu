@@ -1,0 +1,718 @@
+// Training-path kernels (HBM-bound): batch-statistics BatchNorm (forward finalize / apply, backward),
+// per-column reductions (bias / affine / layer-scale gradients), LayerNorm backward, gradient casts.
+// Gradients of activations travel as fp16 tensors multiplied by a power-of-two scale that lives in
+// device memory (grad_scale[0] = S, grad_scale[1] = 1/S); parameter gradients are accumulated in fp32
+// and un-scaled on the fly. Contracts are in include/fvit.h.
+#include <cuda_fp16.h>
+
+#include "../../include/fvit.h"
+#include "common.h"
+
+namespace fvit {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------- column statistics
+// sum[c] += sum_r x[rows[r]][c], sumsq[c] += sum_r x[..]^2 over a row list (fp32 input).
+// Block = 256 threads handles a slab of rows for 64 columns: threadIdx.x & 63 = column, >> 6 = row lane.
+__global__ void colstats_f32_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ rows,
+                                    int nrows, int C, float* __restrict__ sum, float* __restrict__ sumsq) {
+  __shared__ float red[2][4][64];
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    for (int r = blockIdx.x * 4 + rl; r < nrows; r += gridDim.x * 4) {
+      const long long row = rows ? rows[r] : r;
+      const float v = x[row * ldx + c];
+      s += v;
+      q += v * v;
+    }
+  }
+  red[0][rl][threadIdx.x & 63] = s;
+  red[1][rl][threadIdx.x & 63] = q;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    const int k = threadIdx.x & 63;
+    atomicAdd(sum + c, red[0][0][k] + red[0][1][k] + red[0][2][k] + red[0][3][k]);
+    atomicAdd(sumsq + c, red[1][0][k] + red[1][1][k] + red[1][2][k] + red[1][3][k]);
+  }
+}
+
+// BatchNorm2d training-mode finalize (fv.py:459-462, 490-493, 925 with module.training):
+//   mean = sum/n, var = sumsq/n - mean^2 (biased, used to normalise);
+//   running_mean = (1-m) running_mean + m mean ; running_var = (1-m) running_var + m var n/(n-1);
+//   scale = w * rsqrt(var+eps) [* ls] ; shift = (b - mean*scale_raw) [* ls]  -> y = x*scale + shift
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count,
+                                   const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                   float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, const float* __restrict__ ls,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sum[c] / count;
+  float var = sumsq[c] / count - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+  float s = w[c] * rstd, t = b[c] - mean * s;
+  if (ls) {
+    s *= ls[c];
+    t *= ls[c];
+  }
+  scale[c] = s;
+  shift[c] = t;
+  if (mean_out) {
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+  }
+}
+
+// y = act(x16[row]*scale + shift) (+ resid32[row]) for the listed rows; writes fp32 and/or fp16.
+// One thread per (row, 8 channels): 16-byte loads/stores.
+__global__ void affine_rows_kernel(const __half* __restrict__ x, long long ldx, const int* __restrict__ rows,
+                                   int nrows, int C, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, int act, const float* __restrict__ resid,
+                                   long long ldr, float* __restrict__ out32, long long ldo32,
+                                   __half* __restrict__ out16, long long ldo16) {
+  const int c8 = (C + 7) >> 3;
+  const long long total = (long long)nrows * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % c8) * 8;
+    const long long row = rows ? rows[i / c8] : i / c8;
+    float v[8];
+    if (j + 8 <= C) {
+      const uint4 pk = *reinterpret_cast<const uint4*>(x + row * ldx + j);
+      const __half2* h = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[2 * u] = __low2float(h[u]);
+        v[2 * u + 1] = __high2float(h[u]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = j + u < C ? __half2float(x[row * ldx + j + u]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j + u < C) {
+        float y = fmaf(v[u], scale[j + u], shift[j + u]);
+        if (act == FVIT_ACT_RELU) y = fmaxf(y, 0.f);
+        else if (act == FVIT_ACT_GELU) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+        if (resid) y += resid[row * ldr + j + u];
+        v[u] = y;
+      }
+    }
+    if (out32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j + u < C) out32[row * ldo32 + j + u] = v[u];
+    }
+    if (out16) {
+      if (j + 8 <= C) {
+        __half2 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+        *reinterpret_cast<uint4*>(out16 + row * ldo16 + j) = *reinterpret_cast<const uint4*>(h);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j + u < C) out16[row * ldo16 + j + u] = __float2half_rn(v[u]);
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------- gradient scaling
+// gs[0] = S = 2^floor(log2(target / max|x|)), gs[1] = 1/S (single block; x is the loss gradient of the
+// logits). Keeps every fp16 activation gradient inside the normal range without a host round trip.
+__global__ void grad_scale_init_kernel(const float* __restrict__ x, int n, float target, float* __restrict__ gs) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    float S = 1.f;
+    if (m > 0.f && isfinite(m)) S = exp2f(floorf(log2f(target / m)));
+    S = fminf(fmaxf(S, 1.f / 16777216.f), 16777216.f * 65536.f);
+    gs[0] = S;
+    gs[1] = 1.f / S;
+  }
+}
+
+// out[i] = a[i] * b[i]  (tiny vectors of device scalars, e.g. per-branch alpha = inv_scale / branch_scale)
+__global__ void vec_mul_kernel(const float* a, int a_stride, const float* b, int b_stride, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i * a_stride] * b[i * b_stride];
+}
+
+// out[0] = 2^-floor(log2(max|v|)) (power-of-two normaliser of a layer-scale vector), out[1] = 1/out[0]
+__global__ void pow2_norm_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(v[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    float s = 1.f;
+    if (m > 0.f && isfinite(m)) s = exp2f(-floorf(log2f(m)));
+    out[0] = s;
+    out[1] = 1.f / s;
+  }
+}
+
+// out16[r][c] = (half)(x[src(r)][c] * colmul[c] * *scalar)   (fp32 -> fp16 operand cast of a gradient)
+__global__ void cast_scale_f16_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ rows,
+                                      int nrows, int C, const float* __restrict__ colmul,
+                                      const float* __restrict__ scalar, __half* __restrict__ out, long long ldo) {
+  const int c4 = C >> 2;
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  const long long total = (long long)nrows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % c4);
+    const long long r = i / c4;
+    const long long src = rows ? rows[r] : r;
+    float4 v = reinterpret_cast<const float4*>(x + src * ldx)[j];
+    float4 m = make_float4(sc, sc, sc, sc);
+    if (colmul) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(colmul) + j);
+      m.x *= g.x, m.y *= g.y, m.z *= g.z, m.w *= g.w;
+    }
+    const __half2 h0 = __floats2half2_rn(v.x * m.x, v.y * m.y), h1 = __floats2half2_rn(v.z * m.z, v.w * m.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + r * ldo + 4 * j) = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------- column reductions
+// out[c] += *scalar * colmul[c] * sum_r a[ra(r)][c] * (b ? b[rb(r)][c] : 1)
+// a is fp32 (A16 == 0) or fp16; b is fp16. Rows through optional lists (a_rows for a, b indexed by r).
+template <int A16>
+__global__ void colsum_kernel(const void* __restrict__ a, long long lda, const int* __restrict__ a_rows,
+                              const __half* __restrict__ b, long long ldb, int nrows, int C,
+                              const float* __restrict__ colmul, const float* __restrict__ scalar,
+                              float* __restrict__ out) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  float s = 0.f;
+  if (c < C) {
+    for (int r = blockIdx.x * 4 + rl; r < nrows; r += gridDim.x * 4) {
+      const long long ra = a_rows ? a_rows[r] : r;
+      float v = A16 ? __half2float(reinterpret_cast<const __half*>(a)[ra * lda + c])
+                    : reinterpret_cast<const float*>(a)[ra * lda + c];
+      if (b) v *= __half2float(b[(long long)r * ldb + c]);
+      s += v;
+    }
+  }
+  red[rl][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    const int k = threadIdx.x & 63;
+    float t = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+    if (colmul) t *= colmul[c];
+    if (scalar) t *= __ldg(scalar);
+    atomicAdd(out + c, t);
+  }
+}
+
+// out[(t - skip)][c] += *scalar * sum_w a[w*group + t][c]  for skip <= t < group (gradient of a
+// positional embedding that was broadcast-added to every group; fp32 input)
+__global__ void group_sum_kernel(const float* __restrict__ a, long long lda, int ngroups, int group, int skip,
+                                 int C, const float* __restrict__ scalar, float* __restrict__ out) {
+  const int t = blockIdx.x + skip;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int w = blockIdx.z; w < ngroups; w += gridDim.z) s += a[((long long)w * group + t) * lda + c];
+  if (scalar) s *= __ldg(scalar);
+  atomicAdd(out + (long long)(t - skip) * C + c, s);
+}
+
+// ---------------------------------------------------------------------------------- LayerNorm backward
+// For row r (the LayerNorm's r-th input v_r, whose forward gathered it from in_map[r] and wrote it back
+// to row r):  gv = g[r] + rstd * (gam*dy - mean_c(gam*dy) - xhat * mean_c(gam*dy*xhat));
+//             g[in_map[r]] = gv (and g[r] = 0 when the source is another row); dgamma += dy*xhat, dbeta += dy.
+// `use_g` = 0 starts from zero instead of g[r] (first consumer of a freshly produced tensor).
+// One warp per row; per-CTA partial sums of dgamma/dbeta in shared memory, then one atomicAdd per column.
+__global__ void __launch_bounds__(256)
+    ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
+                  const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, int rows, int C, float* __restrict__ g, long long ldg,
+                  const int* __restrict__ in_map, int use_g, const float* __restrict__ scalar,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sh[];  // [warps][2][C]: private per-warp partial sums (lane owns column c)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* sg = sh + (size_t)warp * 2 * C;
+  float* sb = sg + C;
+  for (int c = lane; c < C; c += 32) {
+    sg[c] = 0.f;
+    sb[c] = 0.f;
+  }
+  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    const long long rdy = dy_map ? dy_map[r] : r;
+    if (rdy < 0) continue;  // warp-uniform
+    const __half* dyr = dy + rdy * lddy;
+    const __half* xr = xhat + (long long)r * ldxh;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = __half2float(dyr[c]), xh = __half2float(xr[c]);
+      const float gd = d * __ldg(gamma + c);
+      s1 += gd;
+      s2 += gd * xh;
+      sg[c] += d * xh;
+      sb[c] += d;
+    }
+    s1 = warp_sum_t(s1) / C;
+    s2 = warp_sum_t(s2) / C;
+    const float rs = rstd[r];
+    const long long src = in_map ? in_map[r] : r;
+    float* gr = g + (long long)r * ldg;
+    float* gs_ = g + src * ldg;
+    for (int c = lane; c < C; c += 32) {
+      const float d = __half2float(dyr[c]), xh = __half2float(xr[c]);
+      float v = rs * (d * __ldg(gamma + c) - s1 - xh * s2);
+      if (use_g) v += gr[c];
+      if (src != r) gr[c] = 0.f;
+      gs_[c] = v;
+    }
+  }
+  __syncthreads();
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      a += sh[(size_t)w * 2 * C + c];
+      b += sh[(size_t)w * 2 * C + C + c];
+    }
+    atomicAdd(dgamma + c, a * sc);
+    atomicAdd(dbeta + c, b * sc);
+  }
+}
+
+// ---------------------------------------------------------------------------------- attention backward
+// One CTA per (group of S tokens, head), fp32 math, generic in S / head_dim. Recomputes P from q, k, bias;
+// dV = P^T dO ; dP = dO V^T ; dS = P o (dP - rowsum(P o dP)) ; dQ = scale dS K ; dK = scale dS^T Q ;
+// dbias[h] += dS. Gradients in / out are fp16 (scaled); dbias fp32 atomics (scaled).
+__global__ void attn_bwd_simt_kernel(const __half* __restrict__ qkv, long long ldq, const __half* __restrict__ dout,
+                                     long long lddo, int S, int hd, int hdp, int heads,
+                                     const float* __restrict__ bias, float scale, __half* __restrict__ dqkv,
+                                     long long lddq, float* __restrict__ dbias) {
+  extern __shared__ float sm[];
+  const int hp = hd + 1;
+  float* sq = sm;                // [S][hd+1]
+  float* sk = sq + S * hp;
+  float* sv = sk + S * hp;
+  float* so = sv + S * hp;       // dO
+  float* sp = so + S * hp;       // [S][S+1]  P, then dS
+  float* rd = sp + S * (S + 1);  // [S] rowdot
+  const int g = blockIdx.x / heads, h = blockIdx.x % heads;
+  const long long row0 = (long long)g * S;
+  const int Cp = heads * hdp;
+  for (int i = threadIdx.x; i < S * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const __half* base = qkv + (row0 + t) * ldq + h * hdp + d;
+    sq[t * hp + d] = __half2float(base[0]);
+    sk[t * hp + d] = __half2float(base[Cp]);
+    sv[t * hp + d] = __half2float(base[2 * Cp]);
+    so[t * hp + d] = __half2float(dout[(row0 + t) * lddo + h * hdp + d]);
+  }
+  __syncthreads();
+  const float* bh = bias ? bias + (long long)h * S * S : nullptr;
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+    const int r = i / S, c = i % S;
+    float a = 0.f;
+    for (int d = 0; d < hd; ++d) a = fmaf(sq[r * hp + d], sk[c * hp + d], a);
+    sp[r * (S + 1) + c] = a * scale + (bh ? bh[i] : 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < S; r += nwarps) {  // softmax rows
+    float* pr = sp + r * (S + 1);
+    float m = -INFINITY;
+    for (int c = lane; c < S; c += 32) m = fmaxf(m, pr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < S; c += 32) {
+      const float e = __expf(pr[c] - m);
+      pr[c] = e;
+      s += e;
+    }
+    s = warp_sum_t(s);
+    const float inv = 1.f / s;
+    for (int c = lane; c < S; c += 32) pr[c] *= inv;
+  }
+  __syncthreads();
+  // dV[c][d] = sum_r P[r][c] dO[r][d]  -> write out immediately
+  for (int i = threadIdx.x; i < S * hd; i += blockDim.x) {
+    const int c = i / hd, d = i % hd;
+    float a = 0.f;
+    for (int r = 0; r < S; ++r) a = fmaf(sp[r * (S + 1) + c], so[r * hp + d], a);
+    dqkv[(row0 + c) * lddq + 2 * Cp + h * hdp + d] = __float2half_rn(a);
+  }
+  // rowdot[r] = sum_c P[r][c] * (dO[r] . V[c])
+  for (int r = warp; r < S; r += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < S; c += 32) {
+      float dp = 0.f;
+      for (int d = 0; d < hd; ++d) dp = fmaf(so[r * hp + d], sv[c * hp + d], dp);
+      acc = fmaf(sp[r * (S + 1) + c], dp, acc);
+    }
+    acc = warp_sum_t(acc);
+    if (lane == 0) rd[r] = acc;
+  }
+  __syncthreads();
+  // dS overwrites P
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+    const int r = i / S, c = i % S;
+    float dp = 0.f;
+    for (int d = 0; d < hd; ++d) dp = fmaf(so[r * hp + d], sv[c * hp + d], dp);
+    const float ds = sp[r * (S + 1) + c] * (dp - rd[r]);
+    sp[r * (S + 1) + c] = ds;
+    if (dbias) atomicAdd(dbias + (long long)h * S * S + i, ds);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    float aq = 0.f, ak = 0.f;
+    for (int c = 0; c < S; ++c) {
+      aq = fmaf(sp[t * (S + 1) + c], sk[c * hp + d], aq);   // dQ[t] = sum_c dS[t][c] K[c]
+      ak = fmaf(sp[c * (S + 1) + t], sq[c * hp + d], ak);   // dK[t] = sum_r dS[r][t] Q[r]
+    }
+    dqkv[(row0 + t) * lddq + h * hdp + d] = __float2half_rn(aq * scale);
+    dqkv[(row0 + t) * lddq + Cp + h * hdp + d] = __float2half_rn(ak * scale);
+  }
+  // zero the head-padding columns so padded weight-gradient GEMMs see exact zeros
+  for (int i = threadIdx.x; i < S * (hdp - hd); i += blockDim.x) {
+    const int t = i / (hdp - hd), d = hd + i % (hdp - hd);
+#pragma unroll
+    for (int w3 = 0; w3 < 3; ++w3) dqkv[(row0 + t) * lddq + w3 * Cp + h * hdp + d] = __float2half_rn(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------- small helpers
+// dst[r][(c/hdp)*hd + c%hdp] (+)= *scalar * src[r][c] for c%hdp < hd (pad_cols) or rows likewise (pad_rows):
+// un-pads head-padded gradient matrices into the parameter-gradient layout.
+__global__ void unpad_heads_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst,
+                                   long long ldd, int rows_src, int cols_src, int hd, int hdp, int pad_rows,
+                                   int pad_cols, const float* __restrict__ scalar) {
+  const long long total = (long long)rows_src * cols_src;
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_src), c = (int)(i % cols_src);
+    int dr = r, dc = c;
+    if (pad_rows) {
+      if (r % hdp >= hd) continue;
+      dr = (r / hdp) * hd + r % hdp;
+    }
+    if (pad_cols) {
+      if (c % hdp >= hd) continue;
+      dc = (c / hdp) * hd + c % hdp;
+    }
+    dst[(long long)dr * ldd + dc] += src[(long long)r * lds + c] * sc;
+  }
+}
+
+// d table[idx][h] += *scalar * dbias[h][r][c] * b (1 - b/16) with b = bias[h][r][c] = 16 sigmoid(table[idx][h])
+// for r, c >= ng (backward of fvit_attn_bias_fwd; fv.py:276-299)
+__global__ void attn_bias_bwd_kernel(const float* __restrict__ dbias, const float* __restrict__ bias,
+                                     const long long* __restrict__ index, int heads, int S, int L,
+                                     const float* __restrict__ scalar, float* __restrict__ dtable) {
+  const int ng = S - L;
+  const long long total = (long long)heads * L * L;
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % L), r = (int)((i / L) % L), h = (int)(i / ((long long)L * L));
+    const long long off = ((long long)h * S + r + ng) * S + c + ng;
+    const float b = bias[off];
+    const float dz = dbias[off] * b * (1.f - b * (1.f / 16.f)) * sc;
+    atomicAdd(dtable + index[(long long)r * L + c] * heads + h, dz);
+  }
+}
+
+// Backward of fvit_cpb_mlp_fwd: dout [P, D] (fp32), hidden [P, 512] saved ->
+//   dw1[d][j] += dout[p][d] * hid[p][j] ; dhid[p][j] = (hid > 0) * sum_d dout[p][d] w1[d][j] ;
+//   dw0[j][k] += dhid[p][j] * coords[p][k] ; db0[j] += dhid[p][j]. One CTA per point p.
+__global__ void cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w1,
+                                   const float* __restrict__ hidden, const float* __restrict__ dout, int D,
+                                   const float* __restrict__ scalar, float* __restrict__ dw0,
+                                   float* __restrict__ db0, float* __restrict__ dw1) {
+  extern __shared__ float sd[];  // dout row [D]
+  const int p = blockIdx.x;
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) sd[d] = dout[(long long)p * D + d] * sc;
+  __syncthreads();
+  const float c0 = coords[2 * p], c1 = coords[2 * p + 1];
+  for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+    const float hv = hidden[(long long)p * 512 + j];
+    float dh = 0.f;
+    for (int d = 0; d < D; ++d) {
+      dh = fmaf(sd[d], w1[(long long)d * 512 + j], dh);
+      atomicAdd(dw1 + (long long)d * 512 + j, sd[d] * hv);
+    }
+    if (hv > 0.f) {
+      atomicAdd(dw0 + 2 * j, dh * c0);
+      atomicAdd(dw0 + 2 * j + 1, dh * c1);
+      atomicAdd(db0 + j, dh);
+    }
+  }
+}
+
+// Backward of the head: y[b,t,c] = xhat*w + beta with batch statistics, pooled[b,c] = mean_t y.
+// reduce: s1[c] = sum_b dp[b,c] ; s2[c] = sum_b dp[b,c]/T * sum_t xhat[b,t,c]   (dp = d pooled, scaled)
+__global__ void pool_bn_bwd_reduce_kernel(const float* __restrict__ xs, long long ldx, const int* __restrict__ rows,
+                                          int B, int T, int C, const float* __restrict__ mean,
+                                          const float* __restrict__ rstd, const float* __restrict__ dpool,
+                                          long long lddp, float* __restrict__ s1, float* __restrict__ s2) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a1 = 0.f, a2 = 0.f;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float d = dpool[(long long)b * lddp + c];
+    float sx = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const long long row = rows ? rows[(long long)b * T + t] : (long long)b * T + t;
+      sx += (xs[row * ldx + c] - mean[c]) * rstd[c];
+    }
+    a1 += d;
+    a2 += d / T * sx;
+  }
+  atomicAdd(s1 + c, a1);
+  atomicAdd(s2 + c, a2);
+}
+// apply: g[row(b,t)][c] = w*rstd*(dp[b,c]/T - s1/N - xhat*s2/N) ; dw = s2 * inv, dbeta = s1 * inv (block 0)
+__global__ void pool_bn_bwd_apply_kernel(const float* __restrict__ xs, long long ldx, const int* __restrict__ rows,
+                                         int B, int T, int C, const float* __restrict__ mean,
+                                         const float* __restrict__ rstd, const float* __restrict__ w,
+                                         const float* __restrict__ dpool, long long lddp,
+                                         const float* __restrict__ s1, const float* __restrict__ s2,
+                                         const float* __restrict__ scalar, float* __restrict__ g, long long ldg,
+                                         float* __restrict__ dw, float* __restrict__ dbeta) {
+  const long long total = (long long)B * T * C;
+  const float N = (float)B * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bt = i / C;
+    const int b = (int)(bt / T);
+    const long long row = rows ? rows[bt] : bt;
+    const float xh = (xs[row * ldx + c] - mean[c]) * rstd[c];
+    g[row * ldg + c] = w[c] * rstd[c] * (dpool[(long long)b * lddp + c] / T - s1[c] / N - xh * s2[c] / N);
+  }
+  if (blockIdx.x == 0) {
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dw[c] += s2[c] * sc;
+      dbeta[c] += s1[c] * sc;
+    }
+  }
+}
+
+static inline int grid_cap(long long total, int block, int per_sm) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace fvit
+
+using namespace fvit;
+
+extern "C" {
+
+int fvit_colstats_f32(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C, float* sum,
+                      float* sumsq, void* stream) {
+  FVIT_CHECK(x && sum && sumsq && nrows > 0 && C > 0, "fvit_colstats_f32: bad arguments");
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  colstats_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, nrows, C, sum, sumsq);
+  return post_launch("colstats_f32_kernel");
+}
+
+int fvit_bn_finalize(const float* sum, const float* sumsq, float count, const float* w, const float* b, float eps,
+                     float momentum, float* running_mean, float* running_var, const float* layer_scale,
+                     float* scale, float* shift, float* mean_out, float* rstd_out, int32_t C, void* stream) {
+  FVIT_CHECK(sum && sumsq && w && b && scale && shift && C > 0 && count > 0, "fvit_bn_finalize: bad arguments");
+  FVIT_CHECK((running_mean == nullptr) == (running_var == nullptr), "fvit_bn_finalize: running stats come in pairs");
+  FVIT_CHECK((mean_out == nullptr) == (rstd_out == nullptr), "fvit_bn_finalize: mean/rstd outputs come in pairs");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      sum, sumsq, count, w, b, eps, momentum, running_mean, running_var, layer_scale, scale, shift, mean_out,
+      rstd_out, C);
+  return post_launch("bn_finalize_kernel");
+}
+
+int fvit_affine_rows(const void* x16, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
+                     const float* scale, const float* shift, int32_t act, const float* resid, int64_t ldr,
+                     float* out32, int64_t ldo32, void* out16, int64_t ldo16, void* stream) {
+  FVIT_CHECK(x16 && scale && shift && nrows > 0 && C > 0 && (out32 || out16), "fvit_affine_rows: bad arguments");
+  FVIT_CHECK(ldx % 8 == 0 && (!out16 || ldo16 % 8 == 0), "fvit_affine_rows: fp16 strides must be multiples of 8");
+  const long long total = (long long)nrows * ((C + 7) / 8);
+  affine_rows_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x16, ldx, rows, nrows, C, scale, shift, act, resid, ldr, out32, ldo32, (__half*)out16, ldo16);
+  return post_launch("affine_rows_kernel");
+}
+
+int fvit_grad_scale_init(const float* x, int32_t n, float target, float* gs, void* stream) {
+  FVIT_CHECK(x && gs && n > 0 && target > 0, "fvit_grad_scale_init: bad arguments");
+  grad_scale_init_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, target, gs);
+  return post_launch("grad_scale_init_kernel");
+}
+
+int fvit_vec_mul(const float* a, int32_t a_stride, const float* b, int32_t b_stride, float* out, int32_t n,
+                 void* stream) {
+  FVIT_CHECK(a && b && out && n > 0, "fvit_vec_mul: bad arguments");
+  vec_mul_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(a, a_stride, b, b_stride, out, n);
+  return post_launch("vec_mul_kernel");
+}
+
+int fvit_pow2_norm(const float* v, int32_t n, float* out, void* stream) {
+  FVIT_CHECK(v && out && n > 0, "fvit_pow2_norm: bad arguments");
+  pow2_norm_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(v, n, out);
+  return post_launch("pow2_norm_kernel");
+}
+
+int fvit_cast_scale_f16(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
+                        const float* colmul, const float* scalar, void* out, int64_t ldo, void* stream) {
+  FVIT_CHECK(x && out && nrows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0,
+             "fvit_cast_scale_f16: bad arguments");
+  const long long total = (long long)nrows * (C / 4);
+  cast_scale_f16_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, rows, nrows, C, colmul, scalar, (__half*)out, ldo);
+  return post_launch("cast_scale_f16_kernel");
+}
+
+int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_rows, const void* b16, int64_t ldb,
+                int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, void* stream) {
+  FVIT_CHECK(a && out && nrows > 0 && C > 0, "fvit_colsum: bad arguments");
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  if (a_is_f16)
+    colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
+                                                             colmul, scalar, out);
+  else
+    colsum_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
+                                                             colmul, scalar, out);
+  return post_launch("colsum_kernel");
+}
+
+int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, int32_t skip, int32_t C,
+                   const float* scalar, float* out, void* stream) {
+  FVIT_CHECK(a && out && ngroups > 0 && group > skip && skip >= 0 && C > 0, "fvit_group_sum: bad arguments");
+  int z = ngroups < 32 ? ngroups : 32;
+  dim3 grid((unsigned)(group - skip), (unsigned)((C + 127) / 128), (unsigned)z);
+  group_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, lda, ngroups, group, skip, C, scalar, out);
+  return post_launch("group_sum_kernel");
+}
+
+int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const void* xhat16, int64_t ldxh,
+                const float* rstd, const float* gamma, int32_t rows, int32_t C, float* g, int64_t ldg,
+                const int32_t* in_map, int32_t use_g, const float* scalar, float* dgamma, float* dbeta,
+                void* stream) {
+  FVIT_CHECK(dy16 && xhat16 && rstd && gamma && g && dgamma && dbeta && rows > 0 && C > 0,
+             "fvit_ln_bwd: bad arguments");
+  const int block = 256, wpb = 8;
+  long long grid = ((long long)rows + wpb - 1) / wpb;
+  const long long cap = (long long)num_sms() * 8;
+  if (grid > cap) grid = cap;
+  const size_t smem = (size_t)wpb * 2 * C * sizeof(float);
+  static bool configured = false;
+  if (smem > 48 * 1024 && !configured) {
+    FVIT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  ln_bwd_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
+      (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
+      scalar, dgamma, dbeta);
+  return post_launch("ln_bwd_kernel");
+}
+
+int fvit_attn_core_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, int32_t groups, int32_t S,
+                       int32_t heads, int32_t head_dim, int32_t hdp, const float* bias, float scale, void* dqkv,
+                       int64_t lddq, float* dbias, void* stream) {
+  FVIT_CHECK(qkv && dout && dqkv && groups > 0 && S > 0 && heads > 0 && head_dim > 0 && hdp >= head_dim,
+             "fvit_attn_core_bwd: bad arguments");
+  const size_t smem = ((size_t)4 * S * (head_dim + 1) + (size_t)S * (S + 1) + S) * sizeof(float);
+  FVIT_CHECK(smem <= 227 * 1024, "fvit_attn_core_bwd: S=%d head_dim=%d needs %zu B of shared memory", S, head_dim,
+             smem);
+  static bool configured = false;
+  if (smem > 48 * 1024 && !configured) {
+    FVIT_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  attn_bwd_simt_kernel<<<(unsigned)((long long)groups * heads), 256, smem, (cudaStream_t)stream>>>(
+      (const __half*)qkv, ldq, (const __half*)dout, lddo, S, head_dim, hdp, heads, bias, scale, (__half*)dqkv, lddq,
+      dbias);
+  return post_launch("attn_bwd_simt_kernel");
+}
+
+int fvit_unpad_heads_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t rows_src, int32_t cols_src,
+                         int32_t hd, int32_t hdp, int32_t pad_rows, int32_t pad_cols, const float* scalar,
+                         void* stream) {
+  FVIT_CHECK(src && dst && rows_src > 0 && cols_src > 0 && hd > 0 && hdp >= hd, "fvit_unpad_heads_f32: bad arguments");
+  const long long total = (long long)rows_src * cols_src;
+  unpad_heads_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows_src, cols_src,
+                                                                                  hd, hdp, pad_rows, pad_cols, scalar);
+  return post_launch("unpad_heads_kernel");
+}
+
+int fvit_attn_bias_bwd(const float* dbias, const float* bias, const int64_t* index, int32_t heads, int32_t S,
+                       int32_t L, const float* scalar, float* dtable, void* stream) {
+  FVIT_CHECK(dbias && bias && index && dtable && heads > 0 && S >= L && L > 0, "fvit_attn_bias_bwd: bad arguments");
+  const long long total = (long long)heads * L * L;
+  attn_bias_bwd_kernel<<<grid_cap(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      dbias, bias, (const long long*)index, heads, S, L, scalar, dtable);
+  return post_launch("attn_bias_bwd_kernel");
+}
+
+int fvit_cpb_mlp_bwd(const float* coords, int32_t P, const float* w1, const float* hidden, const float* dout,
+                     int32_t D, const float* scalar, float* dw0, float* db0, float* dw1, void* stream) {
+  FVIT_CHECK(coords && w1 && hidden && dout && dw0 && db0 && dw1 && P > 0 && D > 0, "fvit_cpb_mlp_bwd: bad arguments");
+  cpb_mlp_bwd_kernel<<<P, 256, D * sizeof(float), (cudaStream_t)stream>>>(coords, P, w1, hidden, dout, D, scalar, dw0,
+                                                                         db0, dw1);
+  return post_launch("cpb_mlp_bwd_kernel");
+}
+
+int fvit_pool_bn_bwd(const float* xs, int64_t ldx, const int32_t* rows, int32_t B, int32_t T, int32_t C,
+                     const float* mean, const float* rstd, const float* w, const float* dpool, int64_t lddp,
+                     float* s1, float* s2, const float* scalar, float* g, int64_t ldg, float* dw, float* dbeta,
+                     void* stream) {
+  FVIT_CHECK(xs && mean && rstd && w && dpool && s1 && s2 && g && dw && dbeta && B > 0 && T > 0 && C > 0,
+             "fvit_pool_bn_bwd: bad arguments");
+  FVIT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), (cudaStream_t)stream));
+  FVIT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), (cudaStream_t)stream));
+  dim3 grid((unsigned)(B < 64 ? B : 64), (unsigned)((C + 127) / 128));
+  pool_bn_bwd_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(xs, ldx, rows, B, T, C, mean, rstd, dpool, lddp,
+                                                                    s1, s2);
+  int rc = post_launch("pool_bn_bwd_reduce_kernel");
+  if (rc) return rc;
+  const long long total = (long long)B * T * C;
+  pool_bn_bwd_apply_kernel<<<grid_cap(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      xs, ldx, rows, B, T, C, mean, rstd, w, dpool, lddp, s1, s2, scalar, g, ldg, dw, dbeta);
+  return post_launch("pool_bn_bwd_apply_kernel");
+}
+
+}  // extern "C"

@@ -294,7 +294,7 @@ class Plan:
         src_x = src["x32"] if src["kind"] == "conv" else src["xs"]
         self._op(self.ops, "fvit_ln_fwd", src_x.data_ptr(), Cs, src_rows.data_ptr(), B * Hs * Ws, Cs,
                  None, 1, 0, None, 0, ds.norm.weight.data_ptr(), ds.norm.bias.data_ptr(), float(ds.norm.eps),
-                 planes.data_ptr(), ld, omap.data_ptr(), None, None)
+                 planes.data_ptr(), ld, omap.data_ptr(), None, None, None, 0)
         w16, ldw = self._pack_conv(f"ds{i}.conv", ds.reduction[0])
         if to_conv:
             rmap = self._plane_to_padded_map(f"ds{i}.rmap", B, Ho, Wo)
@@ -509,13 +509,13 @@ class Plan:
                 self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, tl["ct_gather"].data_ptr(), rows_c, Cc,
                          hat_pe.data_ptr() if hat_pe is not None else None, n_ct, 0, ctr_ptr, Cc,
                          blk.hat_norm1.weight.data_ptr(), blk.hat_norm1.bias.data_ptr(), float(blk.hat_norm1.eps),
-                         tl["ctn16"].data_ptr(), Cc, None, None, None)
+                         tl["ctn16"].data_ptr(), Cc, None, None, None, None, 0)
                 hb = self._emit_bias(nm + ".hat_bias", blk.hat_attn.pos_emb_funct, n_ct)
                 self._emit_attention(nm + ".hat_attn", blk.hat_attn, blk.gamma1, rows_c, B, n_ct, tl["ctn16"], Cc,
                                      tl["ctqkv16"], tl["ctao16"], hb, ctr_ptr)
                 self._op(self.ops, "fvit_ln_fwd", ctr_ptr, Cc, None, rows_c, Cc, None, 1, 0, None, 0,
                          blk.hat_norm2.weight.data_ptr(), blk.hat_norm2.bias.data_ptr(), float(blk.hat_norm2.eps),
-                         tl["ctn16"].data_ptr(), Cc, None, None, None)
+                         tl["ctn16"].data_ptr(), Cc, None, None, None, None, 0)
                 self._emit_fc1(nm + ".hat_fc1", blk.hat_mlp.fc1, tl["ctn16"], Cc, rows_c, tl["cth16"])
                 self._emit_branch_out(nm + ".hat_fc2", blk.hat_mlp.fc2, blk.gamma2, tl["cth16"],
                                       tl["cth16"].stride(0), rows_c, ctr_ptr)
@@ -523,13 +523,13 @@ class Plan:
             rows = nW * S
             self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, tl["norm1_gather"].data_ptr() if has_ct else None, rows,
                      Cc, pe.data_ptr(), S, ncw, xs_ptr, Cc, blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(),
-                     float(blk.norm1.eps), tl["xn16"].data_ptr(), Cc, None, None, None)
+                     float(blk.norm1.eps), tl["xn16"].data_ptr(), Cc, None, None, None, None, 0)
             ab = self._emit_bias(nm + ".bias", blk.attn.pos_emb_funct, S)
             self._emit_attention(nm + ".attn", blk.attn, blk.gamma3, rows, nW, S, tl["xn16"], Cc, tl["qkv16"],
                                  tl["ao16"], ab, xs_ptr)
             self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, None, rows, Cc, None, 1, 0, None, 0,
                      blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr(), float(blk.norm2.eps),
-                     tl["xn16"].data_ptr(), Cc, None, None, None)
+                     tl["xn16"].data_ptr(), Cc, None, None, None, None, 0)
             self._emit_fc1(nm + ".fc1", blk.mlp.fc1, tl["xn16"], Cc, rows, tl["h16"])
             self._emit_branch_out(nm + ".fc2", blk.mlp.fc2, blk.gamma4, tl["h16"], tl["h16"].stride(0), rows, xs_ptr)
             if has_ct and blk.last and blk.do_propagation:

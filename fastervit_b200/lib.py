@@ -39,6 +39,8 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int64),
         ("out_f16", C.c_void_p), ("ld_out_f16", C.c_int64),
         ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p),
+        ("alpha_ptr", C.c_void_p), ("row_scale", C.c_void_p),
+        ("out_pre16", C.c_void_p), ("ld_out_pre16", C.c_int64),
     ]
 
 
@@ -85,11 +87,26 @@ _OP_SIGS: dict[str, list] = {
     "fvit_affine_fold": [_P, _P, _I, _P, _P, _P, _P, _F, _P, _P, _P],
     "fvit_stem_conv_fwd": [_P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P, _P, _P],
     "fvit_stem_im2col": [_P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _P],
-    "fvit_ln_fwd": [_P, _L, _P, _I, _I, _P, _I, _I, _P, _L, _P, _P, _F, _P, _L, _P, _P, _P, _P],
+    "fvit_ln_fwd": [_P, _L, _P, _I, _I, _P, _I, _I, _P, _L, _P, _P, _F, _P, _L, _P, _P, _P, _P, _L, _P],
     "fvit_attn_core_fwd": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
     "fvit_attn_tc_fwd": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _L, _P],
     "fvit_cast_headpad_f16": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     "fvit_vec_headpad_f32": [_P, _P, _I, _I, _I, _P],
+    "fvit_colstats_f32": [_P, _L, _P, _I, _I, _P, _P, _P],
+    "fvit_bn_finalize": [_P, _P, _F, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "fvit_affine_rows": [_P, _L, _P, _I, _I, _P, _P, _I, _P, _L, _P, _L, _P, _L, _P],
+    "fvit_grad_scale_init": [_P, _I, _F, _P, _P],
+    "fvit_vec_mul": [_P, _I, _P, _I, _P, _I, _P],
+    "fvit_pow2_norm": [_P, _I, _P, _P],
+    "fvit_cast_scale_f16": [_P, _L, _P, _I, _I, _P, _P, _P, _L, _P],
+    "fvit_colsum": [_P, _I, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P],
+    "fvit_group_sum": [_P, _L, _I, _I, _I, _I, _P, _P, _P],
+    "fvit_ln_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _P, _L, _P, _I, _P, _P, _P, _P],
+    "fvit_attn_core_bwd": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
+    "fvit_unpad_heads_f32": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fvit_attn_bias_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "fvit_cpb_mlp_bwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "fvit_pool_bn_bwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _L, _P, _P, _P],
     "fvit_cpb_mlp_fwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P],
     "fvit_attn_bias_fwd": [_P, _P, _I, _I, _I, _P, _P],
     "fvit_token_init_fwd": [_P, _L, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
@@ -125,7 +142,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
          a_row_off: int = 0, b_row_off: int = 0, split_k: int = 1, tile_n: int = 0,
          alpha: float = 1.0, act: int = ACT_NONE,
          col_scale=None, col_shift=None, col_scale2=None, aux=None, resid=None, row_map=None,
-         out_f32=None, out_f16=None, col_sum=None, col_sumsq=None) -> None:
+         out_f32=None, out_f16=None, col_sum=None, col_sumsq=None, alpha_ptr=None, row_scale=None,
+         out_pre16=None) -> None:
     """Thin functional wrapper over fvit_gemm for 2-D (strided) torch tensors.
 
     K-major operands are [rows, K] tensors, MN-major operands are [K, rows] tensors; only the row
@@ -175,6 +193,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
     if out_f16 is not None:
         g.out_f16, g.ld_out_f16 = out_f16.data_ptr(), out_f16.stride(0)
     g.col_sum, g.col_sumsq = ptr(col_sum), ptr(col_sumsq)
+    g.alpha_ptr, g.row_scale = ptr(alpha_ptr), ptr(row_scale)
+    if out_pre16 is not None:
+        g.out_pre16, g.ld_out_pre16 = out_pre16.data_ptr(), out_pre16.stride(0)
     check(lib.fvit_gemm(C.byref(g), stream_ptr()))
 
 

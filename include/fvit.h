@@ -50,8 +50,9 @@ enum {
  * Operands are 16-bit (fp16, or bf16 when `bf16` != 0), accumulated in fp32 in tensor memory.
  * Epilogue per element:  v = acc * alpha
  *                        v = v * col_scale[n] + col_shift[n]          (each optional)
+ *                        out_pre16[m, n] = (half)v                     (optional: pre-activation copy)
  *                        v = act(v [, aux])                            (FVIT_ACT_*)
- *                        v = v * col_scale2[n]                         (optional, after act)
+ *                        v = v * col_scale2[n] * row_scale[m]          (each optional, after act)
  *                        v += resid[orow, n]                           (optional, fp32)
  *                        out_f32[orow, n] = v ; out_f16[orow, n] = (half)v   (each optional)
  * with orow = row_map ? row_map[m] : m, rows with orow < 0 skipped. If col_sum/col_sumsq are given,
@@ -99,6 +100,13 @@ typedef struct fvit_gemm_args {
   int64_t ld_out_f16;
   float* col_sum;
   float* col_sumsq;
+  /* training-path extras (all optional) */
+  const float* alpha_ptr; /* device scalar multiplied into alpha (gradient un-scaling without a host sync) */
+  const float* row_scale; /* fp32 [m]: v *= row_scale[m] together with col_scale2 (stochastic depth masks,
+                             per-row layer-scale in weight-gradient GEMMs) */
+  void* out_pre16;        /* fp16 [m, n] (indexed by m): value after scale/shift, before act / col_scale2 /
+                             row_scale / resid (pre-GELU activations; un-scaled branch outputs) */
+  int64_t ld_out_pre16;
 } fvit_gemm_args;
 
 int fvit_gemm(const fvit_gemm_args* args, void* stream);
@@ -148,11 +156,13 @@ int fvit_stem_im2col(const float* x, int64_t sb, int64_t sc, int64_t sh, int64_t
  *   v   = x[in_map ? in_map[r] : r] + ( (r % group) >= skip ? add[(r % group) - skip] : 0 )
  *   wb[r] = v (optional fp32 write-back of the updated residual stream)
  *   out[out_map ? out_map[r] : r] = (half)((v - mean) * rstd * gamma + beta)
- * mean_out / rstd_out (optional) receive the row statistics for the backward pass. */
+ * mean_out / rstd_out (optional) receive the row statistics and xhat_out (optional, fp16 [rows, ldxh])
+ * the normalised pre-affine rows for the backward pass. */
 int fvit_ln_fwd(const float* x, int64_t ldx, const int32_t* in_map, int32_t rows, int32_t C,
                 const float* add, int32_t group, int32_t skip, float* wb, int64_t ldwb,
                 const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
-                const int32_t* out_map, float* mean_out, float* rstd_out, void* stream);
+                const int32_t* out_map, float* mean_out, float* rstd_out, void* xhat_out, int64_t ldxh,
+                void* stream);
 
 /* ---- attention core of WindowAttention.forward (fv.py:559-565) on a packed qkv matrix -------------
  * qkv fp16 [groups*S, 3*heads*head_dim] (q | k | v); for every group of S consecutive tokens and every
@@ -168,6 +178,22 @@ int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, 
  * hdp in {32, 64}; out fp16 [groups*S, heads*hdp]; S <= 128. bias fp32 [heads, S, S] or NULL. */
 int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
                      const float* bias, float scale, void* out, int64_t ldo, void* stream);
+
+/* ---- training-mode BatchNorm2d (batch statistics; fv.py:459-462, 490-493, 925 under module.train()) ----
+ * fvit_colstats_f32: sum[c] += sum_r x[rows[r]][c]; sumsq likewise (fp32 input, optional row list).
+ * fvit_bn_finalize : from (sum, sumsq, count) -> biased var for normalisation, running statistics
+ *   update (momentum, unbiased var), epilogue vectors scale = w*rstd*[ls], shift = (b - mean*w*rstd)*[ls],
+ *   and mean / rstd for the backward pass.
+ * fvit_affine_rows : y = act(x16[row]*scale + shift) (+ resid32[row]) over a row list, fp32/fp16 out
+ *   (normalise + ReLU/GELU (+ residual) of a raw convolution output). */
+int fvit_colstats_f32(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C, float* sum,
+                      float* sumsq, void* stream);
+int fvit_bn_finalize(const float* sum, const float* sumsq, float count, const float* w, const float* b, float eps,
+                     float momentum, float* running_mean, float* running_var, const float* layer_scale,
+                     float* scale, float* shift, float* mean_out, float* rstd_out, int32_t C, void* stream);
+int fvit_affine_rows(const void* x16, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
+                     const float* scale, const float* shift, int32_t act, const float* resid, int64_t ldr,
+                     float* out32, int64_t ldo32, void* out16, int64_t ldo16, void* stream);
 
 /* ---- positional MLPs (cpb_mlp: Linear(2,512)+ReLU+Linear(512,D, no bias); fv.py:223-225, 322-324) --
  * out[p][d] for P coordinate pairs; hidden_out (optional, [P,512]) saves the ReLU output. */
@@ -196,6 +222,62 @@ int fvit_propagate_fwd(float* xs, int64_t ldx, const int32_t* src_map, int32_t r
 int fvit_pool_affine_fwd(const float* xs, int64_t ldx, const int32_t* row_map, int32_t B, int32_t T,
                          int32_t C, const float* scale, const float* shift, void* out, int64_t ldo,
                          void* stream);
+
+/* ==== backward pass (fv.py has no backward code: the reference relies on autograd, train.py:879-896) ====
+ * Activation gradients are fp16 tensors (or the fp32 residual-stream gradient) multiplied by a
+ * power-of-two scale S kept in device memory, gs = {S, 1/S}; parameter gradients are fp32, un-scaled by
+ * the `scalar` / alpha_ptr device scalars. Nothing synchronises with the host. */
+/* gs[0] = 2^floor(log2(target / max|x|)), gs[1] = 1/gs[0] (x = d loss / d logits, n elements). */
+int fvit_grad_scale_init(const float* x, int32_t n, float target, float* gs, void* stream);
+/* out[i] = a[i*a_stride] * b[i*b_stride] (vectors of device scalars). */
+int fvit_vec_mul(const float* a, int32_t a_stride, const float* b, int32_t b_stride, float* out, int32_t n,
+                 void* stream);
+/* out = {s, 1/s} with s = 2^-floor(log2(max|v|)) (normaliser of a layer-scale vector gamma, fv.py:637-655,
+ * so that gamma*s is O(1) and fp16 products with gamma = 1e-5 do not underflow). */
+int fvit_pow2_norm(const float* v, int32_t n, float* out, void* stream);
+/* out16[r][c] = (half)(x[rows ? rows[r] : r][c] * colmul[c] * *scalar): tensor-core operand copy of a
+ * fp32 gradient (colmul = layer scale, scalar = its normaliser; both optional). */
+int fvit_cast_scale_f16(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
+                        const float* colmul, const float* scalar, void* out, int64_t ldo, void* stream);
+/* out[c] += *scalar * colmul[c] * sum_r a[a_rows ? a_rows[r] : r][c] * (b16 ? b16[r][c] : 1): bias, LayerNorm /
+ * BatchNorm affine and layer-scale gradients. a is fp32 or fp16 (a_is_f16). */
+int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_rows, const void* b16, int64_t ldb,
+                int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, void* stream);
+/* out[t - skip][c] += *scalar * sum_w a[w*group + t][c], skip <= t < group: gradient of a positional
+ * embedding broadcast-added to every window (fv.py:366). */
+int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, int32_t skip, int32_t C,
+                   const float* scalar, float* out, void* stream);
+/* LayerNorm backward for the forward of fvit_ln_fwd (same row maps): with gv = (use_g ? g[r] : 0) +
+ * rstd[r]*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)):  g[in_map ? in_map[r] : r] = gv (g[r]
+ * cleared when the source is another row); dgamma[c] += *scalar*sum dy*xhat; dbeta[c] += *scalar*sum dy.
+ * dy16 rows through dy_map (rows with dy_map < 0 are skipped). */
+int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const void* xhat16, int64_t ldxh,
+                const float* rstd, const float* gamma, int32_t rows, int32_t C, float* g, int64_t ldg,
+                const int32_t* in_map, int32_t use_g, const float* scalar, float* dgamma, float* dbeta,
+                void* stream);
+/* Backward of the attention core (either forward kernel): recomputes P from q, k, bias; writes dq, dk, dv
+ * (fp16, head-padded layout [rows, 3*heads*hdp], padding columns zero) and accumulates dbias[h][S][S]. */
+int fvit_attn_core_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, int32_t groups, int32_t S,
+                       int32_t heads, int32_t head_dim, int32_t hdp, const float* bias, float scale, void* dqkv,
+                       int64_t lddq, float* dbias, void* stream);
+/* dst (+)= *scalar * src with head padding removed from rows and/or columns (inverse of
+ * fvit_cast_headpad_f16 for gradients). */
+int fvit_unpad_heads_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t rows_src, int32_t cols_src,
+                         int32_t hd, int32_t hdp, int32_t pad_rows, int32_t pad_cols, const float* scalar,
+                         void* stream);
+/* Backward of fvit_attn_bias_fwd: dtable[index][h] += *scalar * dbias * b*(1 - b/16), b = 16 sigmoid(table). */
+int fvit_attn_bias_bwd(const float* dbias, const float* bias, const int64_t* index, int32_t heads, int32_t S,
+                       int32_t L, const float* scalar, float* dtable, void* stream);
+/* Backward of fvit_cpb_mlp_fwd (needs the saved hidden activations): accumulates dw0 [512,2], db0 [512],
+ * dw1 [D,512] from dout [P,D] * *scalar. */
+int fvit_cpb_mlp_bwd(const float* coords, int32_t P, const float* w1, const float* hidden, const float* dout,
+                     int32_t D, const float* scalar, float* dw0, float* db0, float* dw1, void* stream);
+/* Backward of the head's BatchNorm2d (batch statistics) + AdaptiveAvgPool2d(1) (fv.py:953-958): from
+ * dpool [B,C] writes g[row(b,t)] and accumulates the BN weight/bias gradients; s1/s2 are [C] scratch. */
+int fvit_pool_bn_bwd(const float* xs, int64_t ldx, const int32_t* rows, int32_t B, int32_t T, int32_t C,
+                     const float* mean, const float* rstd, const float* w, const float* dpool, int64_t lddp,
+                     float* s1, float* s2, const float* scalar, float* g, int64_t ldg, float* dw, float* dbeta,
+                     void* stream);
 
 #ifdef __cplusplus
 }
