@@ -51,6 +51,25 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __half* __restr
   }
 }
 
+// Explicit-tap variant: dst[r][j][c] for j < ntaps uses source tap taps[j] (no flip):
+//   transpose_io == 0: dst[co][j][ci] = w[co][ci][taps[j]] ; != 0: dst[ci][j][co] = w[co][ci][taps[j]]
+struct TapList { int t[9]; };
+__global__ void pack_conv3x3_taps_kernel(const float* __restrict__ w, __half* __restrict__ dst, int cout, int cin,
+                                         int kc_pad, int transpose_io, int ntaps, TapList taps) {
+  const int rows = transpose_io ? cin : cout;
+  const int inner = transpose_io ? cout : cin;
+  const long long total = (long long)rows * ntaps * kc_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kc_pad);
+    const int j = (int)((i / kc_pad) % ntaps);
+    const int r = (int)(i / ((long long)kc_pad * ntaps));
+    float v = 0.f;
+    if (c < inner) v = transpose_io ? w[((long long)c * cin + r) * 9 + taps.t[j]] : w[((long long)r * cin + c) * 9 + taps.t[j]];
+    dst[i] = __float2half_rn(v);
+  }
+}
+
 // Head-padded packing for the tensor-core attention path: blocks of `hd` rows (pad_rows) and/or
 // columns (pad_cols) of the fp32 source are spread to blocks of `hdp` >= hd with zero fill, e.g. the
 // qkv weight [3*h*hd, C] -> [3*h*hdp, C] and the proj weight [C, h*hd] -> [C, h*hdp].
@@ -608,6 +627,19 @@ int fvit_pack_conv3x3_f16(const float* w, void* dst, int32_t cout, int32_t cin, 
   pack_conv3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       w, (__half*)dst, cout, cin, kc_pad, transpose_io);
   return post_launch("pack_conv3x3_kernel");
+}
+
+int fvit_pack_conv3x3_taps_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,
+                               int32_t transpose_io, int32_t ntaps, int32_t t0, int32_t t1, int32_t t2, int32_t t3,
+                               int32_t t4, int32_t t5, int32_t t6, int32_t t7, int32_t t8, void* stream) {
+  FVIT_CHECK(w && dst && cout > 0 && cin > 0 && ntaps >= 1 && ntaps <= 9, "fvit_pack_conv3x3_taps_f16: bad arguments");
+  FVIT_CHECK(kc_pad >= (transpose_io ? cout : cin), "fvit_pack_conv3x3_taps_f16: kc_pad too small");
+  TapList tl = {{t0, t1, t2, t3, t4, t5, t6, t7, t8}};
+  for (int i = 0; i < ntaps; ++i) FVIT_CHECK(tl.t[i] >= 0 && tl.t[i] < 9, "fvit_pack_conv3x3_taps_f16: bad tap");
+  const long long total = (long long)(transpose_io ? cin : cout) * ntaps * kc_pad;
+  pack_conv3x3_taps_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)dst, cout, cin, kc_pad,
+                                                                                 transpose_io, ntaps, tl);
+  return post_launch("pack_conv3x3_taps_kernel");
 }
 
 int fvit_affine_fold(float* scale, float* shift, int32_t n, const float* bn_w, const float* bn_b,

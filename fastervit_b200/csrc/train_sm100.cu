@@ -532,6 +532,208 @@ __global__ void pool_bn_bwd_apply_kernel(const float* __restrict__ xs, long long
   }
 }
 
+// dst[map[r]][c] += src[r][c]  (fp32; map entries < 0 skipped). Carrier-token gradient back to the window
+// layout (ct_dewindow backward).
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst,
+                                        long long ldd, const int* __restrict__ map, int rows, int C) {
+  const int c4 = C >> 2;
+  const long long total = (long long)rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % c4);
+    const long long r = i / c4;
+    const int d = map[r];
+    if (d < 0) continue;
+    const float4 v = reinterpret_cast<const float4*>(src + r * lds)[j];
+    float4* o = reinterpret_cast<float4*>(dst + (long long)d * ldd) + j;
+    float4 t = *o;
+    t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+    *o = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------- BatchNorm backward
+// y = act(xhat*w + b) with xhat = (raw - mean)*rstd over the listed rows; dyv = upstream gradient
+// (fp32 g rows or fp16 rows) times colmul (layer scale), masked by the activation derivative
+// (ReLU: y > 0; GELU handled by the caller's GEMM epilogue, act = NONE here).
+// reduce: s1[c] += sum dy ; s2[c] += sum dy * xhat
+template <int G16>
+__global__ void bn_bwd_reduce_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
+                                     const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows,
+                                     int nrows, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ w, const float* __restrict__ b, int act,
+                                     const float* __restrict__ colmul, float* __restrict__ s1, float* __restrict__ s2) {
+  __shared__ float red[2][4][64];
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  float a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    const float mu = mean[c], rs = rstd[c], wc = w[c], bc = b[c], cm = colmul ? colmul[c] : 1.f;
+    for (int r = blockIdx.x * 4 + rl; r < nrows; r += gridDim.x * 4) {
+      const long long rg = g_rows ? g_rows[r] : r, rr = r_rows ? r_rows[r] : r;
+      float dy = G16 ? __half2float(reinterpret_cast<const __half*>(gin)[rg * ldg + c])
+                     : reinterpret_cast<const float*>(gin)[rg * ldg + c];
+      const float xh = (__half2float(raw[rr * ldr + c]) - mu) * rs;
+      dy *= cm;
+      if (act == FVIT_ACT_RELU && fmaf(xh, wc, bc) <= 0.f) dy = 0.f;
+      a1 += dy;
+      a2 += dy * xh;
+    }
+  }
+  red[0][rl][threadIdx.x & 63] = a1;
+  red[1][rl][threadIdx.x & 63] = a2;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    const int k = threadIdx.x & 63;
+    atomicAdd(s1 + c, red[0][0][k] + red[0][1][k] + red[0][2][k] + red[0][3][k]);
+    atomicAdd(s2 + c, red[1][0][k] + red[1][1][k] + red[1][2][k] + red[1][3][k]);
+  }
+}
+// apply: dx16[orow][c] = w*rstd*(dy - s1/N - xhat*s2/N); block 0 also emits dw += s2*sc, db += s1*sc
+template <int G16>
+__global__ void bn_bwd_apply_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
+                                    const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows,
+                                    int nrows, int C, float count, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ w,
+                                    const float* __restrict__ b, int act, const float* __restrict__ colmul,
+                                    const float* __restrict__ s1, const float* __restrict__ s2,
+                                    const float* __restrict__ scalar, __half* __restrict__ out, long long ldo,
+                                    const int* __restrict__ o_rows, float* __restrict__ dw, float* __restrict__ db) {
+  const long long total = (long long)nrows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;
+    const long long rg = g_rows ? g_rows[r] : r, rr = r_rows ? r_rows[r] : r, ro = o_rows ? o_rows[r] : r;
+    float dy = G16 ? __half2float(reinterpret_cast<const __half*>(gin)[rg * ldg + c])
+                   : reinterpret_cast<const float*>(gin)[rg * ldg + c];
+    const float xh = (__half2float(raw[rr * ldr + c]) - mean[c]) * rstd[c];
+    if (colmul) dy *= colmul[c];
+    if (act == FVIT_ACT_RELU && fmaf(xh, w[c], b[c]) <= 0.f) dy = 0.f;
+    out[ro * ldo + c] = __float2half_rn(w[c] * rstd[c] * (dy - s1[c] / count - xh * s2[c] / count));
+  }
+  if (blockIdx.x == 0) {
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dw[c] += s2[c] * sc;
+      db[c] += s1[c] * sc;
+    }
+  }
+}
+
+// conv weight gradient repack: dst[co][ci][tap] += src[tap][co][ci] (src ld = ld_ci)
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ src, int ld_ci, float* __restrict__ dst, int cout,
+                                        int cin) {
+  const long long total = (long long)cout * cin * 9;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    const int ci = (int)((i / 9) % cin);
+    const int co = (int)(i / (9LL * cin));
+    dst[i] += src[((long long)tap * cout + co) * ld_ci + ci];
+  }
+}
+
+// TokenInitializer backward: for ct[b, (y0,x0), c] = bias + mean_{pool window} dwconv3x3(x):
+//   dx[pixel] += sum over pooled outputs / taps ; dw[c][tap] += ... ; dbias[c] += sum gct. One thread per
+//   (b, pixel, channel) gathers from the (at most few) pooled outputs that cover the pixel's 3x3 halo.
+__global__ void token_init_bwd_kernel(const float* __restrict__ g, long long ldg, const int* __restrict__ pix_map,
+                                      const int* __restrict__ ct_row_map, int B, int Hp, int Wp, int C,
+                                      const float* __restrict__ w, int kh, int kw, int sh, int sw, int oh, int ow,
+                                      float* __restrict__ gx, long long ldgx) {
+  const long long total = (long long)B * Hp * Wp * C;
+  const float inv = 1.f / (float)(kh * kw);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pos = i / C;
+    const int x = (int)(pos % Wp), y = (int)((pos / Wp) % Hp), b = (int)(pos / ((long long)Wp * Hp));
+    const int row = pix_map[pos];
+    if (row < 0) continue;
+    float acc = 0.f;
+    // pixel (y,x) feeds conv output (cy,cx) = (y - r + 1, x - s + 1) with tap (r,s); that conv pixel is
+    // pooled into every output (y0,x0) with y0*sh <= cy < y0*sh + kh
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        const int cy = y - r + 1, cx = x - s + 1;
+        if (cy < 0 || cy >= Hp || cx < 0 || cx >= Wp) continue;
+        const float wt = w[c * 9 + r * 3 + s] * inv;
+        for (int y0 = 0; y0 < oh; ++y0) {
+          if (cy < y0 * sh || cy >= y0 * sh + kh) continue;
+          for (int x0 = 0; x0 < ow; ++x0) {
+            if (cx < x0 * sw || cx >= x0 * sw + kw) continue;
+            const int crow = ct_row_map[((long long)b * oh + y0) * ow + x0];
+            acc = fmaf(wt, g[(long long)crow * ldg + c], acc);
+          }
+        }
+      }
+    gx[(long long)row * ldgx + c] += acc;
+  }
+}
+// dw[c][tap] += sc * sum_{b,y0,x0} gct * mean_pool x[.. + tap - 1] ; dbias[c] += sc * sum gct
+__global__ void token_init_wgrad_kernel(const float* __restrict__ g, long long ldg, const __half* __restrict__ xs,
+                                        long long ldx, const int* __restrict__ pix_map,
+                                        const int* __restrict__ ct_row_map, int B, int Hp, int Wp, int C, int kh,
+                                        int kw, int sh, int sw, int oh, int ow, const float* __restrict__ scalar,
+                                        float* __restrict__ dw, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv = 1.f / (float)(kh * kw);
+  float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  float ab = 0.f;
+  for (long long pos = blockIdx.y; pos < (long long)B * oh * ow; pos += gridDim.y) {
+    const int x0 = (int)(pos % ow), y0 = (int)((pos / ow) % oh), b = (int)(pos / ((long long)ow * oh));
+    const float gv = g[(long long)ct_row_map[pos] * ldg + c];
+    ab += gv;
+    for (int py = 0; py < kh; ++py)
+      for (int px = 0; px < kw; ++px) {
+        const int cy = y0 * sh + py, cx = x0 * sw + px;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int iy = cy + r - 1, ix = cx + s - 1;
+            if (iy >= 0 && iy < Hp && ix >= 0 && ix < Wp) {
+              const int row = pix_map[((long long)b * Hp + iy) * Wp + ix];
+              if (row >= 0) acc[r * 3 + s] = fmaf(gv * inv, __half2float(xs[(long long)row * ldx + c]), acc[r * 3 + s]);
+            }
+          }
+      }
+  }
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) atomicAdd(dw + c * 9 + t, acc[t] * sc);
+  atomicAdd(dbias + c, ab * sc);
+}
+
+// Backward of fvit_propagate_fwd (x[r] += gamma * x[src[r]]): g[src[r]] += gamma * g[r] (atomics: a carrier
+// row collects ~ws^2/ct^2 token rows) and dgamma[c] += *scalar * sum_r g[r][c] * x[src[r]][c].
+__global__ void propagate_bwd_kernel(float* __restrict__ g, long long ldg, const float* __restrict__ xs, long long ldx,
+                                     const int* __restrict__ src_map, int rows, int C, const float* __restrict__ gamma,
+                                     const float* __restrict__ scalar, float* __restrict__ dgamma) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (c < C) {
+    const float gm = gamma ? gamma[c] : 1.f;
+    for (int r = blockIdx.x * 4 + rl; r < rows; r += gridDim.x * 4) {
+      const int s = src_map[r];
+      if (s < 0) continue;
+      const float gv = g[(long long)r * ldg + c];
+      atomicAdd(g + (long long)s * ldg + c, gm * gv);
+      acc = fmaf(gv, xs[(long long)s * ldx + c], acc);
+    }
+  }
+  red[rl][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (rl == 0 && c < C && dgamma) {
+    const int k = threadIdx.x & 63;
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+    atomicAdd(dgamma + c, (red[0][k] + red[1][k] + red[2][k] + red[3][k]) * sc);
+  }
+}
+
 static inline int grid_cap(long long total, int block, int per_sm) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)num_sms() * per_sm;
@@ -713,6 +915,75 @@ int fvit_pool_bn_bwd(const float* xs, int64_t ldx, const int32_t* rows, int32_t 
   pool_bn_bwd_apply_kernel<<<grid_cap(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       xs, ldx, rows, B, T, C, mean, rstd, w, dpool, lddp, s1, s2, scalar, g, ldg, dw, dbeta);
   return post_launch("pool_bn_bwd_apply_kernel");
+}
+
+int fvit_scatter_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd, const int32_t* map, int32_t rows,
+                          int32_t C, void* stream) {
+  FVIT_CHECK(src && dst && map && rows > 0 && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0,
+             "fvit_scatter_add_rows: bad arguments");
+  const long long total = (long long)rows * (C / 4);
+  scatter_add_rows_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, map, rows, C);
+  return post_launch("scatter_add_rows_kernel");
+}
+
+int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g_rows, const void* raw16, int64_t ldr,
+                const int32_t* r_rows, int32_t nrows, int32_t C, const float* mean, const float* rstd, const float* w,
+                const float* b, int32_t act, const float* colmul, float* s1, float* s2, const float* scalar, void* out16,
+                int64_t ldo, const int32_t* o_rows, float* dw, float* db, void* stream) {
+  FVIT_CHECK(gin && raw16 && mean && rstd && w && b && s1 && s2 && out16 && dw && db && nrows > 0 && C > 0,
+             "fvit_bn_bwd: bad arguments");
+  FVIT_CHECK(act == FVIT_ACT_NONE || act == FVIT_ACT_RELU, "fvit_bn_bwd: act must be NONE or RELU");
+  FVIT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), (cudaStream_t)stream));
+  FVIT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), (cudaStream_t)stream));
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  const long long total = (long long)nrows * C;
+  const int g2 = grid_cap(total, 256, 16);
+  if (g_is_f16) {
+    bn_bwd_reduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
+                                                                    nrows, C, mean, rstd, w, b, act, colmul, s1, s2);
+    bn_bwd_apply_kernel<1><<<g2, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
+                                                                 nrows, C, (float)nrows, mean, rstd, w, b, act, colmul, s1,
+                                                                 s2, scalar, (__half*)out16, ldo, o_rows, dw, db);
+  } else {
+    bn_bwd_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
+                                                                    nrows, C, mean, rstd, w, b, act, colmul, s1, s2);
+    bn_bwd_apply_kernel<0><<<g2, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
+                                                                 nrows, C, (float)nrows, mean, rstd, w, b, act, colmul, s1,
+                                                                 s2, scalar, (__half*)out16, ldo, o_rows, dw, db);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return post_launch("bn_bwd kernels");
+}
+
+int fvit_unpack_conv_grad(const float* src, int32_t ld_ci, float* dst, int32_t cout, int32_t cin, void* stream) {
+  FVIT_CHECK(src && dst && cout > 0 && cin > 0 && ld_ci >= cin, "fvit_unpack_conv_grad: bad arguments");
+  const long long total = (long long)cout * cin * 9;
+  unpack_conv_grad_kernel<<<grid_cap(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, ld_ci, dst, cout, cin);
+  return post_launch("unpack_conv_grad_kernel");
+}
+
+int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ldx, const int32_t* pix_map,
+                        const int32_t* ct_row_map, int32_t B, int32_t Hp, int32_t Wp, int32_t C, const float* w,
+                        int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t oh, int32_t ow, const float* scalar,
+                        float* gx, int64_t ldgx, float* dw, float* dbias, void* stream) {
+  FVIT_CHECK(g && x16 && pix_map && ct_row_map && w && gx && dw && dbias, "fvit_token_init_bwd: null argument");
+  dim3 gw((unsigned)((C + 127) / 128), (unsigned)(B * oh * ow < 256 ? B * oh * ow : 256));
+  token_init_wgrad_kernel<<<gw, 128, 0, (cudaStream_t)stream>>>(g, ldg, (const __half*)x16, ldx, pix_map, ct_row_map, B, Hp, Wp, C, kh, kw,
+                                                                sh, sw, oh, ow, scalar, dw, dbias);
+  int rc = post_launch("token_init_wgrad_kernel");
+  if (rc) return rc;
+  const long long total = (long long)B * Hp * Wp * C;
+  token_init_bwd_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(g, ldg, pix_map, ct_row_map, B, Hp, Wp,
+                                                                                   C, w, kh, kw, sh, sw, oh, ow, gx, ldgx);
+  return post_launch("token_init_bwd_kernel");
+}
+
+int fvit_propagate_bwd(float* g, int64_t ldg, const float* xs, int64_t ldx, const int32_t* src_map, int32_t rows, int32_t C,
+                       const float* gamma, const float* scalar, float* dgamma, void* stream) {
+  FVIT_CHECK(g && xs && src_map && rows > 0 && C > 0, "fvit_propagate_bwd: bad arguments");
+  dim3 grid((unsigned)grid_cap(((long long)rows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  propagate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, ldg, xs, ldx, src_map, rows, C, gamma, scalar, dgamma);
+  return post_launch("propagate_bwd_kernel");
 }
 
 }  // extern "C"

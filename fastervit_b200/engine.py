@@ -600,14 +600,24 @@ class Engine:
         plan = self.plans.get(key)
         if plan is None:
             with torch.cuda.device(x.device):
-                plan = Plan(self.model, x.shape[0], x.shape[2], x.shape[3], training, x.device)
+                if training:
+                    from .engine_train import TrainPlan
+                    plan = TrainPlan(self.model, x.shape[0], x.shape[2], x.shape[3], x.device)
+                else:
+                    plan = Plan(self.model, x.shape[0], x.shape[2], x.shape[3], training, x.device)
             self.plans[key] = plan
         return plan
 
     def forward(self, x: torch.Tensor, features_only: bool = False) -> torch.Tensor:
         plan = self._plan(x)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()) and plan.training:
-            raise L.FvitError("backward kernels are not built yet in this round")
+        if plan.training:
+            if features_only:
+                raise L.FvitError("forward_features is not wired yet; use forward()")
+            from .engine_train import _FasterViTFunction
+            with torch.cuda.device(x.device):
+                if torch.is_grad_enabled() and any(p.requires_grad for p in plan.params):
+                    return _FasterViTFunction.apply(plan, x, *plan.params)
+                return plan.run_forward(x).clone()
         with torch.cuda.device(x.device):
             wk = plan.weights_key()
             if self._prepped.get(id(plan)) != wk:

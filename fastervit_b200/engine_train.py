@@ -1,0 +1,221 @@
+"""Training plan: train-mode forward (batch-statistics BatchNorm, saved activations) and the backward pass
+of FasterViT as static launch lists over libfvit_sm100.so.
+
+The reference has no backward code — fv.py relies on autograd (train.py:879-896) — so this module *is*
+the backward of SURVEY §8 row a16: per layer it emits the weight-gradient GEMM (both operands MN-major:
+dW = dZ^T X, split-K with fp32 atomics into one flat gradient buffer), the data-gradient GEMM (B = the
+forward's packed weight read as an MN-major operand, so no transposed copies exist), and the HBM-bound
+reductions (bias / LayerNorm / BatchNorm / layer-scale / positional-MLP gradients).
+
+Numerics: activation gradients are fp16 operands (fp32 along the residual stream) multiplied by a
+power-of-two scale S chosen on the device from max|dlogits| (scal[0] = S, scal[1] = 1/S); a branch whose
+layer scale gamma is tiny (1e-5 at init for fv3+) is additionally normalised by s_b = 2^-floor(log2 max|gamma|)
+so no fp16 product underflows. Parameter gradients are fp32 and exact in scale.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from .engine import Plan, _ru
+
+
+class TrainPlan(Plan):
+    def __init__(self, model, B: int, H: int, W: int, device):
+        self.bwd_ops: list[tuple] = []
+        self.fwd_zero: list[torch.Tensor] = []   # accumulators zeroed before every forward (BN statistics)
+        self.saved_levels: list[dict] = []
+        super().__init__(model, B, H, W, True, device)
+
+    # ------------------------------------------------------------------------------ infrastructure
+    def _setup_train(self) -> None:
+        m, nb = self.model, self.bufs
+        self.params = [p for p in m.parameters()]
+        offs, n = {}, 0
+        for p in self.params:
+            offs[id(p)] = n
+            n += _ru(p.numel(), 64)            # 256-byte aligned slices
+        self.gflat = nb.new("grad.flat", (n,), torch.float32)
+        self._goff = offs
+        self.scratch_n = 0
+        self._scratch_req: list[tuple[str, int]] = []
+        # device scalars: [0] S, [1] 1/S, [2] 1.0, then per-branch (s_b, 1/s_b, 1/(S s_b))
+        self._nscal = 3
+        self._branch_slots: list[tuple[int, object]] = []
+
+    def G(self, p: torch.Tensor) -> int:
+        """device pointer of the flat-buffer gradient slice of parameter p"""
+        return self.gflat.data_ptr() + 4 * self._goff[id(p)]
+
+    def grad_views(self) -> list[torch.Tensor]:
+        return [self.gflat[self._goff[id(p)]: self._goff[id(p)] + p.numel()].view_as(p) for p in self.params]
+
+    def _scratch(self, name: str, n: int) -> int:
+        """reserve n zero-initialised fp32 (re-zeroed at the start of every backward); returns offset"""
+        off = self.scratch_n
+        self.scratch_n += _ru(n, 64)
+        self._scratch_req.append((name, off))
+        return off
+
+    def _branch(self, gamma) -> dict:
+        """device-scalar pointers of a residual branch: dgrad alpha (1/s_b) and wgrad alpha (1/(S s_b))"""
+        if not isinstance(gamma, torch.Tensor):
+            return dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
+        slot = self._nscal
+        self._nscal += 3
+        self._branch_slots.append((slot, gamma))
+        return dict(gamma=gamma, s=("scal", slot), inv_s=("scal", slot + 1), w_alpha=("scal", slot + 2))
+
+    def _finish_train(self) -> None:
+        nb = self.bufs
+        self.scal = nb.new("grad.scalars", (_ru(self._nscal, 16),), torch.float32)
+        self.scal[2] = 1.0
+        self.scr = nb.new("grad.scratch", (max(self.scratch_n, 64),), torch.float32)
+        sp = self.scal.data_ptr()
+        for slot, gamma in self._branch_slots:
+            self._op(self.prep_ops, "fvit_pow2_norm", gamma.data_ptr(), gamma.numel(), sp + 4 * slot)
+        # resolve symbolic pointers ("scal", i) / ("scr", off) in the op lists
+        def res(v):
+            if isinstance(v, tuple) and len(v) == 2 and v[0] == "scal":
+                return sp + 4 * v[1]
+            if isinstance(v, tuple) and len(v) == 2 and v[0] == "scr":
+                return self.scr.data_ptr() + 4 * v[1]
+            return v
+        for lst in (self.ops, self.bwd_ops, self.prep_ops):
+            for i, (fn, args, name) in enumerate(lst):
+                if isinstance(args, tuple):
+                    lst[i] = (fn, tuple(res(a) for a in args), name)
+        for g in self._gemm_keep:
+            for f in ("alpha_ptr", "out_f32", "col_sum", "col_sumsq"):
+                v = getattr(g, "_sym_" + f, None)
+                if v is not None:
+                    setattr(g, f, res(v))
+        # per-backward prologue: zero accumulators, pick the gradient scale, per-branch wgrad alphas
+        pro: list[tuple] = [("zero", self.gflat, "memset"), ("zero", self.scr, "memset")]
+        for lv in self.lv:
+            pro.append(("zero", lv["g"], "memset"))
+        self._bwd_prologue = pro
+        self._branch_alpha_ops = []
+        for slot, _ in self._branch_slots:
+            self._branch_alpha_ops.append((self.lib.fvit_vec_mul, (sp + 4, 0, sp + 4 * (slot + 1), 0, sp + 4 * (slot + 2), 1),
+                                           "fvit_vec_mul"))
+
+    # symbolic-pointer aware GEMM emitter for the backward list
+    def _bgemm(self, *, a, a_rows, lda, b, b_rows, ldb, m, n, kc, a_mn=False, b_mn=False, taps=None, a_planes=1,
+               a_plane_stride=0, b_row_off=0, split_k=1, alpha_ptr=None, act=L.ACT_NONE, aux=None, ld_aux=0,
+               out_f32=None, ld_o32=0, out_f16=None, ld_o16=0, row_map=None, resid=None, ld_resid=0, target=None,
+               flops=None) -> None:
+        g = L.GemmArgs()
+        g.a, g.a_rows, g.lda, g.a_plane_stride, g.a_planes, g.a_mn_major = a, a_rows, lda, a_plane_stride, a_planes, int(a_mn)
+        g.b, g.b_rows, g.ldb, g.b_mn_major = b, b_rows, ldb, int(b_mn)
+        g.m, g.n, g.kc = m, n, kc
+        taps = taps or [(0, 0)]
+        g.ntaps = len(taps)
+        for i, (s, p) in enumerate(taps):
+            g.tap_shift[i], g.tap_plane[i] = s, p
+        g.b_row_off = b_row_off
+        g.split_k, g.alpha, g.act = split_k, 1.0, act
+        g.aux, g.ld_aux, g.row_map = aux, ld_aux, row_map
+        g.resid, g.ld_resid = resid, ld_resid
+        g.out_f16, g.ld_out_f16, g.ld_out_f32 = out_f16, ld_o16, ld_o32
+        for f, v in (("alpha_ptr", alpha_ptr), ("out_f32", out_f32)):
+            if isinstance(v, tuple):
+                setattr(g, "_sym_" + f, v)
+            elif v is not None:
+                setattr(g, f, v)
+        self._gemm_keep.append(g)
+        lst = self.bwd_ops if target is None else target
+        lst.append((self.lib.fvit_gemm, (C.byref(g),), "fvit_gemm"))
+        if lst is self.bwd_ops:
+            self.bwd_flops[len(lst) - 1] = flops if flops is not None else 2.0 * m * n * kc * len(taps)
+
+    def _split_k(self, m: int, n: int, k_rows: int) -> int:
+        tiles = ((m + 127) // 128) * ((n + 255) // 256)
+        want = max(1, (2 * 148) // max(tiles, 1))
+        return max(1, min(want, (k_rows + 63) // 64, 64))
+
+    # ------------------------------------------------------------------------------ linear layer backward
+    def _linear_bwd(self, *, lin, w16, ldw, x16, ldx, dz16, lddz, rows, n_out, k_in, br, gW=None, gW_ld=None,
+                    dx16=None, lddx=0, dx_act=L.ACT_NONE, dx_aux=None, ld_aux=0, dx_alpha=None, bias_to=None,
+                    flops_k=None, want_dgrad=True) -> None:
+        """dW[n_out, k_in] += alpha_w * dz16^T @ x16 ; db += alpha_w * colsum(dz16) ; dx16 = alpha_d * dz16 @ W."""
+        gW = self.G(lin.weight) if gW is None else gW
+        gW_ld = k_in if gW_ld is None else gW_ld
+        fk = k_in if flops_k is None else flops_k
+        self._bgemm(a=dz16, a_rows=rows, lda=lddz, a_mn=True, b=x16, b_rows=rows, ldb=ldx, b_mn=True, m=n_out, n=k_in,
+                    kc=rows, split_k=self._split_k(n_out, k_in, rows), alpha_ptr=br["w_alpha"], out_f32=gW,
+                    ld_o32=gW_ld, flops=2.0 * rows * n_out * fk)
+        if lin.bias is not None or bias_to is not None:
+            dst = bias_to if bias_to is not None else self.G(lin.bias)
+            self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst)
+        if want_dgrad:
+            self._bgemm(a=dz16, a_rows=rows, lda=lddz, b=w16, b_rows=n_out, ldb=ldw, b_mn=True, m=rows, n=k_in, kc=n_out,
+                        alpha_ptr=dx_alpha if dx_alpha is not None else br["inv_s"], act=dx_act, aux=dx_aux,
+                        ld_aux=ld_aux, out_f16=dx16, ld_o16=lddx, flops=2.0 * rows * n_out * fk)
+
+    # ------------------------------------------------------------------------------ plan construction
+    def _build(self) -> None:
+        m, B = self.model, self.B
+        if any(r > 0 for r in m.drop_path_rates):
+            raise L.FvitError("stochastic depth is not wired into the training kernels yet: create the model "
+                              "with drop_path_rate=0.0 for training (train.py --drop-path 0)")
+        self.bwd_flops: dict[int, float] = {}
+        self._setup_train()
+        self._build_forward()
+        self._build_backward()
+        self._finish_train()
+
+    # forward / backward emitters are attached below from engine_train_levels.py / engine_train_conv.py
+
+    # ------------------------------------------------------------------------------ execution
+    def run_forward(self, x: torch.Tensor) -> torch.Tensor:
+        for t in self.fwd_zero:
+            t.zero_()
+        self.run_ops(self.prep_ops, None)
+        self.run_ops(self.ops, x)
+        for bn in self._bn_modules:
+            bn.num_batches_tracked += 1
+        return self.logits
+
+    def run_backward(self, dlogits: torch.Tensor) -> None:
+        self._dlogits.copy_(dlogits)
+        self.run_ops(self._bwd_prologue, None)
+        st = L.stream_ptr()
+        rc = self.lib.fvit_grad_scale_init(self._dlogits.data_ptr(), self._dlogits.numel(), 64.0, self.scal.data_ptr(), st)
+        if rc:
+            raise L.FvitError(self.lib.fvit_last_error().decode())
+        self.run_ops(self._branch_alpha_ops, None)
+        self.run_ops(self.bwd_ops, None)
+
+
+class _FasterViTFunction(torch.autograd.Function):
+    """One autograd node for the whole network: forward runs the train plan, backward runs the backward
+    plan and hands out views of the flat gradient buffer (one per nn.Parameter, in .parameters() order)."""
+
+    @staticmethod
+    def forward(ctx, plan: TrainPlan, x: torch.Tensor, *params):
+        ctx.plan = plan
+        logits = plan.run_forward(x)
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan: TrainPlan = ctx.plan
+        plan.run_backward(dlogits.contiguous().float())
+        return (None, None, *plan.grad_views())
+
+
+def _attach() -> None:
+    import types
+    from . import engine_train_conv as ec
+    from . import engine_train_levels as el
+    for mod in (el, ec):
+        for name, fn in vars(mod).items():
+            if isinstance(fn, types.FunctionType) and name.startswith("_") and fn.__module__ == mod.__name__:
+                setattr(TrainPlan, name, fn)
+
+
+_attach()

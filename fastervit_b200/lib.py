@@ -84,6 +84,7 @@ _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _OP_SIGS: dict[str, list] = {
     "fvit_cast_pad_f16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "fvit_pack_conv3x3_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "fvit_pack_conv3x3_taps_f16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "fvit_affine_fold": [_P, _P, _I, _P, _P, _P, _P, _F, _P, _P, _P],
     "fvit_stem_conv_fwd": [_P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P, _P, _P],
     "fvit_stem_im2col": [_P, _L, _L, _L, _L, _I, _I, _I, _I, _P, _I, _P],
@@ -107,6 +108,11 @@ _OP_SIGS: dict[str, list] = {
     "fvit_attn_bias_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P],
     "fvit_cpb_mlp_bwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "fvit_pool_bn_bwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _L, _P, _P, _P],
+    "fvit_scatter_add_rows": [_P, _L, _P, _L, _P, _I, _I, _P],
+    "fvit_bn_bwd": [_P, _I, _L, _P, _P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
+    "fvit_unpack_conv_grad": [_P, _I, _P, _I, _I, _P],
+    "fvit_token_init_bwd": [_P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P],
+    "fvit_propagate_bwd": [_P, _L, _P, _L, _P, _I, _I, _P, _P, _P, _P],
     "fvit_cpb_mlp_fwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P],
     "fvit_attn_bias_fwd": [_P, _P, _I, _I, _I, _P, _P],
     "fvit_token_init_fwd": [_P, _L, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],

@@ -127,6 +127,11 @@ int fvit_vec_headpad_f32(const float* src, float* dst, int32_t n_dst, int32_t hd
  * transpose_io != 0 builds the data-gradient operand [cin][9 flipped][kc_pad >= cout]. */
 int fvit_pack_conv3x3_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,
                           int32_t transpose_io, void* stream);
+/* explicit tap list (no flip): dst[co][j][ci] = w[co][ci][t_j], or with transpose_io dst[ci][j][co]; used for the
+ * data gradient of the stride-2 convolutions (one GEMM per input parity plane). */
+int fvit_pack_conv3x3_taps_f16(const float* w, void* dst, int32_t cout, int32_t cin, int32_t kc_pad,
+                               int32_t transpose_io, int32_t ntaps, int32_t t0, int32_t t1, int32_t t2, int32_t t3,
+                               int32_t t4, int32_t t5, int32_t t6, int32_t t7, int32_t t8, void* stream);
 /* scale/shift so that acc*scale+shift == layer_scale * BN_eval(acc + bias) (fv.py:504-510) or
  * layer_scale * (acc + bias) (fv.py:679-680, 690-691). Any of the BN / bias / layer_scale inputs may
  * be NULL. */
@@ -278,6 +283,27 @@ int fvit_pool_bn_bwd(const float* xs, int64_t ldx, const int32_t* rows, int32_t 
                      const float* mean, const float* rstd, const float* w, const float* dpool, int64_t lddp,
                      float* s1, float* s2, const float* scalar, float* g, int64_t ldg, float* dw, float* dbeta,
                      void* stream);
+/* dst[map[r]] += src[r] (fp32 rows; ct_dewindow backward, fv.py:96-101). */
+int fvit_scatter_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd, const int32_t* map, int32_t rows,
+                          int32_t C, void* stream);
+/* BatchNorm2d (batch statistics) backward over row lists: dy = gin (fp32 or fp16) * colmul, masked by the
+ * ReLU derivative when act == FVIT_ACT_RELU (sign of xhat*w + b); out16[o_rows[r]] = w*rstd*(dy - mean(dy) -
+ * xhat*mean(dy*xhat)); dw += *scalar * sum dy*xhat; db += *scalar * sum dy. s1/s2: [C] scratch. */
+int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g_rows, const void* raw16, int64_t ldr,
+                const int32_t* r_rows, int32_t nrows, int32_t C, const float* mean, const float* rstd, const float* w,
+                const float* b, int32_t act, const float* colmul, float* s1, float* s2, const float* scalar, void* out16,
+                int64_t ldo, const int32_t* o_rows, float* dw, float* db, void* stream);
+/* dst[co][ci][tap] += src[tap][co][ci]: the 9 per-tap weight-gradient GEMM outputs -> nn.Conv2d layout. */
+int fvit_unpack_conv_grad(const float* src, int32_t ld_ci, float* dst, int32_t cout, int32_t cin, void* stream);
+/* TokenInitializer backward (fv.py:733-738): gx[pixel rows] += d/dx, dw [C,9], dbias [C] from the carrier-row
+ * gradients g[ct_row_map[...]]; x16 = fp16 copy of the level input tokens (same row layout as xs). */
+int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ldx, const int32_t* pix_map,
+                        const int32_t* ct_row_map, int32_t B, int32_t Hp, int32_t Wp, int32_t C, const float* w,
+                        int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t oh, int32_t ow, const float* scalar,
+                        float* gx, int64_t ldgx, float* dw, float* dbias, void* stream);
+/* Backward of fvit_propagate_fwd (fv.py:697-700): g[src_map[r]] += gamma*g[r]; dgamma += *scalar*sum g[r]*xs[src_map[r]]. */
+int fvit_propagate_bwd(float* g, int64_t ldg, const float* xs, int64_t ldx, const int32_t* src_map, int32_t rows, int32_t C,
+                       const float* gamma, const float* scalar, float* dgamma, void* stream);
 
 #ifdef __cplusplus
 }
