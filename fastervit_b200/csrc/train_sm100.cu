@@ -254,13 +254,14 @@ __global__ void group_sum_kernel(const float* __restrict__ a, long long lda, int
 // For row r (the LayerNorm's r-th input v_r, whose forward gathered it from in_map[r] and wrote it back
 // to row r):  gv = g[r] + rstd * (gam*dy - mean_c(gam*dy) - xhat * mean_c(gam*dy*xhat));
 //             g[in_map[r]] = gv (and g[r] = 0 when the source is another row); dgamma += dy*xhat, dbeta += dy.
-// `use_g` = 0 starts from zero instead of g[r] (first consumer of a freshly produced tensor).
+// `use_g` = 0 starts from zero instead of g[r] (first consumer of a freshly produced tensor); `clear_moved`
+// zeroes g[r] when the source is another row (only meaningful when r indexes rows of g itself).
 // One warp per row; per-CTA partial sums of dgamma/dbeta in shared memory, then one atomicAdd per column.
 __global__ void __launch_bounds__(256)
     ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
                   const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
                   const float* __restrict__ gamma, int rows, int C, float* __restrict__ g, long long ldg,
-                  const int* __restrict__ in_map, int use_g, const float* __restrict__ scalar,
+                  const int* __restrict__ in_map, int use_g, int clear_moved, const float* __restrict__ scalar,
                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sh[];  // [warps][2][C]: private per-warp partial sums (lane owns column c)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256)
       const float d = __half2float(dyr[c]), xh = __half2float(xr[c]);
       float v = rs * (d * __ldg(gamma + c) - s1 - xh * s2);
       if (use_g) v += gr[c];
-      if (src != r) gr[c] = 0.f;
+      if (clear_moved && src != r) gr[c] = 0.f;
       gs_[c] = v;
     }
   }
@@ -832,8 +833,8 @@ int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, 
 
 int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const void* xhat16, int64_t ldxh,
                 const float* rstd, const float* gamma, int32_t rows, int32_t C, float* g, int64_t ldg,
-                const int32_t* in_map, int32_t use_g, const float* scalar, float* dgamma, float* dbeta,
-                void* stream) {
+                const int32_t* in_map, int32_t use_g, int32_t clear_moved, const float* scalar, float* dgamma,
+                float* dbeta, void* stream) {
   FVIT_CHECK(dy16 && xhat16 && rstd && gamma && g && dgamma && dbeta && rows > 0 && C > 0,
              "fvit_ln_bwd: bad arguments");
   const int block = 256, wpb = 8;
@@ -848,7 +849,7 @@ int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const voi
   }
   ln_bwd_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
       (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
-      scalar, dgamma, dbeta);
+      clear_moved, scalar, dgamma, dbeta);
   return post_launch("ln_bwd_kernel");
 }
 

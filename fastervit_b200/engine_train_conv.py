@@ -251,7 +251,7 @@ def _emit_downsample_bwd(self, ds: dict, src: dict, dst: dict) -> None:
                     flops=2.0 * self.B * ds["Ho"] * ds["Wo"] * Cs * 2 * Cs * len(tl_))
     # LayerNorm2d backward: writes the source level's output gradient
     self._op(ops, "fvit_ln_bwd", ds["dplanes"].data_ptr(), ld, ds["omap"].data_ptr(), ds["xh"].data_ptr(), Cs,
-             ds["rs"].data_ptr(), mod.norm.weight.data_ptr(), npix, Cs, src["g"].data_ptr(), Cs, ds["src_rows"].data_ptr(), 0,
+             ds["rs"].data_ptr(), mod.norm.weight.data_ptr(), npix, Cs, src["g"].data_ptr(), Cs, ds["src_rows"].data_ptr(), 0, 0,
              ("scal", 1), self.G(mod.norm.weight), self.G(mod.norm.bias))
 
 

@@ -362,7 +362,7 @@ def _mlp_bwd(self, tl: dict, ms: dict, gamma, g_ptr: int, rows: int, ln: nn.Laye
     self._linear_bwd(lin=mlp.fc1, w16=ms["w1"].data_ptr(), ldw=ms["ld1"], x16=ms["y16"].data_ptr(), ldx=Cc,
                      dz16=dp.data_ptr(), lddz=hid, rows=rows, n_out=hid, k_in=Cc, br=one, dx16=dy.data_ptr(), lddx=Cc)
     self._op(ops, "fvit_ln_bwd", dy.data_ptr(), Cc, None, xh.data_ptr(), Cc, rs.data_ptr(), ln.weight.data_ptr(), rows, Cc,
-             g_ptr, Cc, in_map, 1, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
+             g_ptr, Cc, in_map, 1, 0, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
 
 
 def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh, rs, in_map, g_base: int,
@@ -410,7 +410,7 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
             self._op(ops, "fvit_unpad_heads_f32", gbq, 1, self.G(attn.qkv.bias), 1, 3 * Cp, 1, hd, hdp, 1, 0, None)
     # LayerNorm (with the gather routing of the forward)
     self._op(ops, "fvit_ln_bwd", dy.data_ptr(), Cc, None, xh.data_ptr(), Cc, rs.data_ptr(), ln.weight.data_ptr(), rows, Cc,
-             g_ptr, Cc, in_map, 1, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
+             g_ptr, Cc, in_map, 1, 1 if clear_moved else 0, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
 
 
 def _emit_token_level_bwd(self, tl: dict) -> None:
@@ -496,7 +496,7 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
     # xs carrier rows it was gathered from
     ln = blk.hat_norm1
     self._op(ops, "fvit_ln_bwd", dy.data_ptr(), Cc, None, c["xh1"].data_ptr(), Cc, c["rs1"].data_ptr(),
-             ln.weight.data_ptr(), rows_c, Cc, gc_ptr, Cc, None, 1, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
+             ln.weight.data_ptr(), rows_c, Cc, gc_ptr, Cc, None, 1, 0, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
     if sv["hat_pe"] is not None:
         self._op(ops, "fvit_group_sum", gc_ptr, Cc, B, n_ct, 0, Cc, ("scal", 1), sv["hat_pe"]["dout"])
         _posemb_bwd(self, sv["hat_pe"])

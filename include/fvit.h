@@ -253,13 +253,13 @@ int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_r
 int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, int32_t skip, int32_t C,
                    const float* scalar, float* out, void* stream);
 /* LayerNorm backward for the forward of fvit_ln_fwd (same row maps): with gv = (use_g ? g[r] : 0) +
- * rstd[r]*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)):  g[in_map ? in_map[r] : r] = gv (g[r]
- * cleared when the source is another row); dgamma[c] += *scalar*sum dy*xhat; dbeta[c] += *scalar*sum dy.
+ * rstd[r]*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)):  g[in_map ? in_map[r] : r] = gv (with
+ * clear_moved, g[r] is zeroed when the source is another row — r must then index rows of g); dgamma[c] += *scalar*sum dy*xhat; dbeta[c] += *scalar*sum dy.
  * dy16 rows through dy_map (rows with dy_map < 0 are skipped). */
 int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const void* xhat16, int64_t ldxh,
                 const float* rstd, const float* gamma, int32_t rows, int32_t C, float* g, int64_t ldg,
-                const int32_t* in_map, int32_t use_g, const float* scalar, float* dgamma, float* dbeta,
-                void* stream);
+                const int32_t* in_map, int32_t use_g, int32_t clear_moved, const float* scalar, float* dgamma,
+                float* dbeta, void* stream);
 /* Backward of the attention core (either forward kernel): recomputes P from q, k, bias; writes dq, dk, dv
  * (fp16, head-padded layout [rows, 3*heads*hdp], padding columns zero) and accumulates dbias[h][S][S]. */
 int fvit_attn_core_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, int32_t groups, int32_t S,

@@ -31,7 +31,8 @@ for k, want in tr["bn_after"].items():
     d = (f[::stride].float().cpu() - want["sample"]).abs().max().item() / max(want["amax"], 1e-12)
     worst = max(worst, d)
 print("BN running stats worst rel err:", worst)
-floor = tr["grad_floor"]
+gmax = max(w["amax"] for w in tr["grads"].values())
+floor = 1e-3 * gmax
 rows = []
 for k, p in model.named_parameters():
     want = tr["grads"].get(k)
@@ -45,9 +46,9 @@ for k, p in model.named_parameters():
     smp = f[::stride].float().cpu()
     d = (smp - want["sample"]).abs().max().item() / max(want["amax"], floor)
     rows.append((d, k, p.grad.double().norm().item(), want["l2"]))
-rows.sort(key=lambda r: -r[0] if r[0] == r[0] else -1e9)
-print(f"{len(rows)} parameter gradients; worst 25 (sample max err / amax, key, |g| got, |g| ref):")
-for r in rows[:25]:
-    print(f"  {r[0]:.3e}  {r[1]:60s} {r[2]:.4e} {r[3]:.4e}")
+print(f"{len(rows)} parameter gradients (sample max err / max(amax, 1e-3*global amax), |g| got, |g| ref), model order:")
+for r in rows:
+    flag = "" if r[0] < 2e-2 else ("  <-- BAD" if r[0] > 0.1 else "  <- meh")
+    print(f"  {r[0]:.3e}  {r[1]:62s} {r[2]:.4e} {r[3]:.4e}{flag}")
 ok = sum(1 for r in rows if r[0] < 2e-2)
 print(f"{ok}/{len(rows)} within 2e-2")
