@@ -34,10 +34,15 @@ WORKLOADS = {
     "fv4_fwd": ("faster_vit_4_224", {}, 128, (224, 224), "fwd"),
     "ar0_fwd": ("faster_vit_0_any_res", dict(resolution=[576, 960], window_size=[7, 7, 12, 6], ct_size=2, dim=64),
                 32, (576, 960), "fwd"),
+    # training steps: forward (batch-statistics BN) + cross-entropy + backward; drop_path_rate = 0 (stochastic
+    # depth is a per-window mask multiply: same FLOPs) ; no optimizer (the metric is fwd+bwd img/s)
+    "fv0_train": ("faster_vit_0_224", dict(drop_path_rate=0.0), 256, (224, 224), "train"),
+    "fv4_train": ("faster_vit_4_224", dict(drop_path_rate=0.0), 128, (224, 224), "train"),
 }
-ORACLE_CASE = {"fv0_fwd": "fv0", "fv4_fwd": "fv4", "ar0_fwd": "ar0"}
+ORACLE_CASE = {"fv0_fwd": "fv0", "fv4_fwd": "fv4", "ar0_fwd": "ar0", "fv0_train": "fv0", "fv4_train": "fv4"}
 # algorithmic forward GFLOP per image (measured on the reference with FlopCounterMode)
-ALG_GFLOP_FWD = {"fv0_fwd": 6.7237, "fv4_fwd": 85.3574, "ar0_fwd": 73.0828}
+ALG_GFLOP_FWD = {"fv0_fwd": 6.7237, "fv4_fwd": 85.3574, "ar0_fwd": 73.0828,
+                 "fv0_train": 20.3580, "fv4_train": 258.1946}  # train entries: fwd+bwd
 
 
 def peaks() -> dict:
@@ -102,40 +107,47 @@ def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float =
     from oracle import fastervit_oracle as O
     from oracle.configs import cfg_of
     import fastervit_b200 as F
-    entry, kwargs, _, hw, _ = WORKLOADS[workload]
+    entry, kwargs, _, hw, mode = WORKLOADS[workload]
     cfg = cfg_of(ORACLE_CASE[workload])
     torch.manual_seed(0)
-    model = F.create_model(entry, drop_path_rate=0.0, **kwargs).eval()  # parameter container only
+    model = F.create_model(entry, **{**kwargs, 'drop_path_rate': 0.0}).eval()  # parameter container only
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    bs = {"fv0_fwd": 16, "fv4_fwd": 4, "ar0_fwd": 2}[workload]
+    bs = {"fv0_fwd": 16, "fv4_fwd": 4, "ar0_fwd": 2, "fv0_train": 8, "fv4_train": 2}[workload]
     x = O.synth_input(bs, hw, 1)
+    tgt = torch.randint(0, 1000, (bs,), generator=torch.Generator().manual_seed(2))
+
+    def run(xb, tb):
+        if mode == "train":
+            O.loss_and_grads(sd, cfg, xb, tb, training=True)
+        else:
+            with torch.no_grad():
+                O.forward(sd, cfg, xb)
     # "all the host threads it can use": intra-op parallelism of torch CPU ops stops scaling (and
     # oversubscribes cgroup-limited containers) well before 100+ threads, so pick the fastest of a
     # few candidate thread counts on one small forward and report the count used
     cands = sorted({c for c in (avail, avail // 2, 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
     best, cores = None, cands[-1]
-    with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            O.forward(sd, cfg, x[:2])
-            t0 = time.perf_counter()
-            O.forward(sd, cfg, x[:2])
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, cores = dt, c
-    torch.set_num_threads(cores)
-    with torch.no_grad():
-        for _ in range(max(1, warmup)):
-            O.forward(sd, cfg, x)
+    for c in cands:
+        torch.set_num_threads(c)
+        run(x[:2], tgt[:2])
         t0 = time.perf_counter()
-        n = 0
-        while n < steps and (n == 0 or time.perf_counter() - t0 < budget_s):
-            O.forward(sd, cfg, x)
-            n += 1
+        run(x[:2], tgt[:2])
         dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, c
+    torch.set_num_threads(cores)
+    for _ in range(max(1, warmup)):
+        run(x, tgt)
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps and (n == 0 or time.perf_counter() - t0 < budget_s):
+        run(x, tgt)
+        n += 1
+    dt = time.perf_counter() - t0
+    what = "train-mode forward + cross-entropy + autograd backward" if mode == "train" else "eval forward"
     return dict(value=bs * n / dt, unit="img/s", cores=cores, kind="port",
-                sample=f"{entry} eval forward (oracle port of the reference nn.Modules, fp32 torch CPU ops), "
+                sample=f"{entry} {what} (oracle port of the reference nn.Modules, fp32 torch CPU ops), "
                        f"batch {bs} x {n} iterations in {dt:.1f}s, {cores} threads",
                 ms_per_step=1e3 * dt / n, steps_done=n, batch=bs)
 
@@ -159,8 +171,12 @@ def main() -> None:
     entry, kwargs, batch, hw, mode = WORKLOADS[args.workload]
     if args.batch:
         batch = args.batch
-    config = {"workload": f"{entry} forward-only (eval), batch {batch}/GPU, 3x{hw[0]}x{hw[1]} synthetic N(0,1), "
-                          "random-init weights", "global_batch": batch * world, "parallelism": f"dp{world} replicas",
+    what = ("fwd+bwd training step (train-mode BN, cross-entropy, no optimizer, drop_path_rate=0)" if mode == "train"
+            else "forward-only (eval)")
+    config = {"workload": f"{entry} {what}, batch {batch}/GPU, 3x{hw[0]}x{hw[1]} synthetic N(0,1), "
+                          "random-init weights", "global_batch": batch * world,
+              "parallelism": (f"dp{world}: batch sharded, NCCL all-reduce of the flat gradient buffer" if mode == "train"
+                              else f"dp{world} replicas"),
               "l2": "inputs larger than L2 (rotating device batches; no explicit flush)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -191,7 +207,10 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
-    model = F.create_model(entry, **kwargs).to(dev).eval()
+    model = F.create_model(entry, **kwargs).to(dev)
+    model = model.train() if mode == "train" else model.eval()
+    if mode == "train" and dist is not None:
+        model.enable_grad_allreduce()
     nbuf = 2
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     xs = [torch.randn(batch, 3, hw[0], hw[1], device=dev, generator=g) for _ in range(nbuf)]
@@ -202,9 +221,19 @@ def main() -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    with torch.no_grad():
+    targets = torch.randint(0, 1000, (batch,), device=dev, generator=g)
+
+    def step(xb):
+        if mode == "train":
+            loss = torch.nn.functional.cross_entropy(model(xb), targets)
+            loss.backward()
+            model.zero_grad(set_to_none=True)
+            return loss
+        return model(xb)
+
+    with torch.set_grad_enabled(mode == "train"):
         for i in range(args.warmup):
-            model(xs[i % nbuf])
+            step(xs[i % nbuf])
         sync_all()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -212,7 +241,7 @@ def main() -> None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            out = model(xs[i % nbuf])
+            out = step(xs[i % nbuf])
         e1.record()
         sync_all()
         launches = L.launch_count()
@@ -250,12 +279,16 @@ def main() -> None:
                         dev_in[nxt].copy_(host_in[nxt], non_blocking=True)
                         ready[nxt].record(copy_stream)
                 torch.cuda.current_stream().wait_event(ready[cur])
-                logits = model(dev_in[cur])
+                res = step(dev_in[cur])
                 done[cur].record()
-                host_out.copy_(logits, non_blocking=True)
+                if mode == "train":
+                    host_loss.copy_(res.detach().reshape(1), non_blocking=True)
+                else:
+                    host_out.copy_(res, non_blocking=True)
             torch.cuda.synchronize()
 
-        with torch.no_grad():
+        host_loss = torch.empty(1).pin_memory()
+        with torch.set_grad_enabled(mode == "train"):
             e2e_loop(2)
             sync_all()
             t0 = time.perf_counter()
@@ -265,8 +298,10 @@ def main() -> None:
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": batch * world * steps_e / t.item(), "unit": "img/s",
-               "h2d_bytes_per_step": batch * 3 * hw[0] * hw[1] * 4, "d2h_bytes_per_step": batch * model.num_classes * 4,
-               "steps": steps_e, "note": "pinned host input uploaded on a prefetch stream, logits copied back, wall clock"}
+               "h2d_bytes_per_step": batch * 3 * hw[0] * hw[1] * 4,
+               "d2h_bytes_per_step": 4 if mode == "train" else batch * model.num_classes * 4,
+               "steps": steps_e, "note": "pinned host input uploaded on a prefetch stream, "
+                                         + ("loss" if mode == "train" else "logits") + " copied back, wall clock"}
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
     pk = peaks()
@@ -277,6 +312,9 @@ def main() -> None:
         with torch.no_grad():
             plan.profile(xs[0])
             prof = plan.profile(xs[1])
+        if mode == "train":
+            for r in prof:
+                r["name"] = r["name"] + "@fwd" if r["name"] != "fvit_gemm" else r["name"]
         by = {}
         for r in prof:
             d = by.setdefault(r["name"], dict(ms=0.0, n=0, flops=0.0))
@@ -289,7 +327,8 @@ def main() -> None:
                               gflop=round(v["flops"] / 1e9, 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
         if gm:
             ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
-            roofline = {"kernel": "gemm_tcgen05_kernel (fvit_gemm: conv taps + linear layers)", "bound": "tensor",
+            roofline = {"kernel": "gemm_tcgen05_kernel (fvit_gemm: conv taps + linear layers; fwd, dgrad and wgrad launches)",
+                        "bound": "tensor",
                         "achieved": round(ach, 2), "peak": pk["tensor"], "unit": "TFLOP/s",
                         "frac": round(ach / pk["tensor"], 4), "traffic": None,
                         "peak_source": f"{pk['src']} bf16 dense sustained (MEASURED_PEAKS.json)",

@@ -51,7 +51,10 @@ class TrainPlan(Plan):
         return self.gflat.data_ptr() + 4 * self._goff[id(p)]
 
     def grad_views(self) -> list[torch.Tensor]:
-        return [self.gflat[self._goff[id(p)]: self._goff[id(p)] + p.numel()].view_as(p) for p in self.params]
+        """Per-parameter views of a *copy* of the flat gradient buffer: autograd's AccumulateGrad may keep
+        the tensors it is handed, and the flat buffer itself is reused (zeroed) by the next backward."""
+        flat = self.gflat.clone()
+        return [flat[self._goff[id(p)]: self._goff[id(p)] + p.numel()].view_as(p) for p in self.params]
 
     def _scratch(self, name: str, n: int) -> int:
         """reserve n zero-initialised fp32 (re-zeroed at the start of every backward); returns offset"""
@@ -180,7 +183,7 @@ class TrainPlan(Plan):
             bn.num_batches_tracked += 1
         return self.logits
 
-    def run_backward(self, dlogits: torch.Tensor) -> None:
+    def _bwd_start(self, dlogits: torch.Tensor) -> None:
         self._dlogits.copy_(dlogits)
         self.run_ops(self._bwd_prologue, None)
         st = L.stream_ptr()
@@ -188,7 +191,38 @@ class TrainPlan(Plan):
         if rc:
             raise L.FvitError(self.lib.fvit_last_error().decode())
         self.run_ops(self._branch_alpha_ops, None)
+
+    def run_backward(self, dlogits: torch.Tensor) -> None:
+        self._bwd_start(dlogits)
         self.run_ops(self.bwd_ops, None)
+        grp = getattr(self.model, "_grad_allreduce", None)
+        if grp is not None:
+            # data parallel (train.py:542-551): ONE exchange per step — mean of the flat gradient buffer over
+            # the ranks (NCCL over NVLink/NVSwitch); BatchNorm statistics stay per-GPU like the reference
+            import torch.distributed as dist
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.AVG, group=None if grp is True else grp)
+
+    def profile(self, x: torch.Tensor) -> list[dict]:
+        """Per-launch CUDA-event timing of one training step (forward list, then backward list with the
+        gradient of sum(logits)/B as a stand-in loss gradient)."""
+        for t in self.fwd_zero:
+            t.zero_()
+        self.run_ops(self.prep_ops, None)
+        out = []
+        for ops, flops, tag in ((self.ops, self.op_flops, ""), (self.bwd_ops, self.bwd_flops, "")):
+            if ops is self.bwd_ops:
+                self._bwd_start(torch.full_like(self._dlogits, 1.0 / self.B))
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)]
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(8e8))
+            evs[0].record()
+            for i, op in enumerate(ops):
+                self.run_ops([op], x)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            out += [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=flops.get(i, 0.0),
+                         phase="bwd" if ops is self.bwd_ops else "fwd") for i, op in enumerate(ops)]
+        return out
 
 
 class _FasterViTFunction(torch.autograd.Function):

@@ -237,6 +237,7 @@ class FasterViT(nn.Module):
         self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
         self.apply(self._init_weights)
         self._engine = None
+        self._grad_allreduce = None
 
     # fv.py:930-943: Linear trunc_normal(.02)/zero bias, norms to identity, convs keep torch default
     def _init_weights(self, m):
@@ -269,6 +270,12 @@ class FasterViT(nn.Module):
         for k, v in self.__dict__.items():
             new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
         return new
+
+    def enable_grad_allreduce(self, group=None) -> None:
+        """Data-parallel training without wrapping in DistributedDataParallel: after every backward the flat
+        gradient buffer is averaged over `group` (default: the world) with a single NCCL all-reduce — the one
+        collective of the path (train.py:551). Parameters must start identical on all ranks."""
+        self._grad_allreduce = True if group is None else group
 
     def forward_features(self, x):
         return self._get_engine().forward(x, features_only=True)
