@@ -146,7 +146,19 @@ __device__ __forceinline__ int colsum16_owner_col(int lane) {
 // Epilogue specialisation: GENERIC = every option decided at run time (backward modes, statistics,
 // split-K atomics); otherwise ACT / RESID / O32 / O16 are compile-time and the unused paths vanish
 // (the epilogue is instruction-issue bound, so this is worth ~2.5x on short-K tiles).
-template <bool GENERIC, int ACT, bool RESID, bool O32, bool O16>
+// FEAT: compile-time feature mask (see EF_* below); EF_GENERIC keeps every switch at run time.
+enum : uint32_t {
+  EF_GENERIC = 1u << 0,
+  EF_ACT_SHIFT = 1,          // 3 bits: FVIT_ACT_* code
+  EF_RESID = 1u << 4,
+  EF_O32 = 1u << 5,
+  EF_O16 = 1u << 6,
+  EF_STATS = 1u << 7,
+  EF_PRE = 1u << 8,
+  EF_ATOMIC = 1u << 9,
+  EF_ALPHAPTR = 1u << 10,
+};
+template <uint32_t FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const __grid_constant__ CUtensorMap tmap_b,
@@ -291,17 +303,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float* stg = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES) + ew * (32 * STG_LD);
     const int sub = lane >> 3;   // row within a 4-row group
     const int c4 = lane & 7;     // which float4 of the 32-column chunk
-    const bool atomic_out = GENERIC && p.atomic_out;
-    const bool use_resid = GENERIC ? (p.resid != nullptr && !p.atomic_out) : RESID;
-    const bool use_aux = GENERIC && (p.act == FVIT_ACT_GELU_BWD || p.act == FVIT_ACT_RELU_BWD) && !p.atomic_out;
+    constexpr bool GENERIC = (FEAT & EF_GENERIC) != 0;
+    constexpr int ACT = (FEAT >> EF_ACT_SHIFT) & 7;
+    const bool atomic_out = GENERIC ? (p.atomic_out != 0) : ((FEAT & EF_ATOMIC) != 0);
+    const bool use_resid = GENERIC ? (p.resid != nullptr && !p.atomic_out) : ((FEAT & EF_RESID) != 0);
     const int act = GENERIC ? p.act : ACT;
-    const bool out32 = GENERIC ? (p.out_f32 != nullptr) : O32;
-    const bool out16 = GENERIC ? (p.out_f16 != nullptr) : O16;
-    const bool stats = GENERIC && p.col_sum != nullptr && !p.atomic_out;
+    const bool use_aux = (act == FVIT_ACT_GELU_BWD || act == FVIT_ACT_RELU_BWD) && !atomic_out;
+    const bool out32 = GENERIC ? (p.out_f32 != nullptr) : ((FEAT & EF_O32) != 0);
+    const bool out16 = GENERIC ? (p.out_f16 != nullptr) : ((FEAT & EF_O16) != 0);
+    const bool stats = GENERIC ? (p.col_sum != nullptr && !p.atomic_out) : ((FEAT & EF_STATS) != 0);
     const bool has_cs2 = GENERIC && p.col_scale2 != nullptr;
     const bool has_rs = GENERIC && p.row_scale != nullptr;
-    const bool has_pre = GENERIC && p.out_pre16 != nullptr;
-    const float alpha = (GENERIC && p.alpha_ptr) ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    const bool has_pre = GENERIC ? (p.out_pre16 != nullptr) : ((FEAT & EF_PRE) != 0);
+    const bool has_aptr = GENERIC ? (p.alpha_ptr != nullptr) : ((FEAT & EF_ALPHAPTR) != 0);
+    const float alpha = has_aptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -704,12 +719,19 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES;
   const long long work = (long long)p.tiles_m * p.tiles_n * p.split_k;
   const int grid = (int)(work < sms ? work : sms);
-  const bool generic = p.atomic_out || a->col_sum || a->col_scale2 || a->aux || a->act > FVIT_ACT_GELU ||
-                       a->alpha_ptr || a->row_scale || a->out_pre16;
-  const bool resid = a->resid != nullptr, o32 = a->out_f32 != nullptr, o16 = a->out_f16 != nullptr;
-#define FVIT_GEMM_LAUNCH(GEN, ACTV, RES, O32V, O16V)                                                   \
+  // feature mask of this call; launch the matching specialisation if one was instantiated
+  uint32_t feat = ((uint32_t)a->act << EF_ACT_SHIFT);
+  if (a->resid && !p.atomic_out) feat |= EF_RESID;
+  if (a->out_f32) feat |= EF_O32;
+  if (a->out_f16) feat |= EF_O16;
+  if (a->col_sum) feat |= EF_STATS;
+  if (a->out_pre16) feat |= EF_PRE;
+  if (p.atomic_out) feat |= EF_ATOMIC;
+  if (a->alpha_ptr) feat |= EF_ALPHAPTR;
+  const bool needs_generic = a->col_scale2 || a->row_scale;
+#define FVIT_GEMM_LAUNCH(F)                                                                            \
   do {                                                                                                 \
-    auto kfn = gemm_tcgen05_kernel<GEN, ACTV, RES, O32V, O16V>;                                        \
+    auto kfn = gemm_tcgen05_kernel<(F)>;                                                               \
     static bool attr_set = false;                                                                      \
     if (!attr_set) {                                                                                   \
       FVIT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));  \
@@ -718,17 +740,31 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
     kfn<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tma, tmb, p);                        \
     return post_launch("gemm_tcgen05_kernel");                                                         \
   } while (0)
-  if (!generic) {
-    const int act = a->act;
-    if (act == FVIT_ACT_NONE && !resid && !o32 && o16) FVIT_GEMM_LAUNCH(false, 0, false, false, true);   // qkv
-    if (act == FVIT_ACT_GELU && !resid && !o32 && o16) FVIT_GEMM_LAUNCH(false, 2, false, false, true);   // fc1, conv1
-    if (act == FVIT_ACT_RELU && !resid && !o32 && o16) FVIT_GEMM_LAUNCH(false, 1, false, false, true);   // stem conv1
-    if (act == FVIT_ACT_RELU && !resid && o32 && o16) FVIT_GEMM_LAUNCH(false, 1, false, true, true);     // stem conv2
-    if (act == FVIT_ACT_NONE && resid && o32 && !o16) FVIT_GEMM_LAUNCH(false, 0, true, true, false);     // proj, fc2
-    if (act == FVIT_ACT_NONE && resid && o32 && o16) FVIT_GEMM_LAUNCH(false, 0, true, true, true);       // conv2
-    if (act == FVIT_ACT_NONE && !resid && o32 && !o16) FVIT_GEMM_LAUNCH(false, 0, false, true, false);   // downsample, head
-    if (act == FVIT_ACT_NONE && !resid && o32 && o16) FVIT_GEMM_LAUNCH(false, 0, false, true, true);     // downsample -> conv level
+#define FVIT_ACTF(x) ((uint32_t)(x) << EF_ACT_SHIFT)
+  if (!needs_generic) {
+    switch (feat) {
+      // ---- inference / shared forward shapes
+      case FVIT_ACTF(0) | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O16);                               // qkv
+      case FVIT_ACTF(2) | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(2) | EF_O16);                               // fc1, conv1 (eval)
+      case FVIT_ACTF(1) | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(1) | EF_O16);                               // stem conv1 (eval)
+      case FVIT_ACTF(1) | EF_O32 | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(1) | EF_O32 | EF_O16);             // stem conv2 (eval)
+      case FVIT_ACTF(0) | EF_RESID | EF_O32: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32);         // proj, fc2, conv dgrad
+      case FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_O16);  // conv2 (eval)
+      case FVIT_ACTF(0) | EF_O32: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O32);                               // downsample, head
+      case FVIT_ACTF(0) | EF_O32 | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O32 | EF_O16);             // downsample -> next level
+      // ---- training forward
+      case FVIT_ACTF(0) | EF_O16 | EF_STATS: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O16 | EF_STATS);         // raw conv + BN statistics
+      case FVIT_ACTF(2) | EF_O16 | EF_PRE: FVIT_GEMM_LAUNCH(FVIT_ACTF(2) | EF_O16 | EF_PRE);             // fc1 saving the pre-GELU value
+      // ---- backward
+      case FVIT_ACTF(0) | EF_O32 | EF_ATOMIC | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O32 | EF_ATOMIC | EF_ALPHAPTR);  // wgrad split-K
+      case FVIT_ACTF(0) | EF_O32 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O32 | EF_ALPHAPTR);   // wgrad single pass
+      case FVIT_ACTF(0) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O16 | EF_ALPHAPTR);   // dgrad
+      case FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR);   // dgrad * gelu'
+      case FVIT_ACTF(3) | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16);                               // conv dgrad * gelu'
+      default: break;
+    }
   }
-  FVIT_GEMM_LAUNCH(true, 0, false, false, false);
+  FVIT_GEMM_LAUNCH(EF_GENERIC);
+#undef FVIT_ACTF
 #undef FVIT_GEMM_LAUNCH
 }

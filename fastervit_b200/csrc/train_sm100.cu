@@ -752,7 +752,7 @@ extern "C" {
 int fvit_colstats_f32(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C, float* sum,
                       float* sumsq, void* stream) {
   FVIT_CHECK(x && sum && sumsq && nrows > 0 && C > 0, "fvit_colstats_f32: bad arguments");
-  dim3 grid((unsigned)grid_cap(((long long)nrows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 15) / 16, 1, 24), (unsigned)((C + 63) / 64));
   colstats_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, nrows, C, sum, sumsq);
   return post_launch("colstats_f32_kernel");
 }
@@ -812,7 +812,7 @@ int fvit_cast_scale_f16(const float* x, int64_t ldx, const int32_t* rows, int32_
 int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_rows, const void* b16, int64_t ldb,
                 int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, void* stream) {
   FVIT_CHECK(a && out && nrows > 0 && C > 0, "fvit_colsum: bad arguments");
-  dim3 grid((unsigned)grid_cap(((long long)nrows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 15) / 16, 1, 24), (unsigned)((C + 63) / 64));
   if (a_is_f16)
     colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
                                                              colmul, scalar, out);
@@ -936,7 +936,7 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
   FVIT_CHECK(act == FVIT_ACT_NONE || act == FVIT_ACT_RELU, "fvit_bn_bwd: act must be NONE or RELU");
   FVIT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), (cudaStream_t)stream));
   FVIT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), (cudaStream_t)stream));
-  dim3 grid((unsigned)grid_cap(((long long)nrows + 3) / 4, 1, 4), (unsigned)((C + 63) / 64));
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 15) / 16, 1, 24), (unsigned)((C + 63) / 64));
   const long long total = (long long)nrows * C;
   const int g2 = grid_cap(total, 256, 16);
   if (g_is_f16) {
