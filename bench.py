@@ -126,16 +126,18 @@ def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float =
     # "all the host threads it can use": intra-op parallelism of torch CPU ops stops scaling (and
     # oversubscribes cgroup-limited containers) well before 100+ threads, so pick the fastest of a
     # few candidate thread counts on one small forward and report the count used
-    cands = sorted({c for c in (avail, avail // 2, 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
-    best, cores = None, cands[-1]
-    for c in cands:
+    cands = sorted({c for c in (avail, 64, 32, 16, 8) if 1 <= c <= avail})
+    best, cores = None, cands[0]
+    for c in cands:  # ascending; stop as soon as more threads stop helping (keeps the probe short)
         torch.set_num_threads(c)
-        run(x[:2], tgt[:2])
+        run(x[:1], tgt[:1])
         t0 = time.perf_counter()
-        run(x[:2], tgt[:2])
+        run(x[:1], tgt[:1])
         dt = time.perf_counter() - t0
         if best is None or dt < best:
             best, cores = dt, c
+        elif dt > 1.3 * best:
+            break
     torch.set_num_threads(cores)
     for _ in range(max(1, warmup)):
         run(x, tgt)

@@ -72,10 +72,12 @@ def test_second_step_and_grad_accumulation_semantics():
     logits2 = model(x)
     loss2 = torch.nn.functional.cross_entropy(logits2, tr["target"].cuda())
     loss2.backward()   # accumulates: .grad should now be ~2x
+    gmax = max(v.abs().max().item() for v in g1.values())
     for k, p in model.named_parameters():
         ref = 2 * g1[k]
-        tol = 1e-3 * max(ref.abs().max().item(), 1e-8) + 1e-9
-        assert (p.grad - ref).abs().max().item() <= 20 * tol, k
+        # split-K / reduction atomics make the summation order (not the math) run-dependent
+        tol = 2e-2 * max(ref.abs().max().item(), 1e-3 * gmax)
+        assert (p.grad - ref).abs().max().item() <= tol, k
     model.zero_grad(set_to_none=True)
     assert torch.allclose(logits2, logits, rtol=0, atol=1e-5 * logits.abs().max().item())
 
