@@ -197,10 +197,7 @@ class TrainPlan(Plan):
         self.run_ops(self.bwd_ops, None)
         grp = getattr(self.model, "_grad_allreduce", None)
         if grp is not None:
-            # data parallel (train.py:542-551): ONE exchange per step — mean of the flat gradient buffer over
-            # the ranks (NCCL over NVLink/NVSwitch); BatchNorm statistics stay per-GPU like the reference
-            import torch.distributed as dist
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.AVG, group=None if grp is True else grp)
+            allreduce_mean_(self.gflat, None if grp is True else grp)
 
     def profile(self, x: torch.Tensor) -> list[dict]:
         """Per-launch CUDA-event timing of one training step (forward list, then backward list with the
@@ -223,6 +220,24 @@ class TrainPlan(Plan):
             out += [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=flops.get(i, 0.0),
                          phase="bwd" if ops is self.bwd_ops else "fwd") for i, op in enumerate(ops)]
         return out
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Data parallel (train.py:542-551): the ONE exchange of the path — the flat gradient buffer is averaged
+    over the ranks with a single all-reduce (NCCL over NVLink/NVSwitch on the B200 box; gloo in the CPU
+    tests). BatchNorm statistics stay per-GPU like the reference (sync_bn: false)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        raise L.FvitError("enable_grad_allreduce() needs an initialised torch.distributed process group")
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:  # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    return flat
 
 
 class _FasterViTFunction(torch.autograd.Function):

@@ -1,0 +1,76 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: the flat-gradient all-reduce that makes
+data-parallel training one collective per step, and bench.py's rank handling under torchrun-style env."""
+import json
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT))
+    from fastervit_b200.engine_train import allreduce_mean_
+    import fastervit_b200 as F
+    # identical replicas (same seed), rank-dependent "gradients"
+    torch.manual_seed(0)
+    model = F.create_model("faster_vit_0_224", dim=16, in_dim=16, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8])
+    n = sum(p.numel() for p in model.parameters())
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    allreduce_mean_(flat)
+    expect = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(flat, expect)
+    # parameters of both replicas are bit-identical (what the gradient-only exchange relies on)
+    digest = float(sum(p.double().sum() for p in model.parameters()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, digest)
+    Path(out_dir, f"rank{rank}.json").write_text(json.dumps({"ok": bool(ok), "same_init": len(set(gathered)) == 1}))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = json.loads((tmp_path / f"rank{r}.json").read_text())
+        assert res["ok"] and res["same_init"], res
+
+
+def test_allreduce_requires_process_group():
+    from fastervit_b200.engine_train import allreduce_mean_
+    from fastervit_b200.lib import FvitError
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised in this interpreter")
+    with pytest.raises(FvitError):
+        allreduce_mean_(torch.zeros(4))
+
+
+def test_bench_reference_arm_only_rank0_prints():
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    outs = []
+    for rank in (1, 0):
+        env["RANK"] = env["LOCAL_RANK"] = str(rank)
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                            "--warmup", "1"], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == ""                       # rank 1: exits 0 without work
+    line = json.loads(outs[1].splitlines()[-1])  # rank 0: one JSON line
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["e2e"]["h2d_bytes_per_step"] == 0
