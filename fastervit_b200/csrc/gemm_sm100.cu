@@ -157,6 +157,8 @@ enum : uint32_t {
   EF_PRE = 1u << 8,
   EF_ATOMIC = 1u << 9,
   EF_ALPHAPTR = 1u << 10,
+  EF_CS2 = 1u << 11,
+  EF_RS = 1u << 12,
 };
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -312,8 +314,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool out32 = GENERIC ? (p.out_f32 != nullptr) : ((FEAT & EF_O32) != 0);
     const bool out16 = GENERIC ? (p.out_f16 != nullptr) : ((FEAT & EF_O16) != 0);
     const bool stats = GENERIC ? (p.col_sum != nullptr && !p.atomic_out) : ((FEAT & EF_STATS) != 0);
-    const bool has_cs2 = GENERIC && p.col_scale2 != nullptr;
-    const bool has_rs = GENERIC && p.row_scale != nullptr;
+    const bool has_cs2 = GENERIC ? (p.col_scale2 != nullptr) : ((FEAT & EF_CS2) != 0);
+    const bool has_rs = GENERIC ? (p.row_scale != nullptr) : ((FEAT & EF_RS) != 0);
     const bool has_pre = GENERIC ? (p.out_pre16 != nullptr) : ((FEAT & EF_PRE) != 0);
     const bool has_aptr = GENERIC ? (p.alpha_ptr != nullptr) : ((FEAT & EF_ALPHAPTR) != 0);
     const float alpha = has_aptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
@@ -728,7 +730,9 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (a->out_pre16) feat |= EF_PRE;
   if (p.atomic_out) feat |= EF_ATOMIC;
   if (a->alpha_ptr) feat |= EF_ALPHAPTR;
-  const bool needs_generic = a->col_scale2 || a->row_scale;
+  if (a->col_scale2) feat |= EF_CS2;
+  if (a->row_scale) feat |= EF_RS;
+  const bool needs_generic = false;
 #define FVIT_GEMM_LAUNCH(F)                                                                            \
   do {                                                                                                 \
     auto kfn = gemm_tcgen05_kernel<(F)>;                                                               \
@@ -755,6 +759,11 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
       // ---- training forward
       case FVIT_ACTF(0) | EF_O16 | EF_STATS: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O16 | EF_STATS);         // raw conv + BN statistics
       case FVIT_ACTF(2) | EF_O16 | EF_PRE: FVIT_GEMM_LAUNCH(FVIT_ACTF(2) | EF_O16 | EF_PRE);             // fc1 saving the pre-GELU value
+      case FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_RS: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_RS);  // branch + stochastic depth
+      case FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_CS2 | EF_PRE:
+        FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_CS2 | EF_PRE);                             // branch with layer scale
+      case FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_CS2 | EF_PRE | EF_RS:
+        FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_CS2 | EF_PRE | EF_RS);                     // layer scale + stochastic depth
       // ---- backward
       case FVIT_ACTF(0) | EF_O32 | EF_ATOMIC | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O32 | EF_ATOMIC | EF_ALPHAPTR);  // wgrad split-K
       case FVIT_ACTF(0) | EF_O32 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O32 | EF_ALPHAPTR);   // wgrad single pass

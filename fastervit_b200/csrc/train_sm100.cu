@@ -83,13 +83,15 @@ __global__ void affine_rows_kernel(const __half* __restrict__ x, long long ldx, 
                                    int nrows, int C, const float* __restrict__ scale,
                                    const float* __restrict__ shift, int act, const float* __restrict__ resid,
                                    long long ldr, float* __restrict__ out32, long long ldo32,
-                                   __half* __restrict__ out16, long long ldo16) {
+                                   __half* __restrict__ out16, long long ldo16,
+                                   const float* __restrict__ row_scale) {
   const int c8 = (C + 7) >> 3;
   const long long total = (long long)nrows * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % c8) * 8;
     const long long row = rows ? rows[i / c8] : i / c8;
+    const float rsc = row_scale ? row_scale[row] : 1.f;  // stochastic-depth mask / keep of this row
     float v[8];
     if (j + 8 <= C) {
       const uint4 pk = *reinterpret_cast<const uint4*>(x + row * ldx + j);
@@ -109,6 +111,7 @@ __global__ void affine_rows_kernel(const __half* __restrict__ x, long long ldx, 
         float y = fmaf(v[u], scale[j + u], shift[j + u]);
         if (act == FVIT_ACT_RELU) y = fmaxf(y, 0.f);
         else if (act == FVIT_ACT_GELU) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+        y *= rsc;
         if (resid) y += resid[row * ldr + j + u];
         v[u] = y;
       }
@@ -182,7 +185,8 @@ __global__ void pow2_norm_kernel(const float* __restrict__ v, int n, float* __re
 // out16[r][c] = (half)(x[src(r)][c] * colmul[c] * *scalar)   (fp32 -> fp16 operand cast of a gradient)
 __global__ void cast_scale_f16_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ rows,
                                       int nrows, int C, const float* __restrict__ colmul,
-                                      const float* __restrict__ scalar, __half* __restrict__ out, long long ldo) {
+                                      const float* __restrict__ scalar, __half* __restrict__ out, long long ldo,
+                                      const float* __restrict__ row_scale) {
   const int c4 = C >> 2;
   const float sc = scalar ? __ldg(scalar) : 1.f;
   const long long total = (long long)nrows * c4;
@@ -192,7 +196,8 @@ __global__ void cast_scale_f16_kernel(const float* __restrict__ x, long long ldx
     const long long r = i / c4;
     const long long src = rows ? rows[r] : r;
     float4 v = reinterpret_cast<const float4*>(x + src * ldx)[j];
-    float4 m = make_float4(sc, sc, sc, sc);
+    const float rsc = row_scale ? sc * row_scale[r] : sc;
+    float4 m = make_float4(rsc, rsc, rsc, rsc);
     if (colmul) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(colmul) + j);
       m.x *= g.x, m.y *= g.y, m.z *= g.z, m.w *= g.w;
@@ -212,7 +217,7 @@ template <int A16>
 __global__ void colsum_kernel(const void* __restrict__ a, long long lda, const int* __restrict__ a_rows,
                               const __half* __restrict__ b, long long ldb, int nrows, int C,
                               const float* __restrict__ colmul, const float* __restrict__ scalar,
-                              float* __restrict__ out) {
+                              float* __restrict__ out, const float* __restrict__ row_scale) {
   __shared__ float red[4][64];
   const int c = blockIdx.y * 64 + (threadIdx.x & 63);
   const int rl = threadIdx.x >> 6;
@@ -223,6 +228,7 @@ __global__ void colsum_kernel(const void* __restrict__ a, long long lda, const i
       float v = A16 ? __half2float(reinterpret_cast<const __half*>(a)[ra * lda + c])
                     : reinterpret_cast<const float*>(a)[ra * lda + c];
       if (b) v *= __half2float(b[(long long)r * ldb + c]);
+      if (row_scale) v *= row_scale[r];
       s += v;
     }
   }
@@ -563,7 +569,8 @@ __global__ void bn_bwd_reduce_kernel(const void* __restrict__ gin, long long ldg
                                      const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows,
                                      int nrows, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ w, const float* __restrict__ b, int act,
-                                     const float* __restrict__ colmul, float* __restrict__ s1, float* __restrict__ s2) {
+                                     const float* __restrict__ colmul, float* __restrict__ s1, float* __restrict__ s2,
+                                     const float* __restrict__ row_scale) {
   __shared__ float red[2][4][64];
   const int c = blockIdx.y * 64 + (threadIdx.x & 63);
   const int rl = threadIdx.x >> 6;
@@ -576,6 +583,7 @@ __global__ void bn_bwd_reduce_kernel(const void* __restrict__ gin, long long ldg
                      : reinterpret_cast<const float*>(gin)[rg * ldg + c];
       const float xh = (__half2float(raw[rr * ldr + c]) - mu) * rs;
       dy *= cm;
+      if (row_scale) dy *= row_scale[rg];
       if (act == FVIT_ACT_RELU && fmaf(xh, wc, bc) <= 0.f) dy = 0.f;
       a1 += dy;
       a2 += dy * xh;
@@ -599,7 +607,8 @@ __global__ void bn_bwd_apply_kernel(const void* __restrict__ gin, long long ldg,
                                     const float* __restrict__ b, int act, const float* __restrict__ colmul,
                                     const float* __restrict__ s1, const float* __restrict__ s2,
                                     const float* __restrict__ scalar, __half* __restrict__ out, long long ldo,
-                                    const int* __restrict__ o_rows, float* __restrict__ dw, float* __restrict__ db) {
+                                    const int* __restrict__ o_rows, float* __restrict__ dw, float* __restrict__ db,
+                                    const float* __restrict__ row_scale) {
   const long long total = (long long)nrows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -610,6 +619,7 @@ __global__ void bn_bwd_apply_kernel(const void* __restrict__ gin, long long ldg,
                    : reinterpret_cast<const float*>(gin)[rg * ldg + c];
     const float xh = (__half2float(raw[rr * ldr + c]) - mean[c]) * rstd[c];
     if (colmul) dy *= colmul[c];
+    if (row_scale) dy *= row_scale[rg];
     if (act == FVIT_ACT_RELU && fmaf(xh, w[c], b[c]) <= 0.f) dy = 0.f;
     out[ro * ldo + c] = __float2half_rn(w[c] * rstd[c] * (dy - s1[c] / count - xh * s2[c] / count));
   }
@@ -771,12 +781,13 @@ int fvit_bn_finalize(const float* sum, const float* sumsq, float count, const fl
 
 int fvit_affine_rows(const void* x16, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
                      const float* scale, const float* shift, int32_t act, const float* resid, int64_t ldr,
-                     float* out32, int64_t ldo32, void* out16, int64_t ldo16, void* stream) {
+                     float* out32, int64_t ldo32, void* out16, int64_t ldo16, const float* row_scale, void* stream) {
   FVIT_CHECK(x16 && scale && shift && nrows > 0 && C > 0 && (out32 || out16), "fvit_affine_rows: bad arguments");
   FVIT_CHECK(ldx % 8 == 0 && (!out16 || ldo16 % 8 == 0), "fvit_affine_rows: fp16 strides must be multiples of 8");
   const long long total = (long long)nrows * ((C + 7) / 8);
   affine_rows_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)x16, ldx, rows, nrows, C, scale, shift, act, resid, ldr, out32, ldo32, (__half*)out16, ldo16);
+      (const __half*)x16, ldx, rows, nrows, C, scale, shift, act, resid, ldr, out32, ldo32, (__half*)out16, ldo16,
+      row_scale);
   return post_launch("affine_rows_kernel");
 }
 
@@ -800,25 +811,27 @@ int fvit_pow2_norm(const float* v, int32_t n, float* out, void* stream) {
 }
 
 int fvit_cast_scale_f16(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
-                        const float* colmul, const float* scalar, void* out, int64_t ldo, void* stream) {
+                        const float* colmul, const float* scalar, void* out, int64_t ldo, const float* row_scale,
+                        void* stream) {
   FVIT_CHECK(x && out && nrows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0,
              "fvit_cast_scale_f16: bad arguments");
   const long long total = (long long)nrows * (C / 4);
   cast_scale_f16_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      x, ldx, rows, nrows, C, colmul, scalar, (__half*)out, ldo);
+      x, ldx, rows, nrows, C, colmul, scalar, (__half*)out, ldo, row_scale);
   return post_launch("cast_scale_f16_kernel");
 }
 
 int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_rows, const void* b16, int64_t ldb,
-                int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, void* stream) {
+                int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, const float* row_scale,
+                void* stream) {
   FVIT_CHECK(a && out && nrows > 0 && C > 0, "fvit_colsum: bad arguments");
   dim3 grid((unsigned)grid_cap(((long long)nrows + 15) / 16, 1, 24), (unsigned)((C + 63) / 64));
   if (a_is_f16)
     colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
-                                                             colmul, scalar, out);
+                                                             colmul, scalar, out, row_scale);
   else
     colsum_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
-                                                             colmul, scalar, out);
+                                                             colmul, scalar, out, row_scale);
   return post_launch("colsum_kernel");
 }
 
@@ -930,7 +943,7 @@ int fvit_scatter_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd
 int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g_rows, const void* raw16, int64_t ldr,
                 const int32_t* r_rows, int32_t nrows, int32_t C, const float* mean, const float* rstd, const float* w,
                 const float* b, int32_t act, const float* colmul, float* s1, float* s2, const float* scalar, void* out16,
-                int64_t ldo, const int32_t* o_rows, float* dw, float* db, void* stream) {
+                int64_t ldo, const int32_t* o_rows, float* dw, float* db, const float* row_scale, void* stream) {
   FVIT_CHECK(gin && raw16 && mean && rstd && w && b && s1 && s2 && out16 && dw && db && nrows > 0 && C > 0,
              "fvit_bn_bwd: bad arguments");
   FVIT_CHECK(act == FVIT_ACT_NONE || act == FVIT_ACT_RELU, "fvit_bn_bwd: act must be NONE or RELU");
@@ -941,16 +954,16 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
   const int g2 = grid_cap(total, 256, 16);
   if (g_is_f16) {
     bn_bwd_reduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
-                                                                    nrows, C, mean, rstd, w, b, act, colmul, s1, s2);
+                                                                    nrows, C, mean, rstd, w, b, act, colmul, s1, s2, row_scale);
     bn_bwd_apply_kernel<1><<<g2, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
                                                                  nrows, C, (float)nrows, mean, rstd, w, b, act, colmul, s1,
-                                                                 s2, scalar, (__half*)out16, ldo, o_rows, dw, db);
+                                                                 s2, scalar, (__half*)out16, ldo, o_rows, dw, db, row_scale);
   } else {
     bn_bwd_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
-                                                                    nrows, C, mean, rstd, w, b, act, colmul, s1, s2);
+                                                                    nrows, C, mean, rstd, w, b, act, colmul, s1, s2, row_scale);
     bn_bwd_apply_kernel<0><<<g2, 256, 0, (cudaStream_t)stream>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows,
                                                                  nrows, C, (float)nrows, mean, rstd, w, b, act, colmul, s1,
-                                                                 s2, scalar, (__half*)out16, ldo, o_rows, dw, db);
+                                                                 s2, scalar, (__half*)out16, ldo, o_rows, dw, db, row_scale);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return post_launch("bn_bwd kernels");

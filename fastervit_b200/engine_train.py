@@ -153,7 +153,7 @@ class TrainPlan(Plan):
                     ld_o32=gW_ld, flops=2.0 * rows * n_out * fk)
         if lin.bias is not None or bias_to is not None:
             dst = bias_to if bias_to is not None else self.G(lin.bias)
-            self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst)
+            self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst, None)
         if want_dgrad:
             self._bgemm(a=dz16, a_rows=rows, lda=lddz, b=w16, b_rows=n_out, ldb=ldw, b_mn=True, m=rows, n=k_in, kc=n_out,
                         alpha_ptr=dx_alpha if dx_alpha is not None else br["inv_s"], act=dx_act, aux=dx_aux,
@@ -162,9 +162,6 @@ class TrainPlan(Plan):
     # ------------------------------------------------------------------------------ plan construction
     def _build(self) -> None:
         m, B = self.model, self.B
-        if any(r > 0 for r in m.drop_path_rates):
-            raise L.FvitError("stochastic depth is not wired into the training kernels yet: create the model "
-                              "with drop_path_rate=0.0 for training (train.py --drop-path 0)")
         self.bwd_flops: dict[int, float] = {}
         self._setup_train()
         self._build_forward()
@@ -177,6 +174,8 @@ class TrainPlan(Plan):
     def run_forward(self, x: torch.Tensor) -> torch.Tensor:
         for t in self.fwd_zero:
             t.zero_()
+        if self.drop_specs:
+            self._gen_drop_masks()   # stochastic-depth masks of this step (torch RNG, like timm's DropPath)
         self.run_ops(self.prep_ops, None)
         self.run_ops(self.ops, x)
         for bn in self._bn_modules:

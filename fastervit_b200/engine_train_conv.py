@@ -70,7 +70,7 @@ def _emit_conv_part_train(self) -> dict:
     self.op_flops[len(self.ops) - 1] = 2.0 * npix1 * in_dim * 27
     _bn_finalize(self, bn1)
     self._op(self.ops, "fvit_affine_rows", raw1.data_ptr(), ld_in, stem_map.data_ptr(), npix1, in_dim, bn1["sc"].data_ptr(),
-             bn1["sh"].data_ptr(), L.ACT_RELU, None, 0, None, 0, planes.data_ptr(), ld_in)
+             bn1["sh"].data_ptr(), L.ACT_RELU, None, 0, None, 0, planes.data_ptr(), ld_in, None)
     # conv2 (stride 2) -> raw2 in the level-0 layout
     lvl = self._conv_level_train_buffers(0, dim, H0, W0, len(m.levels[0].blocks))
     w2, ldw2 = self._pack_conv("stem.conv2", pe[3])
@@ -83,7 +83,7 @@ def _emit_conv_part_train(self) -> dict:
     _bn_finalize(self, bn2)
     self._op(self.ops, "fvit_affine_rows", raw2.data_ptr(), lvl["ld"], lvl["pix"].data_ptr(), B * H0 * W0, dim,
              bn2["sc"].data_ptr(), bn2["sh"].data_ptr(), L.ACT_RELU, None, 0, lvl["x32"].data_ptr(), dim,
-             lvl["x16s"][0].data_ptr(), lvl["ld"])
+             lvl["x16s"][0].data_ptr(), lvl["ld"], None)
     st.update(col16=col16, w1=w1, raw1=raw1, planes=planes, bn1=bn1, w2=w2, ldw2=ldw2, raw2=raw2, bn2=bn2, to_l0=to_l0)
     self.stem_sv = st
     # conv levels
@@ -136,6 +136,9 @@ def _emit_conv_blocks_train(self, i: int, level, lv: dict) -> None:
         if hasattr(blk, "gamma"):
             raise L.FvitError("layer_scale_conv is not supported by the training kernels (unused by every shipped config)")
         nm = f"l{i}.b{j}"
+        rate = self.model.drop_path_rates[self._block_counter]
+        self._block_counter += 1
+        rs = self._drop_buf(f"levels.{i}.blocks.{j}", rate, B, (lv["H"] + 2) * (lv["W"] + 2))
         w1, ld1 = self._pack_conv(nm + ".conv1", blk.conv1)
         w2, ld2 = self._pack_conv(nm + ".conv2", blk.conv2)
         rawA = nb.new(nm + ".rawA", (rows, ld), torch.float16)
@@ -148,19 +151,19 @@ def _emit_conv_blocks_train(self, i: int, level, lv: dict) -> None:
                    out_f16=rawA.data_ptr(), ld_o16=ld, col_sum=bnA["st"][0].data_ptr(), col_sumsq=bnA["st"][1].data_ptr())
         _bn_finalize(self, bnA)
         self._op(self.ops, "fvit_affine_rows", rawA.data_ptr(), ld, lv["pix"].data_ptr(), npix, Cc, bnA["sc"].data_ptr(),
-                 bnA["sh"].data_ptr(), L.ACT_GELU, None, 0, None, 0, lv["h16"].data_ptr(), ld)
+                 bnA["sh"].data_ptr(), L.ACT_GELU, None, 0, None, 0, lv["h16"].data_ptr(), ld, None)
         self._gemm(a=lv["h16"].data_ptr(), a_rows=rows, lda=ld, b=w2.data_ptr(), ldb=ld2, m=rows, n=Cc, kc=Cc, taps=taps,
                    m_alg=npix, col_shift=blk.conv2.bias.data_ptr(), row_map=lv["interior"].data_ptr(),
                    out_f16=rawB.data_ptr(), ld_o16=ld, col_sum=bnB["st"][0].data_ptr(), col_sumsq=bnB["st"][1].data_ptr())
         _bn_finalize(self, bnB)
         self._op(self.ops, "fvit_affine_rows", rawB.data_ptr(), ld, lv["pix"].data_ptr(), npix, Cc, bnB["sc"].data_ptr(),
-                 bnB["sh"].data_ptr(), L.ACT_NONE, lv["x32"].data_ptr(), Cc, lv["x32"].data_ptr(), Cc, xout.data_ptr(), ld)
+                 bnB["sh"].data_ptr(), L.ACT_NONE, lv["x32"].data_ptr(), Cc, lv["x32"].data_ptr(), Cc, xout.data_ptr(), ld, rs)
         # data-gradient operands: flipped / transposed packed weights
         wT1 = nb.new(nm + ".conv1.wT16", (Cc, 9 * _ru(Cc, 64)), torch.float16)
         wT2 = nb.new(nm + ".conv2.wT16", (Cc, 9 * _ru(Cc, 64)), torch.float16)
         self._op(self.prep_ops, "fvit_pack_conv3x3_f16", blk.conv1.weight.data_ptr(), wT1.data_ptr(), Cc, Cc, _ru(Cc, 64), 1)
         self._op(self.prep_ops, "fvit_pack_conv3x3_f16", blk.conv2.weight.data_ptr(), wT2.data_ptr(), Cc, Cc, _ru(Cc, 64), 1)
-        lv["blocks_sv"].append(dict(blk=blk, rawA=rawA, rawB=rawB, bnA=bnA, bnB=bnB, xin=xin, wT1=wT1, wT2=wT2))
+        lv["blocks_sv"].append(dict(blk=blk, rawA=rawA, rawB=rawB, bnA=bnA, bnB=bnB, xin=xin, wT1=wT1, wT2=wT2, rs=rs))
 
 
 def _emit_downsample_train(self, i: int, src: dict, dst: dict) -> None:
@@ -240,7 +243,7 @@ def _emit_downsample_bwd(self, ds: dict, src: dict, dst: dict) -> None:
     mod = ds["mod"]
     # gradient of the conv output in plane space (border rows read the buffer's zero row)
     self._op(ops, "fvit_cast_scale_f16", dst["g"].data_ptr(), 2 * Cs, ds["rmap_g"].data_ptr(), pl_rows, 2 * Cs, None, None,
-             ds["dY"].data_ptr(), 2 * Cs)
+             ds["dY"].data_ptr(), 2 * Cs, None)
     shifts = [p * pl_rows + s for (s, p) in ds["taps"]]
     _conv_wgrad(self, dz=ds["dY"].data_ptr(), lddz=2 * Cs, x=ds["planes"].data_ptr(), ldx=ld, x_rows=4 * pl_rows,
                 rows=pl_rows, cout=2 * Cs, cin=Cs, shifts=shifts, conv_weight=mod.reduction[0].weight, name=f"ds{ds['i']}")
@@ -268,25 +271,25 @@ def _emit_conv_blocks_bwd(self, lv: dict) -> None:
         self._op(ops, "fvit_bn_bwd", g, 0, Cc, pix, sv["rawB"].data_ptr(), ld, pix, npix, Cc, bnB["mu"].data_ptr(),
                  bnB["rs"].data_ptr(), blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr(), L.ACT_NONE, None,
                  bnB["s12"][0].data_ptr(), bnB["s12"][1].data_ptr(), inv, lv["dzB"].data_ptr(), ld, pix,
-                 self.G(blk.norm2.weight), self.G(blk.norm2.bias))
+                 self.G(blk.norm2.weight), self.G(blk.norm2.bias), sv["rs"])
         # recompute h = GELU(pre), pre = BN1(rawA) from the saved raw output
         self._op(ops, "fvit_affine_rows", sv["rawA"].data_ptr(), ld, pix, npix, Cc, bnA["sc"].data_ptr(), bnA["sh"].data_ptr(),
-                 L.ACT_GELU, None, 0, None, 0, lv["h16"].data_ptr(), ld)
+                 L.ACT_GELU, None, 0, None, 0, lv["h16"].data_ptr(), ld, None)
         self._op(ops, "fvit_affine_rows", sv["rawA"].data_ptr(), ld, pix, npix, Cc, bnA["sc"].data_ptr(), bnA["sh"].data_ptr(),
-                 L.ACT_NONE, None, 0, None, 0, lv["pre16"].data_ptr(), ld)
+                 L.ACT_NONE, None, 0, None, 0, lv["pre16"].data_ptr(), ld, None)
         _conv_wgrad(self, dz=lv["dzB"].data_ptr(), lddz=ld, x=lv["h16"].data_ptr(), ldx=ld, x_rows=rows, rows=rows, cout=Cc,
                     cin=Cc, shifts=shifts, conv_weight=blk.conv2.weight, name="convB")
-        self._op(ops, "fvit_colsum", lv["dzB"].data_ptr(), 1, ld, None, None, 0, rows, Cc, None, inv, self.G(blk.conv2.bias))
+        self._op(ops, "fvit_colsum", lv["dzB"].data_ptr(), 1, ld, None, None, 0, rows, Cc, None, inv, self.G(blk.conv2.bias), None)
         self._bgemm(a=lv["dzB"].data_ptr(), a_rows=rows, lda=ld, b=sv["wT2"].data_ptr(), b_rows=Cc, ldb=9 * _ru(Cc, 64),
                     m=rows, n=Cc, kc=Cc, taps=lv["taps"], act=L.ACT_GELU_BWD, aux=lv["pre16"].data_ptr(), ld_aux=ld,
                     row_map=interior, out_f16=lv["dyA"].data_ptr(), ld_o16=ld, flops=2.0 * npix * Cc * Cc * 9)
         self._op(ops, "fvit_bn_bwd", lv["dyA"].data_ptr(), 1, ld, pix, sv["rawA"].data_ptr(), ld, pix, npix, Cc,
                  bnA["mu"].data_ptr(), bnA["rs"].data_ptr(), blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(), L.ACT_NONE,
                  None, bnA["s12"][0].data_ptr(), bnA["s12"][1].data_ptr(), inv, lv["dzA"].data_ptr(), ld, pix,
-                 self.G(blk.norm1.weight), self.G(blk.norm1.bias))
+                 self.G(blk.norm1.weight), self.G(blk.norm1.bias), None)
         _conv_wgrad(self, dz=lv["dzA"].data_ptr(), lddz=ld, x=sv["xin"].data_ptr(), ldx=ld, x_rows=rows, rows=rows, cout=Cc,
                     cin=Cc, shifts=shifts, conv_weight=blk.conv1.weight, name="convA")
-        self._op(ops, "fvit_colsum", lv["dzA"].data_ptr(), 1, ld, None, None, 0, rows, Cc, None, inv, self.G(blk.conv1.bias))
+        self._op(ops, "fvit_colsum", lv["dzA"].data_ptr(), 1, ld, None, None, 0, rows, Cc, None, inv, self.G(blk.conv1.bias), None)
         # g += conv1 data gradient
         self._bgemm(a=lv["dzA"].data_ptr(), a_rows=rows, lda=ld, b=sv["wT1"].data_ptr(), b_rows=Cc, ldb=9 * _ru(Cc, 64),
                     m=rows, n=Cc, kc=Cc, taps=lv["taps"], row_map=interior, resid=g, ld_resid=Cc, out_f32=g, ld_o32=Cc,
@@ -315,7 +318,7 @@ def _emit_conv_part_bwd(self) -> None:
     self._op(ops, "fvit_bn_bwd", lv0["g"].data_ptr(), 0, dim, lv0["pix"].data_ptr(), st["raw2"].data_ptr(), lv0["ld"],
              lv0["pix"].data_ptr(), B * H0 * W0, dim, bn2["mu"].data_ptr(), bn2["rs"].data_ptr(), pe[4].weight.data_ptr(),
              pe[4].bias.data_ptr(), L.ACT_RELU, None, bn2["s12"][0].data_ptr(), bn2["s12"][1].data_ptr(), inv,
-             dY2.data_ptr(), lv0["ld"], q_of_pix.data_ptr(), self.G(pe[4].weight), self.G(pe[4].bias))
+             dY2.data_ptr(), lv0["ld"], q_of_pix.data_ptr(), self.G(pe[4].weight), self.G(pe[4].bias), None)
     taps = self._s2_taps(W0)
     shifts = [p * pl_rows + s for (s, p) in taps]
     _conv_wgrad(self, dz=dY2.data_ptr(), lddz=lv0["ld"], x=st["planes"].data_ptr(), ldx=ld_in, x_rows=4 * pl_rows,
@@ -336,7 +339,7 @@ def _emit_conv_part_bwd(self) -> None:
     self._op(ops, "fvit_bn_bwd", dplanes.data_ptr(), 1, ld_in, st["stem_map"].data_ptr(), st["raw1"].data_ptr(), ld_in,
              st["stem_map"].data_ptr(), npix1, in_dim, bn1["mu"].data_ptr(), bn1["rs"].data_ptr(), pe[1].weight.data_ptr(),
              pe[1].bias.data_ptr(), L.ACT_RELU, None, bn1["s12"][0].data_ptr(), bn1["s12"][1].data_ptr(), inv, dz1.data_ptr(),
-             ld_in, None, self.G(pe[1].weight), self.G(pe[1].bias))
+             ld_in, None, self.G(pe[1].weight), self.G(pe[1].bias), None)
     self._bgemm(a=dz1.data_ptr(), a_rows=npix1, lda=ld_in, a_mn=True, b=st["col16"].data_ptr(), b_rows=npix1, ldb=self.STEM_LD,
                 b_mn=True, m=in_dim, n=27, kc=npix1, split_k=self._split_k(in_dim, 27, npix1), alpha_ptr=inv,
                 out_f32=self.G(pe[0].weight), ld_o32=27, flops=2.0 * npix1 * in_dim * 27)

@@ -16,10 +16,33 @@ def P(t):
     return None if t is None else t.data_ptr()
 
 
+def _drop_buf(self, name: str, rate: float, groups: int, group_size: int):
+    """row-scale vector (mask / keep per row) of one stochastic-depth site (timm DropPath: one Bernoulli draw
+    per leading index — per window for x, per image for carrier tokens and ConvBlocks; fv.py:500,630,652).
+    Returns the device pointer or None when the rate is 0."""
+    if rate <= 0.0:
+        return None
+    buf = self.bufs.new(name + ".droppath", (groups * group_size,), torch.float32)
+    self.drop_specs.append(dict(name=name, buf=buf, groups=groups, gs=group_size, keep=1.0 - rate))
+    return buf.data_ptr()
+
+
+def _gen_drop_masks(self) -> None:
+    forced = getattr(self, "forced_drop_masks", None) or {}
+    for d in self.drop_specs:
+        if d["name"] in forced:
+            m = forced[d["name"]].to(device=d["buf"].device, dtype=torch.float32)
+        else:
+            m = torch.bernoulli(torch.full((d["groups"],), d["keep"], device=d["buf"].device)) / d["keep"]
+        d["buf"].view(d["groups"], d["gs"]).copy_(m.view(-1, 1).expand(d["groups"], d["gs"]))
+
+
 # ====================================================================================== forward (train)
 def _build_forward(self) -> None:
     m, B = self.model, self.B
     cfg = m.cfg
+    self.drop_specs: list[dict] = []
+    self._block_counter = 0
     self._bn_modules = [mod for mod in m.modules() if isinstance(mod, nn.BatchNorm2d)]
     self.lv: list[dict] = []          # per-level geometry/buffers (+ "sv": saved activations)
     self.ds: list[dict] = []          # per-downsample saved state
@@ -81,7 +104,7 @@ def _bias_train(self, nm: str, rpb, S: int) -> dict:
 
 
 def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, y16, qkv, ao, bias, stream_buf,
-                    u16) -> dict:
+                    u16, rs=None) -> dict:
     """Train-mode copy of Plan._emit_attention: same three launches, un-folded layer scale so that the
     branch output u = proj(...) + b can be saved (u16) for the layer-scale gradient."""
     Cc, h, hd = attn.qkv.in_features, attn.num_heads, attn.head_dim
@@ -126,14 +149,14 @@ def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, 
                  0, 1)
     has_ls = isinstance(gamma, torch.Tensor)
     self._gemm_train_branch(a=ao.data_ptr(), lda=Cp, w=wp.data_ptr(), ldw=ldp, rows=rows, n=n, k=Cp, bias=lin.bias,
-                            gamma=gamma if has_ls else None, stream_buf=stream_buf, u16=u16 if has_ls else None)
+                            gamma=gamma if has_ls else None, stream_buf=stream_buf, u16=u16 if has_ls else None, rs=rs)
     self.op_flops[len(self.ops) - 1] = 2.0 * rows * n * Cc
-    return dict(attn=attn, wq=wq, ldq=ldq, wp=wp, ldp=ldp, hd=hd, hdp=hdp, Cp=Cp, use_tc=use_tc, scale=scale, S=S,
+    return dict(rs=rs, attn=attn, wq=wq, ldq=ldq, wp=wp, ldp=ldp, hd=hd, hdp=hdp, Cp=Cp, use_tc=use_tc, scale=scale, S=S,
                 groups=groups, rows=rows, qkv=qkv, ao=ao, y16=y16, bias=bias, u16=u16 if has_ls else None)
 
 
-def _gemm_train_branch(self, *, a, lda, w, ldw, rows, n, k, bias, gamma, stream_buf, u16) -> None:
-    """x += gamma * (a @ W^T + b), saving u = a @ W^T + b (fp16) when gamma is a parameter."""
+def _gemm_train_branch(self, *, a, lda, w, ldw, rows, n, k, bias, gamma, stream_buf, u16, rs=None) -> None:
+    """x += droppath_row * gamma * (a @ W^T + b), saving u = a @ W^T + b (fp16) when gamma is a parameter."""
     g = L.GemmArgs()
     g.a, g.a_rows, g.lda, g.a_planes = a, rows, lda, 1
     g.b, g.b_rows, g.ldb = w, n, ldw
@@ -143,6 +166,7 @@ def _gemm_train_branch(self, *, a, lda, w, ldw, rows, n, k, bias, gamma, stream_
     if gamma is not None:
         g.col_scale2 = gamma.data_ptr()
         g.out_pre16, g.ld_out_pre16 = u16.data_ptr(), n
+    g.row_scale = rs
     g.resid, g.ld_resid, g.out_f32, g.ld_out_f32 = stream_buf, n, stream_buf, n
     self._gemm_keep.append(g)
     import ctypes as C
@@ -176,7 +200,15 @@ def _emit_token_level_train(self, i: int, level, tl: dict) -> None:
 
     for j, blk in enumerate(level.blocks):
         nm = f"l{i}.b{j}"
+        key = f"levels.{i}.blocks.{j}"
+        rate = self.model.drop_path_rates[self._block_counter]
+        self._block_counter += 1
         sv: dict = dict(blk=blk)
+        sv["rs_attn"] = self._drop_buf(key + ".attn", rate, nW, S)
+        sv["rs_mlp"] = self._drop_buf(key + ".mlp", rate, nW, S)
+        if has_ct:
+            sv["rs_hat_attn"] = self._drop_buf(key + ".hat_attn", rate, B, n_ct)
+            sv["rs_hat_mlp"] = self._drop_buf(key + ".hat_mlp", rate, B, n_ct)
         sv["pe"] = self._posemb_train(nm + ".pe", blk.pos_embed, ws, Cc)
         if has_ct:
             ctr_ptr = xs_ptr + tl["ctr0"] * Cc * 4
@@ -197,12 +229,12 @@ def _emit_token_level_train(self, i: int, level, tl: dict) -> None:
                      c["y1"].data_ptr(), Cc, None, c["mu1"].data_ptr(), c["rs1"].data_ptr(), c["xh1"].data_ptr(), Cc)
             sv["c_bias"] = self._bias_train(nm + ".hat_bias", blk.hat_attn.pos_emb_funct, n_ct)
             sv["c_attn"] = self._attn_fwd_train(nm + ".hat_attn", blk.hat_attn, blk.gamma1, rows_c, B, n_ct, c["y1"],
-                                                c["qkv"], c["ao"], sv["c_bias"], ctr_ptr, c["u1"])
+                                                c["qkv"], c["ao"], sv["c_bias"], ctr_ptr, c["u1"], sv["rs_hat_attn"])
             self._op(self.ops, "fvit_ln_fwd", ctr_ptr, Cc, None, rows_c, Cc, None, 1, 0, None, 0,
                      blk.hat_norm2.weight.data_ptr(), blk.hat_norm2.bias.data_ptr(), float(blk.hat_norm2.eps),
                      c["y2"].data_ptr(), Cc, None, c["mu2"].data_ptr(), c["rs2"].data_ptr(), c["xh2"].data_ptr(), Cc)
             sv["c_mlp"] = self._mlp_fwd_train(nm + ".hat_mlp", blk.hat_mlp, blk.gamma2, rows_c, c["y2"], c["p"], c["h"],
-                                              ctr_ptr, c["u2"])
+                                              ctr_ptr, c["u2"], sv["rs_hat_mlp"])
         w = dict(y1=new16(nm + ".w.y1", rows, Cc), xh1=new16(nm + ".w.xh1", rows, Cc), rs1=new32(nm + ".w.rs1", rows),
                  mu1=new32(nm + ".w.mu1", rows), y2=new16(nm + ".w.y2", rows, Cc), xh2=new16(nm + ".w.xh2", rows, Cc),
                  rs2=new32(nm + ".w.rs2", rows), mu2=new32(nm + ".w.mu2", rows), qkv=new16(nm + ".w.qkv", rows, 3 * Cp),
@@ -215,11 +247,12 @@ def _emit_token_level_train(self, i: int, level, tl: dict) -> None:
                  w["xh1"].data_ptr(), Cc)
         sv["w_bias"] = self._bias_train(nm + ".bias", blk.attn.pos_emb_funct, S)
         sv["w_attn"] = self._attn_fwd_train(nm + ".attn", blk.attn, blk.gamma3, rows, nW, S, w["y1"], w["qkv"], w["ao"],
-                                            sv["w_bias"], xs_ptr, w["u1"])
+                                            sv["w_bias"], xs_ptr, w["u1"], sv["rs_attn"])
         self._op(self.ops, "fvit_ln_fwd", xs_ptr, Cc, None, rows, Cc, None, 1, 0, None, 0, blk.norm2.weight.data_ptr(),
                  blk.norm2.bias.data_ptr(), float(blk.norm2.eps), w["y2"].data_ptr(), Cc, None, w["mu2"].data_ptr(),
                  w["rs2"].data_ptr(), w["xh2"].data_ptr(), Cc)
-        sv["w_mlp"] = self._mlp_fwd_train(nm + ".mlp", blk.mlp, blk.gamma4, rows, w["y2"], w["p"], w["h"], xs_ptr, w["u2"])
+        sv["w_mlp"] = self._mlp_fwd_train(nm + ".mlp", blk.mlp, blk.gamma4, rows, w["y2"], w["p"], w["h"], xs_ptr, w["u2"],
+                                          sv["rs_mlp"])
         if has_ct and blk.last and blk.do_propagation:
             g1 = blk.gamma1.data_ptr() if isinstance(blk.gamma1, torch.Tensor) else None
             self._op(self.ops, "fvit_propagate_fwd", xs_ptr, Cc, tl["prop_src"].data_ptr(), rows, Cc, g1)
@@ -233,7 +266,7 @@ def _emit_token_level_train(self, i: int, level, tl: dict) -> None:
     tl["dqkv"] = nb.new(f"l{i}.dqkv", (max(rows, 1), 3 * Cp), torch.float16)
 
 
-def _mlp_fwd_train(self, nm: str, mlp, gamma, rows: int, y16, p16, h16, stream_buf, u16) -> dict:
+def _mlp_fwd_train(self, nm: str, mlp, gamma, rows: int, y16, p16, h16, stream_buf, u16, rs=None) -> dict:
     n1, k1 = mlp.fc1.weight.shape
     w1, ld1 = self._pack_linear(nm + ".fc1", mlp.fc1)
     # fc1: pre-GELU saved through out_pre16, GELU output is the fc2 operand
@@ -253,8 +286,8 @@ def _mlp_fwd_train(self, nm: str, mlp, gamma, rows: int, y16, p16, h16, stream_b
     has_ls = isinstance(gamma, torch.Tensor)
     self._gemm_train_branch(a=h16.data_ptr(), lda=k2, w=w2.data_ptr(), ldw=ld2, rows=rows, n=n2, k=k2,
                             bias=mlp.fc2.bias, gamma=gamma if has_ls else None, stream_buf=stream_buf,
-                            u16=u16 if has_ls else None)
-    return dict(mlp=mlp, w1=w1, ld1=ld1, w2=w2, ld2=ld2, rows=rows, y16=y16, p16=p16, h16=h16,
+                            u16=u16 if has_ls else None, rs=rs)
+    return dict(rs=rs, mlp=mlp, w1=w1, ld1=ld1, w2=w2, ld2=ld2, rows=rows, y16=y16, p16=p16, h16=h16,
                 u16=u16 if has_ls else None)
 
 
@@ -309,11 +342,11 @@ def _emit_head_bwd(self, feat: dict) -> None:
     ops = self.bwd_ops
     if ncls % 4 == 0:
         self._op(ops, "fvit_cast_scale_f16", self._dlogits.data_ptr(), ncls, None, B, ncls, None, ("scal", 0),
-                 dl16.data_ptr(), ldl)
+                 dl16.data_ptr(), ldl, None)
     else:
         raise L.FvitError("num_classes must be a multiple of 4 for the training kernels")
     self._op(ops, "fvit_colsum", self._dlogits.data_ptr(), 0, ncls, None, None, 0, B, ncls, None, None,
-             self.G(m.head.bias))
+             self.G(m.head.bias), None)
     # dW_head = dl^T pooled ; dpooled = dl W_head
     self._bgemm(a=dl16.data_ptr(), a_rows=B, lda=ldl, a_mn=True, b=hs["pooled"].data_ptr(), b_rows=B,
                 ldb=hs["pooled"].stride(0), b_mn=True, m=ncls, n=nf, kc=B, alpha_ptr=inv, out_f32=self.G(m.head.weight),
@@ -350,10 +383,10 @@ def _mlp_bwd(self, tl: dict, ms: dict, gamma, g_ptr: int, rows: int, ln: nn.Laye
     Cc, hid = mlp.fc1.weight.shape[1], mlp.fc1.weight.shape[0]
     br = self._branch(gamma)
     dz, dp, dy = tl["dz"], tl["dp"], tl["dy"]
-    self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc)
+    self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, ms["rs"])
     if br["gamma"] is not None:
         self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, ms["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
-                 self.G(gamma))
+                 self.G(gamma), ms["rs"])
     # fc2: dW2, db2, dp = (dz W2) o gelu'(p)
     self._linear_bwd(lin=mlp.fc2, w16=ms["w2"].data_ptr(), ldw=ms["ld2"], x16=ms["h16"].data_ptr(), ldx=hid,
                      dz16=dz.data_ptr(), lddz=Cc, rows=rows, n_out=Cc, k_in=hid, br=br, dx16=dp.data_ptr(), lddx=hid,
@@ -375,10 +408,10 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     br = self._branch(gamma)
     dz, dy, dao, dqkv = tl["dz"], tl["dy"], tl["dao"], tl["dqkv"]
     padded = hdp != hd
-    self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc)
+    self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, at["rs"])
     if br["gamma"] is not None:
         self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, at["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
-                 self.G(gamma))
+                 self.G(gamma), at["rs"])
     # proj
     if padded:
         gWp = ("scr", self._scratch("dWproj_pad", Cc * Cp))
@@ -465,10 +498,10 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
     br = self._branch(blk.gamma1)
     dz, dy, dao, dqkv = tl["dz"], tl["dy"], tl["dao"], tl["dqkv"]
     padded = hdp != hd
-    self._op(ops, "fvit_cast_scale_f16", gc_ptr, Cc, None, rows_c, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc)
+    self._op(ops, "fvit_cast_scale_f16", gc_ptr, Cc, None, rows_c, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, at["rs"])
     if br["gamma"] is not None:
         self._op(ops, "fvit_colsum", gc_ptr, 0, Cc, None, at["u16"].data_ptr(), Cc, rows_c, Cc, None, ("scal", 1),
-                 self.G(blk.gamma1))
+                 self.G(blk.gamma1), at["rs"])
     gWp = ("scr", self._scratch("dWproj_pad_c", Cc * Cp)) if padded else self.G(attn.proj.weight)
     self._linear_bwd(lin=attn.proj, w16=at["wp"].data_ptr(), ldw=at["ldp"], x16=at["ao"].data_ptr(), ldx=Cp,
                      dz16=dz.data_ptr(), lddz=Cc, rows=rows_c, n_out=Cc, k_in=Cp, br=br, gW=gWp, gW_ld=Cp,

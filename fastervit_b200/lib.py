@@ -95,12 +95,12 @@ _OP_SIGS: dict[str, list] = {
     "fvit_vec_headpad_f32": [_P, _P, _I, _I, _I, _P],
     "fvit_colstats_f32": [_P, _L, _P, _I, _I, _P, _P, _P],
     "fvit_bn_finalize": [_P, _P, _F, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P],
-    "fvit_affine_rows": [_P, _L, _P, _I, _I, _P, _P, _I, _P, _L, _P, _L, _P, _L, _P],
+    "fvit_affine_rows": [_P, _L, _P, _I, _I, _P, _P, _I, _P, _L, _P, _L, _P, _L, _P, _P],
     "fvit_grad_scale_init": [_P, _I, _F, _P, _P],
     "fvit_vec_mul": [_P, _I, _P, _I, _P, _I, _P],
     "fvit_pow2_norm": [_P, _I, _P, _P],
-    "fvit_cast_scale_f16": [_P, _L, _P, _I, _I, _P, _P, _P, _L, _P],
-    "fvit_colsum": [_P, _I, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P],
+    "fvit_cast_scale_f16": [_P, _L, _P, _I, _I, _P, _P, _P, _L, _P, _P],
+    "fvit_colsum": [_P, _I, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P],
     "fvit_group_sum": [_P, _L, _I, _I, _I, _I, _P, _P, _P],
     "fvit_ln_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _P, _L, _P, _I, _I, _P, _P, _P, _P],
     "fvit_attn_core_bwd": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
@@ -109,7 +109,7 @@ _OP_SIGS: dict[str, list] = {
     "fvit_cpb_mlp_bwd": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "fvit_pool_bn_bwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _L, _P, _P, _P],
     "fvit_scatter_add_rows": [_P, _L, _P, _L, _P, _I, _I, _P],
-    "fvit_bn_bwd": [_P, _I, _L, _P, _P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P],
+    "fvit_bn_bwd": [_P, _I, _L, _P, _P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P],
     "fvit_unpack_conv_grad": [_P, _I, _P, _I, _I, _P],
     "fvit_token_init_bwd": [_P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P],
     "fvit_propagate_bwd": [_P, _L, _P, _L, _P, _I, _I, _P, _P, _P, _P],

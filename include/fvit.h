@@ -189,8 +189,8 @@ int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, in
  * fvit_bn_finalize : from (sum, sumsq, count) -> biased var for normalisation, running statistics
  *   update (momentum, unbiased var), epilogue vectors scale = w*rstd*[ls], shift = (b - mean*w*rstd)*[ls],
  *   and mean / rstd for the backward pass.
- * fvit_affine_rows : y = act(x16[row]*scale + shift) (+ resid32[row]) over a row list, fp32/fp16 out
- *   (normalise + ReLU/GELU (+ residual) of a raw convolution output). */
+ * fvit_affine_rows : y = act(x16[row]*scale + shift) * row_scale[row] (+ resid32[row]) over a row list,
+ *   fp32/fp16 out (normalise + ReLU/GELU (+ stochastic-depth mask, + residual) of a raw convolution output). */
 int fvit_colstats_f32(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C, float* sum,
                       float* sumsq, void* stream);
 int fvit_bn_finalize(const float* sum, const float* sumsq, float count, const float* w, const float* b, float eps,
@@ -198,7 +198,7 @@ int fvit_bn_finalize(const float* sum, const float* sumsq, float count, const fl
                      float* scale, float* shift, float* mean_out, float* rstd_out, int32_t C, void* stream);
 int fvit_affine_rows(const void* x16, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
                      const float* scale, const float* shift, int32_t act, const float* resid, int64_t ldr,
-                     float* out32, int64_t ldo32, void* out16, int64_t ldo16, void* stream);
+                     float* out32, int64_t ldo32, void* out16, int64_t ldo16, const float* row_scale, void* stream);
 
 /* ---- positional MLPs (cpb_mlp: Linear(2,512)+ReLU+Linear(512,D, no bias); fv.py:223-225, 322-324) --
  * out[p][d] for P coordinate pairs; hidden_out (optional, [P,512]) saves the ReLU output. */
@@ -240,14 +240,17 @@ int fvit_vec_mul(const float* a, int32_t a_stride, const float* b, int32_t b_str
 /* out = {s, 1/s} with s = 2^-floor(log2(max|v|)) (normaliser of a layer-scale vector gamma, fv.py:637-655,
  * so that gamma*s is O(1) and fp16 products with gamma = 1e-5 do not underflow). */
 int fvit_pow2_norm(const float* v, int32_t n, float* out, void* stream);
-/* out16[r][c] = (half)(x[rows ? rows[r] : r][c] * colmul[c] * *scalar): tensor-core operand copy of a
- * fp32 gradient (colmul = layer scale, scalar = its normaliser; both optional). */
+/* out16[r][c] = (half)(x[rows ? rows[r] : r][c] * colmul[c] * *scalar * row_scale[r]): tensor-core operand copy
+ * of a fp32 gradient (colmul = layer scale, scalar = its normaliser, row_scale = stochastic-depth mask/keep;
+ * all optional). fvit_colsum and fvit_bn_bwd take the same optional row_scale (indexed by r / by the g row). */
 int fvit_cast_scale_f16(const float* x, int64_t ldx, const int32_t* rows, int32_t nrows, int32_t C,
-                        const float* colmul, const float* scalar, void* out, int64_t ldo, void* stream);
+                        const float* colmul, const float* scalar, void* out, int64_t ldo, const float* row_scale,
+                        void* stream);
 /* out[c] += *scalar * colmul[c] * sum_r a[a_rows ? a_rows[r] : r][c] * (b16 ? b16[r][c] : 1): bias, LayerNorm /
  * BatchNorm affine and layer-scale gradients. a is fp32 or fp16 (a_is_f16). */
 int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_rows, const void* b16, int64_t ldb,
-                int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, void* stream);
+                int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, const float* row_scale,
+                void* stream);
 /* out[t - skip][c] += *scalar * sum_w a[w*group + t][c], skip <= t < group: gradient of a positional
  * embedding broadcast-added to every window (fv.py:366). */
 int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, int32_t skip, int32_t C,
@@ -292,7 +295,7 @@ int fvit_scatter_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd
 int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g_rows, const void* raw16, int64_t ldr,
                 const int32_t* r_rows, int32_t nrows, int32_t C, const float* mean, const float* rstd, const float* w,
                 const float* b, int32_t act, const float* colmul, float* s1, float* s2, const float* scalar, void* out16,
-                int64_t ldo, const int32_t* o_rows, float* dw, float* db, void* stream);
+                int64_t ldo, const int32_t* o_rows, float* dw, float* db, const float* row_scale, void* stream);
 /* dst[co][ci][tap] += src[tap][co][ci]: the 9 per-tap weight-gradient GEMM outputs -> nn.Conv2d layout. */
 int fvit_unpack_conv_grad(const float* src, int32_t ld_ci, float* dst, int32_t cout, int32_t cin, void* stream);
 /* TokenInitializer backward (fv.py:733-738): gx[pixel rows] += d/dx, dw [C,9], dbias [C] from the carrier-row

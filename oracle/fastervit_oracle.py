@@ -156,8 +156,18 @@ def _gamma(sd, key):
     return 1 if g is None else g
 
 
-def hat_block(sd, prefix, x, ct, *, num_heads, ws, sr, ct_size, last, do_propagation, square, quant):
-    """HAT.forward (fv.py:662-701; fvar.py:668-707). sr = (sr_h, sr_w)."""
+def _dp(t, masks, key):
+    """timm DropPath with an explicit mask: t * (bernoulli/keep)[:, None, ...] (identity without a mask)."""
+    if masks is None or key not in masks:
+        return t
+    m = masks[key].to(t.dtype)
+    return t * m.view(-1, *([1] * (t.dim() - 1)))
+
+
+def hat_block(sd, prefix, x, ct, *, num_heads, ws, sr, ct_size, last, do_propagation, square, quant, masks=None):
+    """HAT.forward (fv.py:662-701; fvar.py:668-707). sr = (sr_h, sr_w). `masks` (optional) holds explicit
+    stochastic-depth factors per drop_path call site: prefix + .attn/.mlp (per window), .hat_attn/.hat_mlp
+    (per image) — the reference draws them with torch RNG (fv.py:679-680, 690-691)."""
     B, T, N = x.shape
     x = x + pos_embed_1d(sd, prefix + ".pos_embed", T, x.dtype)
     do_sr = sr[0] > 1 or sr[1] > 1
@@ -167,17 +177,18 @@ def hat_block(sd, prefix, x, ct, *, num_heads, ws, sr, ct_size, last, do_propaga
         if square:
             ct = ct + pos_embed_1d(sd, prefix + ".hat_pos_embed", ct.shape[1], x.dtype)
         n_ct = ct.shape[1]
-        ct = ct + _gamma(sd, prefix + ".gamma1") * window_attention(
+        ct = ct + _dp(_gamma(sd, prefix + ".gamma1") * window_attention(
             sd, prefix + ".hat_attn", _ln(ct, sd, prefix + ".hat_norm1", 1e-5), num_heads,
-            int(n_ct ** 0.5), quant)
-        ct = ct + _gamma(sd, prefix + ".gamma2") * mlp(
-            sd, prefix + ".hat_mlp", _ln(ct, sd, prefix + ".hat_norm2", 1e-5), quant)
+            int(n_ct ** 0.5), quant), masks, prefix + ".hat_attn")
+        ct = ct + _dp(_gamma(sd, prefix + ".gamma2") * mlp(
+            sd, prefix + ".hat_mlp", _ln(ct, sd, prefix + ".hat_norm2", 1e-5), quant), masks, prefix + ".hat_mlp")
         ct = ct_window(ct, ct_size * sr[0], ct_size * sr[1], ct_size)
         ct = ct.reshape(x.shape[0], -1, N)
         x = torch.cat((ct, x), dim=1)
-    x = x + _gamma(sd, prefix + ".gamma3") * window_attention(
-        sd, prefix + ".attn", _ln(x, sd, prefix + ".norm1", 1e-5), num_heads, ws, quant)
-    x = x + _gamma(sd, prefix + ".gamma4") * mlp(sd, prefix + ".mlp", _ln(x, sd, prefix + ".norm2", 1e-5), quant)
+    x = x + _dp(_gamma(sd, prefix + ".gamma3") * window_attention(
+        sd, prefix + ".attn", _ln(x, sd, prefix + ".norm1", 1e-5), num_heads, ws, quant), masks, prefix + ".attn")
+    x = x + _dp(_gamma(sd, prefix + ".gamma4") * mlp(sd, prefix + ".mlp", _ln(x, sd, prefix + ".norm2", 1e-5), quant),
+                masks, prefix + ".mlp")
     if do_sr:
         ctr, x = x.split([x.shape[1] - ws * ws, ws * ws], dim=1)
         ct = ctr.reshape(Bg, Ng, Hg)
@@ -207,7 +218,7 @@ def token_initializer(sd, prefix, x, res_hw, ws, ct_size, quant):
 
 def forward(sd: dict, cfg: dict, x: torch.Tensor, *, training: bool = False,
             quant: Optional[str] = None, capture: Optional[dict] = None,
-            bn_stats: Optional[dict] = None) -> torch.Tensor:
+            bn_stats: Optional[dict] = None, drop_masks: Optional[dict] = None) -> torch.Tensor:
     """FasterViT.forward (fv.py:949-965 / fvar.py:979-995) for a reference-schema state_dict.
 
     cfg keys: dim, in_dim, depths, num_heads, window_size, ct_size, mlp_ratio, resolution (int or
@@ -240,7 +251,7 @@ def forward(sd: dict, cfg: dict, x: torch.Tensor, *, training: bool = False,
                 h = _bn(h, sd, bp + ".norm2", 1e-5, training, bn_stats)
                 if bp + ".gamma" in sd:
                     h = h * sd[bp + ".gamma"].view(1, -1, 1, 1)
-                x = x + h
+                x = x + _dp(h, drop_masks, bp)  # DropPath per image (fv.py:511)
         else:
             ws = wss[i]
             B, C, H, W = x.shape
@@ -268,7 +279,7 @@ def forward(sd: dict, cfg: dict, x: torch.Tensor, *, training: bool = False,
                 xw, ct = hat_block(sd, f"{lp}.blocks.{j}", xw, ct, num_heads=heads[i], ws=ws, sr=sr,
                                    ct_size=ct_size, last=(j == depths[i] - 1),
                                    do_propagation=cfg.get("do_propagation", False),
-                                   square=(sr[0] == sr[1]), quant=quant)
+                                   square=(sr[0] == sr[1]), quant=quant, masks=drop_masks)
                 cap(f"{lp}.blocks.{j}", xw)
             x = window_reverse(xw, ws, Hp, Wp, B)
             if Hp != H or Wp != W:
@@ -340,7 +351,7 @@ def synth_input(batch: int, hw, seed: int, dtype=torch.float32) -> torch.Tensor:
 
 
 def loss_and_grads(sd: dict, cfg: dict, x: torch.Tensor, target: torch.Tensor, *, training=True,
-                   quant=None) -> tuple[torch.Tensor, torch.Tensor, dict]:
+                   quant=None, drop_masks=None) -> tuple[torch.Tensor, torch.Tensor, dict]:
     """CrossEntropy(logits, target) and d loss / d parameter for every float tensor with requires-grad
     semantics in the reference (all nn.Parameters; buffers excluded by name)."""
     buf = ("running_mean", "running_var", "num_batches_tracked", "relative_coords_table",
@@ -355,7 +366,7 @@ def loss_and_grads(sd: dict, cfg: dict, x: torch.Tensor, target: torch.Tensor, *
     for k in list(leaf.keys()):
         if ".global_tokenizer.to_global_feature.pos." in k:
             leaf[k] = leaf[k.replace(".to_global_feature.pos.", ".pos_embed.")]
-    logits = forward(leaf, cfg, x, training=training, quant=quant)
+    logits = forward(leaf, cfg, x, training=training, quant=quant, drop_masks=drop_masks)
     loss = F.cross_entropy(logits, target)
     names = [k for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad
              and ".to_global_feature.pos." not in k]

@@ -91,3 +91,40 @@ def test_train_then_eval_uses_running_stats():
         out = model(x)
         ref = O.forward({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, g["cfg"], x.cpu())
     assert ((out.cpu() - ref).abs().max() / ref.abs().max()).item() < 1e-3
+
+
+def test_stochastic_depth_matches_oracle_with_explicit_masks():
+    """DropPath (timm semantics: one Bernoulli draw per window / per image, scaled by 1/keep). The RNG is
+    not reproducible across implementations, so the same explicit masks are forced into the kernels and fed
+    to the fp64 oracle; logits and gradients must agree."""
+    import fastervit_b200 as F
+    from oracle import fastervit_oracle as O
+    from oracle.configs import cfg_of
+    kw = dict(dim=24, in_dim=16, depths=[1, 2, 2, 2], num_heads=[1, 2, 8, 16])
+    cfg = dict(cfg_of("tiny_b"))
+    model = F.create_model("faster_vit_4_224", drop_path_rate=0.3, **kw)
+    O.synth_fill_(model.state_dict(), 4321)
+    sd64 = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    B = 3
+    x = O.synth_input(B, 224, 77, torch.float32)
+    target = torch.tensor([5, 900, 17])
+    plan = model._get_engine()._plan(x.cuda())
+    g = torch.Generator().manual_seed(5)
+    masks = {}
+    for d in plan.drop_specs:
+        m = torch.bernoulli(torch.full((d["groups"],), d["keep"]), generator=g) / d["keep"]
+        masks[d["name"]] = m
+    assert any((m == 0).any() for m in masks.values()) and len(masks) >= 10
+    plan.forced_drop_masks = masks
+    logits = model(x.cuda())
+    loss = torch.nn.functional.cross_entropy(logits, target.cuda())
+    loss.backward()
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd64, cfg, x.double(), target, training=True,
+                                                       drop_masks={k: v.double() for k, v in masks.items()})
+    assert ((logits.double().cpu() - ref_logits).abs().max() / ref_logits.abs().max()).item() < 2e-3
+    gmax = max(v.abs().max().item() for v in ref_grads.values())
+    for k, p in model.named_parameters():
+        want = ref_grads[k]
+        err = (p.grad.double().cpu() - want).norm().item() / max(want.norm().item(), 1e-3 * gmax * want.numel() ** 0.5)
+        assert err < 4e-2, (k, err)
