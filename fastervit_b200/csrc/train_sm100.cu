@@ -211,35 +211,74 @@ __global__ void cast_scale_f16_kernel(const float* __restrict__ x, long long ldx
 }
 
 // ---------------------------------------------------------------------------------- column reductions
-// out[c] += *scalar * colmul[c] * sum_r a[ra(r)][c] * (b ? b[rb(r)][c] : 1)
-// a is fp32 (A16 == 0) or fp16; b is fp16. Rows through optional lists (a_rows for a, b indexed by r).
+// out[c] += *scalar * colmul[c] * sum_r a[ra(r)][c] * (b ? b[r][c] : 1) * (row_scale ? row_scale[r] : 1)
+// a is fp32 (A16 == 0) or fp16; b is fp16. Block = 32 column groups of 8 x 8 row lanes: every thread
+// streams 8 consecutive columns (16-byte fp16 / 2 x 16-byte fp32 loads) over its rows, 2 rows in flight.
 template <int A16>
-__global__ void colsum_kernel(const void* __restrict__ a, long long lda, const int* __restrict__ a_rows,
-                              const __half* __restrict__ b, long long ldb, int nrows, int C,
-                              const float* __restrict__ colmul, const float* __restrict__ scalar,
-                              float* __restrict__ out, const float* __restrict__ row_scale) {
-  __shared__ float red[4][64];
-  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
-  const int rl = threadIdx.x >> 6;
-  float s = 0.f;
-  if (c < C) {
-    for (int r = blockIdx.x * 4 + rl; r < nrows; r += gridDim.x * 4) {
+__global__ void __launch_bounds__(256)
+    colsum_kernel(const void* __restrict__ a, long long lda, const int* __restrict__ a_rows,
+                  const __half* __restrict__ b, long long ldb, int nrows, int C, const float* __restrict__ colmul,
+                  const float* __restrict__ scalar, float* __restrict__ out, const float* __restrict__ row_scale) {
+  __shared__ float red[8][32][9];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (blockIdx.y * 32 + cg) * 8;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  const bool full = c0 + 8 <= C;
+  if (c0 < C) {
+    for (int r = blockIdx.x * 8 + rl; r < nrows; r += gridDim.x * 8) {
       const long long ra = a_rows ? a_rows[r] : r;
-      float v = A16 ? __half2float(reinterpret_cast<const __half*>(a)[ra * lda + c])
-                    : reinterpret_cast<const float*>(a)[ra * lda + c];
-      if (b) v *= __half2float(b[(long long)r * ldb + c]);
-      if (row_scale) v *= row_scale[r];
-      s += v;
+      float v[8];
+      if (full) {
+        if (A16) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a) + ra * lda + c0);
+          const __half2* h = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[2 * u] = __low2float(h[u]), v[2 * u + 1] = __high2float(h[u]);
+        } else {
+          const float4 p0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a) + ra * lda + c0);
+          const float4 p1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a) + ra * lda + c0 + 4);
+          v[0] = p0.x, v[1] = p0.y, v[2] = p0.z, v[3] = p0.w, v[4] = p1.x, v[5] = p1.y, v[6] = p1.z, v[7] = p1.w;
+        }
+        if (b) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(b + (long long)r * ldb + c0);
+          const __half2* h = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[2 * u] *= __low2float(h[u]), v[2 * u + 1] *= __high2float(h[u]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float x = 0.f;
+          if (c0 + u < C) {
+            x = A16 ? __half2float(reinterpret_cast<const __half*>(a)[ra * lda + c0 + u])
+                    : reinterpret_cast<const float*>(a)[ra * lda + c0 + u];
+            if (b) x *= __half2float(b[(long long)r * ldb + c0 + u]);
+          }
+          v[u] = x;
+        }
+      }
+      const float rs = row_scale ? row_scale[r] : 1.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(v[u], rs, acc[u]);
     }
   }
-  red[rl][threadIdx.x & 63] = s;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[rl][cg][u] = acc[u];
   __syncthreads();
-  if (rl == 0 && c < C) {
-    const int k = threadIdx.x & 63;
-    float t = red[0][k] + red[1][k] + red[2][k] + red[3][k];
-    if (colmul) t *= colmul[c];
-    if (scalar) t *= __ldg(scalar);
-    atomicAdd(out + c, t);
+  if (rl == 0 && c0 < C) {
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][cg][u];
+        if (colmul) s *= colmul[c0 + u];
+        atomicAdd(out + c0 + u, s * sc);
+      }
+    }
   }
 }
 
@@ -263,8 +302,9 @@ __global__ void group_sum_kernel(const float* __restrict__ a, long long lda, int
 // `use_g` = 0 starts from zero instead of g[r] (first consumer of a freshly produced tensor); `clear_moved`
 // zeroes g[r] when the source is another row (only meaningful when r indexes rows of g itself).
 // One warp per row; per-CTA partial sums of dgamma/dbeta in shared memory, then one atomicAdd per column.
+// generic (any C, scalar accesses) fallback of the vectorised kernel below
 __global__ void __launch_bounds__(256)
-    ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
+    ln_bwd_generic_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
                   const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
                   const float* __restrict__ gamma, int rows, int C, float* __restrict__ g, long long ldg,
                   const int* __restrict__ in_map, int use_g, int clear_moved, const float* __restrict__ scalar,
@@ -303,6 +343,95 @@ __global__ void __launch_bounds__(256)
       if (use_g) v += gr[c];
       if (clear_moved && src != r) gr[c] = 0.f;
       gs_[c] = v;
+    }
+  }
+  __syncthreads();
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      a += sh[(size_t)w * 2 * C + c];
+      b += sh[(size_t)w * 2 * C + C + c];
+    }
+    atomicAdd(dgamma + c, a * sc);
+    atomicAdd(dbeta + c, b * sc);
+  }
+}
+
+constexpr int LNB_MAXV = 7;  // 8-half vectors per lane: C <= 32 * 8 * 7 = 1792
+__global__ void __launch_bounds__(256)
+    ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
+                  const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, int rows, int C, float* __restrict__ g, long long ldg,
+                  const int* __restrict__ in_map, int use_g, int clear_moved, const float* __restrict__ scalar,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sh[];  // [warps][2][C]: private per-warp partial sums (lane owns its columns)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* sg = sh + (size_t)warp * 2 * C;
+  float* sb = sg + C;
+  for (int c = lane; c < C; c += 32) {
+    sg[c] = 0.f;
+    sb[c] = 0.f;
+  }
+  __syncwarp();
+  const int nv = C >> 3;  // vectors of 8 halves per row (C % 8 == 0)
+  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    const long long rdy = dy_map ? dy_map[r] : r;
+    if (rdy < 0) continue;  // warp-uniform
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + rdy * lddy);
+    const uint4* xr = reinterpret_cast<const uint4*>(xhat + (long long)r * ldxh);
+    float d[LNB_MAXV][8], xh[LNB_MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LNB_MAXV; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nv) {
+        const uint4 a = dyr[i], b = xr[i];
+        const __half2* ha = reinterpret_cast<const __half2*>(&a);
+        const __half2* hb = reinterpret_cast<const __half2*>(&b);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          d[j][2 * u] = __low2float(ha[u]), d[j][2 * u + 1] = __high2float(ha[u]);
+          xh[j][2 * u] = __low2float(hb[u]), xh[j][2 * u + 1] = __high2float(hb[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float gd = d[j][u] * gm[u];
+          s1 += gd;
+          s2 += gd * xh[j][u];
+          sg[8 * i + u] += d[j][u] * xh[j][u];
+          sb[8 * i + u] += d[j][u];
+          d[j][u] = gd;  // keep gamma*dy
+        }
+      }
+    }
+    s1 = warp_sum_t(s1) / C;
+    s2 = warp_sum_t(s2) / C;
+    const float rs = rstd[r];
+    const long long src = in_map ? in_map[r] : r;
+    float* gr = g + (long long)r * ldg;
+    float* gs_ = g + src * ldg;
+#pragma unroll
+    for (int j = 0; j < LNB_MAXV; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nv) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = rs * (d[j][u] - s1 - xh[j][u] * s2);
+        if (use_g) {
+          const float4 a = reinterpret_cast<const float4*>(gr)[2 * i], b = reinterpret_cast<const float4*>(gr)[2 * i + 1];
+          v[0] += a.x, v[1] += a.y, v[2] += a.z, v[3] += a.w, v[4] += b.x, v[5] += b.y, v[6] += b.z, v[7] += b.w;
+        }
+        if (clear_moved && src != r) {
+          reinterpret_cast<float4*>(gr)[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(gr)[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        reinterpret_cast<float4*>(gs_)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(gs_)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
   }
   __syncthreads();
@@ -461,13 +590,23 @@ __global__ void attn_bias_bwd_kernel(const float* __restrict__ dbias, const floa
   }
 }
 
-// Backward of fvit_cpb_mlp_fwd: dout [P, D] (fp32), hidden [P, 512] saved ->
-//   dw1[d][j] += dout[p][d] * hid[p][j] ; dhid[p][j] = (hid > 0) * sum_d dout[p][d] w1[d][j] ;
-//   dw0[j][k] += dhid[p][j] * coords[p][k] ; db0[j] += dhid[p][j]. One CTA per point p.
+// Backward of fvit_cpb_mlp_fwd: dout [P, D] (fp32), hidden [P, 512] saved.
+//   kernel A (grid D): dw1[d][j] += sc * sum_p dout[p][d] * hid[p][j]        (thread per j, no atomics)
+//   kernel B (grid P): dhid[p][j] = (hid > 0) * sc * sum_d dout[p][d] w1[d][j]; dw0 / db0 via 3 atomics per j
+__global__ void cpb_mlp_bwd_w1_kernel(int P, const float* __restrict__ hidden, const float* __restrict__ dout, int D,
+                                      const float* __restrict__ scalar, float* __restrict__ dw1) {
+  const int d = blockIdx.x;
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+    float a = 0.f;
+    for (int p = 0; p < P; ++p) a = fmaf(dout[(long long)p * D + d], hidden[(long long)p * 512 + j], a);
+    dw1[(long long)d * 512 + j] += a * sc;
+  }
+}
 __global__ void cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w1,
                                    const float* __restrict__ hidden, const float* __restrict__ dout, int D,
                                    const float* __restrict__ scalar, float* __restrict__ dw0,
-                                   float* __restrict__ db0, float* __restrict__ dw1) {
+                                   float* __restrict__ db0) {
   extern __shared__ float sd[];  // dout row [D]
   const int p = blockIdx.x;
   const float sc = scalar ? __ldg(scalar) : 1.f;
@@ -476,12 +615,9 @@ __global__ void cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, cons
   const float c0 = coords[2 * p], c1 = coords[2 * p + 1];
   for (int j = threadIdx.x; j < 512; j += blockDim.x) {
     const float hv = hidden[(long long)p * 512 + j];
-    float dh = 0.f;
-    for (int d = 0; d < D; ++d) {
-      dh = fmaf(sd[d], w1[(long long)d * 512 + j], dh);
-      atomicAdd(dw1 + (long long)d * 512 + j, sd[d] * hv);
-    }
     if (hv > 0.f) {
+      float dh = 0.f;
+      for (int d = 0; d < D; ++d) dh = fmaf(sd[d], w1[(long long)d * 512 + j], dh);
       atomicAdd(dw0 + 2 * j, dh * c0);
       atomicAdd(dw0 + 2 * j + 1, dh * c1);
       atomicAdd(db0 + j, dh);
@@ -825,7 +961,9 @@ int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_r
                 int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, const float* row_scale,
                 void* stream) {
   FVIT_CHECK(a && out && nrows > 0 && C > 0, "fvit_colsum: bad arguments");
-  dim3 grid((unsigned)grid_cap(((long long)nrows + 15) / 16, 1, 24), (unsigned)((C + 63) / 64));
+  FVIT_CHECK(lda % (a_is_f16 ? 8 : 4) == 0 && (!b16 || ldb % 8 == 0) && (reinterpret_cast<uintptr_t>(a) & 15) == 0,
+             "fvit_colsum: rows must be 16-byte aligned");
+  dim3 grid((unsigned)grid_cap(((long long)nrows + 63) / 64, 1, 16), (unsigned)((C + 255) / 256));
   if (a_is_f16)
     colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
                                                              colmul, scalar, out, row_scale);
@@ -850,6 +988,7 @@ int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const voi
                 float* dbeta, void* stream) {
   FVIT_CHECK(dy16 && xhat16 && rstd && gamma && g && dgamma && dbeta && rows > 0 && C > 0,
              "fvit_ln_bwd: bad arguments");
+  const bool vec = C % 8 == 0 && C <= 32 * 8 * LNB_MAXV && lddy % 8 == 0 && ldxh % 8 == 0 && ldg % 4 == 0;
   const int block = 256, wpb = 8;
   long long grid = ((long long)rows + wpb - 1) / wpb;
   const long long cap = (long long)num_sms() * 8;
@@ -858,11 +997,17 @@ int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const voi
   static bool configured = false;
   if (smem > 48 * 1024 && !configured) {
     FVIT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FVIT_CUDA(cudaFuncSetAttribute(ln_bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  ln_bwd_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
-      (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
-      clear_moved, scalar, dgamma, dbeta);
+  if (vec)
+    ln_bwd_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
+        (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
+        clear_moved, scalar, dgamma, dbeta);
+  else
+    ln_bwd_generic_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
+        (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
+        clear_moved, scalar, dgamma, dbeta);
   return post_launch("ln_bwd_kernel");
 }
 
@@ -907,8 +1052,11 @@ int fvit_attn_bias_bwd(const float* dbias, const float* bias, const int64_t* ind
 int fvit_cpb_mlp_bwd(const float* coords, int32_t P, const float* w1, const float* hidden, const float* dout,
                      int32_t D, const float* scalar, float* dw0, float* db0, float* dw1, void* stream) {
   FVIT_CHECK(coords && w1 && hidden && dout && dw0 && db0 && dw1 && P > 0 && D > 0, "fvit_cpb_mlp_bwd: bad arguments");
+  cpb_mlp_bwd_w1_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(P, hidden, dout, D, scalar, dw1);
+  int rc = post_launch("cpb_mlp_bwd_w1_kernel");
+  if (rc) return rc;
   cpb_mlp_bwd_kernel<<<P, 256, D * sizeof(float), (cudaStream_t)stream>>>(coords, P, w1, hidden, dout, D, scalar, dw0,
-                                                                         db0, dw1);
+                                                                         db0);
   return post_launch("cpb_mlp_bwd_kernel");
 }
 

@@ -360,6 +360,15 @@ def _emit_head_bwd(self, feat: dict) -> None:
              self.G(m.norm.bias))
 
 
+def _attn_bwd_entry(S: int, hdp: int, use_tc: bool) -> str:
+    """tensor-core attention backward when the tile fits (S <= 64, head slices of 32/64, shared memory budget)"""
+    if use_tc and S <= 64 and hdp in (32, 64):
+        ss = (S * S * 4 + 15) // 16 * 16
+        if 1024 + 2 * 4 * 128 * hdp * 2 + 2 * 128 * 128 * 2 + 2 * ss + 128 <= 227 * 1024:
+            return "fvit_attn_tc_bwd"
+    return "fvit_attn_core_bwd"
+
+
 def _posemb_bwd(self, pe: dict) -> None:
     mod = pe["mod"]
     self._op(self.bwd_ops, "fvit_cpb_mlp_bwd", pe["coords"].data_ptr(), pe["npts"], mod.cpb_mlp[2].weight.data_ptr(),
@@ -423,8 +432,8 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
     # attention core
-    self._op(ops, "fvit_attn_core_bwd", at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, groups, S, h, hd, hdp,
-             at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
+    self._op(ops, _attn_bwd_entry(S, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, groups, S, h, hd,
+             hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
     self.bwd_flops[len(ops) - 1] = 10.0 * groups * h * S * S * hd
     _bias_bwd(self, at["bias"])
     # qkv
@@ -508,8 +517,8 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
                      dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc)
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
-    self._op(ops, "fvit_attn_core_bwd", at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, B, n_ct, h, hd, hdp,
-             at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
+    self._op(ops, _attn_bwd_entry(n_ct, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, B, n_ct, h, hd,
+             hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
     _bias_bwd(self, at["bias"])
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
     if padded:

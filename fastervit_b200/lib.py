@@ -103,6 +103,7 @@ _OP_SIGS: dict[str, list] = {
     "fvit_colsum": [_P, _I, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P],
     "fvit_group_sum": [_P, _L, _I, _I, _I, _I, _P, _P, _P],
     "fvit_ln_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _P, _L, _P, _I, _I, _P, _P, _P, _P],
+    "fvit_attn_tc_bwd": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
     "fvit_attn_core_bwd": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
     "fvit_unpad_heads_f32": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P, _P],
     "fvit_attn_bias_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P],

@@ -268,6 +268,11 @@ int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const voi
 int fvit_attn_core_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, int32_t groups, int32_t S,
                        int32_t heads, int32_t head_dim, int32_t hdp, const float* bias, float scale, void* dqkv,
                        int64_t lddq, float* dbias, void* stream);
+/* Tensor-core version for S <= 64 and hdp in {32, 64} (tcgen05: S = QK^T, dP = dO V^T, then dV = P^T dO,
+ * dK = dS^T Q, dQ = dS K with the P / dS tiles read as MN-major / K-major operands); same contract. */
+int fvit_attn_tc_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, int32_t groups, int32_t S,
+                     int32_t heads, int32_t head_dim, int32_t hdp, const float* bias, float scale, void* dqkv,
+                     int64_t lddq, float* dbias, void* stream);
 /* dst (+)= *scalar * src with head padding removed from rows and/or columns (inverse of
  * fvit_cast_headpad_f16 for gradients). */
 int fvit_unpad_heads_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t rows_src, int32_t cols_src,

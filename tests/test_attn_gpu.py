@@ -56,3 +56,43 @@ def test_attn_simt_matches_torch(S, heads, hd, groups):
     ref = _ref(qkv, groups, S, heads, hd, hd, bias, scale)
     err = ((out.float() - ref).abs().max() / ref.abs().max()).item()
     assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("S,heads,hd,groups", [(53, 8, 32, 37), (49, 16, 32, 20), (16, 8, 32, 11), (53, 16, 49, 9),
+                                               (60, 8, 32, 5), (36, 4, 24, 13), (53, 8, 32, 1024)])
+@pytest.mark.parametrize("tc", [True, False])
+def test_attn_backward_matches_autograd(S, heads, hd, groups, tc):
+    """dq, dk, dv and dbias of both backward kernels (tcgen05 / SIMT) vs torch autograd in fp32."""
+    from fastervit_b200 import lib
+    lib.load()
+    hdp = 32 if hd <= 32 else 64
+    g = torch.Generator(device="cuda").manual_seed(S * 17 + heads + hd)
+    qkv = torch.zeros(groups * S, 3, heads, hdp, device="cuda")
+    qkv[..., :hd] = torch.randn(groups * S, 3, heads, hd, device="cuda", generator=g)
+    qkv16 = qkv.reshape(groups * S, 3 * heads * hdp).half()
+    bias = (torch.randn(heads, S, S, device="cuda", generator=g) * 2 + 4).requires_grad_(True)
+    do = torch.zeros(groups * S, heads, hdp, device="cuda")
+    do[..., :hd] = torch.randn(groups * S, heads, hd, device="cuda", generator=g)
+    do16 = do.reshape(groups * S, heads * hdp).half()
+    scale = hd ** -0.5
+    # autograd reference on the fp16-rounded operands
+    x = qkv16.float().view(groups, S, 3, heads, hdp)[..., :hd].clone().requires_grad_(True)
+    q, k, v = x.permute(2, 0, 3, 1, 4)
+    p = ((q @ k.transpose(-2, -1)) * scale + bias[None]).softmax(-1)
+    o = (p @ v).permute(0, 2, 1, 3)
+    o.backward(do16.float().view(groups, S, heads, hdp)[..., :hd])
+    ref = torch.zeros(groups, S, 3, heads, hdp, device="cuda")
+    ref[..., :hd] = x.grad
+    ref = ref.reshape(groups * S, 3 * heads * hdp)
+    dqkv = torch.full((groups * S, 3 * heads * hdp), float("nan"), device="cuda", dtype=torch.half)
+    dbias = torch.zeros(heads, S, S, device="cuda")
+    name = "fvit_attn_tc_bwd" if tc else "fvit_attn_core_bwd"
+    lib.call(name, qkv16.data_ptr(), qkv16.stride(0), do16.data_ptr(), do16.stride(0), groups, S, heads, hd, hdp,
+             bias.data_ptr(), scale, dqkv.data_ptr(), dqkv.stride(0), dbias.data_ptr())
+    assert torch.isfinite(dqkv.float()).all()
+    for w, nm in enumerate("qkv"):
+        sl = slice(w * heads * hdp, (w + 1) * heads * hdp)
+        err = ((dqkv[:, sl].float() - ref[:, sl]).abs().max() / ref[:, sl].abs().max()).item()
+        assert err < 4e-3, (nm, err)
+    err = ((dbias - bias.grad).abs().max() / bias.grad.abs().max()).item()
+    assert err < 4e-3, ("dbias", err)
