@@ -38,6 +38,8 @@ constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem base, placed after the
 constexpr int SMEM_ALIGN_SLACK = 1024;
 constexpr int STG_LD = 36;  // floats per staging row: 32 + 4 pad -> conflict-free float4 access both ways
 constexpr int SMEM_STG_BYTES = 8 * 32 * STG_LD * 4;  // one 32x32 fp32 staging tile per epilogue warp
+constexpr int STATS_MAX_N = 1024;                    // widest GEMM with per-column statistics (BatchNorm channels)
+constexpr int SMEM_STATS_BYTES = 2 * STATS_MAX_N * 4;
 
 struct GemmParams {
   int m, n;
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int chunk_par = ew >> 2;
     float* stg = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES) + ew * (32 * STG_LD);
+    // per-CTA partial BatchNorm statistics (sum | sum of squares), flushed with one atomic per column at the end
+    float* stat_s = reinterpret_cast<float*>(ctrl + SMEM_CTRL_BYTES + SMEM_STG_BYTES);
     const int sub = lane >> 3;   // row within a 4-row group
     const int c4 = lane & 7;     // which float4 of the 32-column chunk
     constexpr bool GENERIC = (FEAT & EF_GENERIC) != 0;
@@ -319,6 +323,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool has_pre = GENERIC ? (p.out_pre16 != nullptr) : ((FEAT & EF_PRE) != 0);
     const bool has_aptr = GENERIC ? (p.alpha_ptr != nullptr) : ((FEAT & EF_ALPHAPTR) != 0);
     const float alpha = has_aptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    if (stats) {
+      for (int i = threadIdx.x - 64; i < 2 * p.n; i += GEMM_THREADS - 64) stat_s[i] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -514,10 +522,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o), s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
           }
           if (sub == 0 && cany) {
-            atomicAdd(p.col_sum + col, s1.x), atomicAdd(p.col_sumsq + col, s2.x);
-            if (col + 1 < n_end) atomicAdd(p.col_sum + col + 1, s1.y), atomicAdd(p.col_sumsq + col + 1, s2.y);
-            if (col + 2 < n_end) atomicAdd(p.col_sum + col + 2, s1.z), atomicAdd(p.col_sumsq + col + 2, s2.z);
-            if (col + 3 < n_end) atomicAdd(p.col_sum + col + 3, s1.w), atomicAdd(p.col_sumsq + col + 3, s2.w);
+            atomicAdd(stat_s + col, s1.x), atomicAdd(stat_s + p.n + col, s2.x);
+            if (col + 1 < n_end) atomicAdd(stat_s + col + 1, s1.y), atomicAdd(stat_s + p.n + col + 1, s2.y);
+            if (col + 2 < n_end) atomicAdd(stat_s + col + 2, s1.z), atomicAdd(stat_s + p.n + col + 2, s2.z);
+            if (col + 3 < n_end) atomicAdd(stat_s + col + 3, s1.w), atomicAdd(stat_s + p.n + col + 3, s2.w);
           }
         }
       }
@@ -532,6 +540,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
+      }
+    }
+    if (stats) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < p.n; i += GEMM_THREADS - 64) {
+        const float a = stat_s[i], b = stat_s[p.n + i];
+        if (a != 0.f || b != 0.f) {
+          atomicAdd(p.col_sum + i, a);
+          atomicAdd(p.col_sumsq + i, b);
+        }
       }
     }
   }
@@ -626,6 +644,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
     FVIT_CHECK(a->aux != nullptr, "fvit_gemm: backward activation needs aux");
   FVIT_CHECK((a->col_sum == nullptr) == (a->col_sumsq == nullptr),
              "fvit_gemm: col_sum and col_sumsq go together");
+  FVIT_CHECK(!a->col_sum || a->n <= STATS_MAX_N, "fvit_gemm: statistics support n <= %d", STATS_MAX_N);
 
   const int sms = num_sms();
   int tile_n = a->tile_n;
@@ -651,7 +670,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (p.split_k < 1) p.split_k = 1;
   p.atomic_out = split_k > 1 ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + tile_n * BK * 2;
-  int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK - SMEM_STG_BYTES) / stage_bytes;
+  const int stats_bytes = a->col_sum ? SMEM_STATS_BYTES : 0;
+  int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK - SMEM_STG_BYTES - stats_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   FVIT_CHECK(stages >= 2, "fvit_gemm: not enough shared memory for 2 stages");
   p.stages = stages;
@@ -718,7 +738,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   }
   if (rc) return rc;
 
-  const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES;
+  const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES + stats_bytes;
   const long long work = (long long)p.tiles_m * p.tiles_n * p.split_k;
   const int grid = (int)(work < sms ? work : sms);
   // feature mask of this call; launch the matching specialisation if one was instantiated

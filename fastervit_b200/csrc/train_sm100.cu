@@ -359,31 +359,26 @@ __global__ void __launch_bounds__(256)
 }
 
 constexpr int LNB_MAXV = 7;  // 8-half vectors per lane: C <= 32 * 8 * 7 = 1792
+// Vectorised dx part (C % 8 == 0): one warp per row, the row's dy / xhat live in registers between the two
+// passes. MAXV (vectors per lane) is a template parameter so narrow rows do not pay for wide rows' registers.
+template <int MAXV>
 __global__ void __launch_bounds__(256)
-    ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
-                  const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
-                  const float* __restrict__ gamma, int rows, int C, float* __restrict__ g, long long ldg,
-                  const int* __restrict__ in_map, int use_g, int clear_moved, const float* __restrict__ scalar,
-                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sh[];  // [warps][2][C]: private per-warp partial sums (lane owns its columns)
+    ln_bwd_dx_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
+                     const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, int rows, int C, float* __restrict__ g, long long ldg,
+                     const int* __restrict__ in_map, int use_g, int clear_moved) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float* sg = sh + (size_t)warp * 2 * C;
-  float* sb = sg + C;
-  for (int c = lane; c < C; c += 32) {
-    sg[c] = 0.f;
-    sb[c] = 0.f;
-  }
-  __syncwarp();
-  const int nv = C >> 3;  // vectors of 8 halves per row (C % 8 == 0)
+  const int nv = C >> 3;
+  const float invC = 1.f / (float)C;
   for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
     const long long rdy = dy_map ? dy_map[r] : r;
     if (rdy < 0) continue;  // warp-uniform
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + rdy * lddy);
     const uint4* xr = reinterpret_cast<const uint4*>(xhat + (long long)r * ldxh);
-    float d[LNB_MAXV][8], xh[LNB_MAXV][8];
+    float d[MAXV][8], xh[MAXV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < LNB_MAXV; ++j) {
+    for (int j = 0; j < MAXV; ++j) {
       const int i = lane + 32 * j;
       if (i < nv) {
         const uint4 a = dyr[i], b = xr[i];
@@ -394,28 +389,24 @@ __global__ void __launch_bounds__(256)
         const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          d[j][2 * u] = __low2float(ha[u]), d[j][2 * u + 1] = __high2float(ha[u]);
+          d[j][2 * u] = __low2float(ha[u]) * gm[2 * u], d[j][2 * u + 1] = __high2float(ha[u]) * gm[2 * u + 1];
           xh[j][2 * u] = __low2float(hb[u]), xh[j][2 * u + 1] = __high2float(hb[u]);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const float gd = d[j][u] * gm[u];
-          s1 += gd;
-          s2 += gd * xh[j][u];
-          sg[8 * i + u] += d[j][u] * xh[j][u];
-          sb[8 * i + u] += d[j][u];
-          d[j][u] = gd;  // keep gamma*dy
+          s1 += d[j][u];
+          s2 += d[j][u] * xh[j][u];
         }
       }
     }
-    s1 = warp_sum_t(s1) / C;
-    s2 = warp_sum_t(s2) / C;
+    s1 = warp_sum_t(s1) * invC;
+    s2 = warp_sum_t(s2) * invC;
     const float rs = rstd[r];
     const long long src = in_map ? in_map[r] : r;
     float* gr = g + (long long)r * ldg;
     float* gs_ = g + src * ldg;
 #pragma unroll
-    for (int j = 0; j < LNB_MAXV; ++j) {
+    for (int j = 0; j < MAXV; ++j) {
       const int i = lane + 32 * j;
       if (i < nv) {
         float v[8];
@@ -434,16 +425,49 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  __syncthreads();
-  const float sc = scalar ? __ldg(scalar) : 1.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < nw; ++w) {
-      a += sh[(size_t)w * 2 * C + c];
-      b += sh[(size_t)w * 2 * C + C + c];
+}
+// Parameter-gradient part: dgamma[c] += sc * sum_r dy*xhat, dbeta[c] += sc * sum_r dy. A thread owns one
+// 8-column vector and walks rows; block = vpr column vectors x (256/vpr) row lanes, reduced through smem.
+__global__ void __launch_bounds__(256)
+    ln_bwd_param_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
+                        const __half* __restrict__ xhat, long long ldxh, int rows, int C, int vpr,
+                        const float* __restrict__ scalar, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[256 * 17];
+  const int cx = threadIdx.x % vpr, rl = threadIdx.x / vpr, RL = 256 / vpr;
+  const int cv = blockIdx.y * vpr + cx;  // vector index
+  float ag[8], ab[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) ag[u] = 0.f, ab[u] = 0.f;
+  if (cv * 8 < C) {
+#pragma unroll 2
+    for (int r = blockIdx.x * RL + rl; r < rows; r += gridDim.x * RL) {
+      const long long rdy = dy_map ? dy_map[r] : r;
+      if (rdy < 0) continue;
+      const uint4 a = reinterpret_cast<const uint4*>(dy + rdy * lddy)[cv];
+      const uint4 b = reinterpret_cast<const uint4*>(xhat + (long long)r * ldxh)[cv];
+      const __half2* ha = reinterpret_cast<const __half2*>(&a);
+      const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 d = __half22float2(ha[u]), x = __half22float2(hb[u]);
+        ag[2 * u] += d.x * x.x, ag[2 * u + 1] += d.y * x.y;
+        ab[2 * u] += d.x, ab[2 * u + 1] += d.y;
+      }
     }
-    atomicAdd(dgamma + c, a * sc);
-    atomicAdd(dbeta + c, b * sc);
+  }
+  float* mine = red + threadIdx.x * 17;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) mine[u] = ag[u], mine[8 + u] = ab[u];
+  __syncthreads();
+  // vpr*16 output sums per block; spread them over the threads
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int o = threadIdx.x; o < vpr * 16; o += 256) {
+    const int v = o >> 4, u = o & 15;
+    const int c = (blockIdx.y * vpr + v) * 8 + (u & 7);
+    if (c >= C) continue;
+    float s = 0.f;
+    for (int k = 0; k < RL; ++k) s += red[(k * vpr + v) * 17 + u];
+    atomicAdd((u < 8 ? dgamma : dbeta) + c, s * sc);
   }
 }
 
@@ -768,6 +792,123 @@ __global__ void bn_bwd_apply_kernel(const void* __restrict__ gin, long long ldg,
   }
 }
 
+// Vectorised variants (C % 4 == 0, all leading dimensions % 4 == 0): each thread owns 4 adjacent channels, keeps
+// their constants in registers and walks rows with 8/16-byte accesses. Block = vpr column vectors x (256/vpr) rows.
+template <int G16>
+__device__ __forceinline__ float4 bn_load_dy4(const void* gin, long long off) {
+  if (G16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(gin) + off);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gin) + off);
+}
+__device__ __forceinline__ float4 bn_load_h4(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <int G16>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_v4_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
+                        const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows, int nrows, int C,
+                        int vpr, const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ w, const float* __restrict__ b, int act,
+                        const float* __restrict__ colmul, float* __restrict__ s1, float* __restrict__ s2,
+                        const float* __restrict__ row_scale) {
+  __shared__ float4 red[2][256];
+  const int cx = threadIdx.x % vpr, rl = threadIdx.x / vpr, RL = 256 / vpr;
+  const int c = (blockIdx.y * vpr + cx) * 4;
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+  if (c < C) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 wc = *reinterpret_cast<const float4*>(w + c), bc = *reinterpret_cast<const float4*>(b + c);
+    const float4 cm = colmul ? *reinterpret_cast<const float4*>(colmul + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const bool relu = act == FVIT_ACT_RELU;
+#pragma unroll 2
+    for (int r = blockIdx.x * RL + rl; r < nrows; r += gridDim.x * RL) {
+      const long long rg = g_rows ? g_rows[r] : r, rr = r_rows ? r_rows[r] : r;
+      float4 dy = bn_load_dy4<G16>(gin, rg * ldg + c);
+      const float4 x = bn_load_h4(raw + rr * ldr + c);
+      const float rsc = row_scale ? row_scale[rg] : 1.f;
+      const float xh0 = (x.x - mu.x) * rs.x, xh1 = (x.y - mu.y) * rs.y, xh2 = (x.z - mu.z) * rs.z,
+                  xh3 = (x.w - mu.w) * rs.w;
+      dy.x *= cm.x * rsc, dy.y *= cm.y * rsc, dy.z *= cm.z * rsc, dy.w *= cm.w * rsc;
+      if (relu) {
+        if (fmaf(xh0, wc.x, bc.x) <= 0.f) dy.x = 0.f;
+        if (fmaf(xh1, wc.y, bc.y) <= 0.f) dy.y = 0.f;
+        if (fmaf(xh2, wc.z, bc.z) <= 0.f) dy.z = 0.f;
+        if (fmaf(xh3, wc.w, bc.w) <= 0.f) dy.w = 0.f;
+      }
+      a1.x += dy.x, a1.y += dy.y, a1.z += dy.z, a1.w += dy.w;
+      a2.x += dy.x * xh0, a2.y += dy.y * xh1, a2.z += dy.z * xh2, a2.w += dy.w * xh3;
+    }
+  }
+  red[0][threadIdx.x] = a1;
+  red[1][threadIdx.x] = a2;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    for (int k = 1; k < RL; ++k) {
+      const float4 u = red[0][k * vpr + cx], v = red[1][k * vpr + cx];
+      a1.x += u.x, a1.y += u.y, a1.z += u.z, a1.w += u.w;
+      a2.x += v.x, a2.y += v.y, a2.z += v.z, a2.w += v.w;
+    }
+    atomicAdd(s1 + c, a1.x), atomicAdd(s1 + c + 1, a1.y), atomicAdd(s1 + c + 2, a1.z), atomicAdd(s1 + c + 3, a1.w);
+    atomicAdd(s2 + c, a2.x), atomicAdd(s2 + c + 1, a2.y), atomicAdd(s2 + c + 2, a2.z), atomicAdd(s2 + c + 3, a2.w);
+  }
+}
+template <int G16>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v4_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
+                       const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows, int nrows, int C,
+                       int vpr, float inv_count, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ w, const float* __restrict__ b, int act,
+                       const float* __restrict__ colmul, const float* __restrict__ s1, const float* __restrict__ s2,
+                       const float* __restrict__ scalar, __half* __restrict__ out, long long ldo,
+                       const int* __restrict__ o_rows, float* __restrict__ dw, float* __restrict__ db,
+                       const float* __restrict__ row_scale) {
+  const int cx = threadIdx.x % vpr, rl = threadIdx.x / vpr, RL = 256 / vpr;
+  const int c = (blockIdx.y * vpr + cx) * 4;
+  if (c >= C) return;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+  const float4 wc = *reinterpret_cast<const float4*>(w + c), bc = *reinterpret_cast<const float4*>(b + c);
+  const float4 cm = colmul ? *reinterpret_cast<const float4*>(colmul + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 t1 = *reinterpret_cast<const float4*>(s1 + c), t2 = *reinterpret_cast<const float4*>(s2 + c);
+  const float m1x = t1.x * inv_count, m1y = t1.y * inv_count, m1z = t1.z * inv_count, m1w = t1.w * inv_count;
+  const float m2x = t2.x * inv_count, m2y = t2.y * inv_count, m2z = t2.z * inv_count, m2w = t2.w * inv_count;
+  const float kx = wc.x * rs.x, ky = wc.y * rs.y, kz = wc.z * rs.z, kw = wc.w * rs.w;
+  const bool relu = act == FVIT_ACT_RELU;
+#pragma unroll 2
+  for (int r = blockIdx.x * RL + rl; r < nrows; r += gridDim.x * RL) {
+    const long long rg = g_rows ? g_rows[r] : r, rr = r_rows ? r_rows[r] : r, ro = o_rows ? o_rows[r] : r;
+    float4 dy = bn_load_dy4<G16>(gin, rg * ldg + c);
+    const float4 x = bn_load_h4(raw + rr * ldr + c);
+    const float rsc = row_scale ? row_scale[rg] : 1.f;
+    const float xh0 = (x.x - mu.x) * rs.x, xh1 = (x.y - mu.y) * rs.y, xh2 = (x.z - mu.z) * rs.z,
+                xh3 = (x.w - mu.w) * rs.w;
+    dy.x *= cm.x * rsc, dy.y *= cm.y * rsc, dy.z *= cm.z * rsc, dy.w *= cm.w * rsc;
+    if (relu) {
+      if (fmaf(xh0, wc.x, bc.x) <= 0.f) dy.x = 0.f;
+      if (fmaf(xh1, wc.y, bc.y) <= 0.f) dy.y = 0.f;
+      if (fmaf(xh2, wc.z, bc.z) <= 0.f) dy.z = 0.f;
+      if (fmaf(xh3, wc.w, bc.w) <= 0.f) dy.w = 0.f;
+    }
+    const __half2 o0 = __floats2half2_rn(kx * (dy.x - m1x - xh0 * m2x), ky * (dy.y - m1y - xh1 * m2y));
+    const __half2 o1 = __floats2half2_rn(kz * (dy.z - m1z - xh2 * m2z), kw * (dy.w - m1w - xh3 * m2w));
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&o0);
+    u.y = *reinterpret_cast<const uint32_t*>(&o1);
+    *reinterpret_cast<uint2*>(out + ro * ldo + c) = u;
+  }
+  if (blockIdx.x == 0 && rl == 0) {
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+    dw[c] += t2.x * sc, dw[c + 1] += t2.y * sc, dw[c + 2] += t2.z * sc, dw[c + 3] += t2.w * sc;
+    db[c] += t1.x * sc, db[c + 1] += t1.y * sc, db[c + 2] += t1.z * sc, db[c + 3] += t1.w * sc;
+  }
+}
+
 // conv weight gradient repack: dst[co][ci][tap] += src[tap][co][ci] (src ld = ld_ci)
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ src, int ld_ci, float* __restrict__ dst, int cout,
                                         int cin) {
@@ -963,7 +1104,12 @@ int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_r
   FVIT_CHECK(a && out && nrows > 0 && C > 0, "fvit_colsum: bad arguments");
   FVIT_CHECK(lda % (a_is_f16 ? 8 : 4) == 0 && (!b16 || ldb % 8 == 0) && (reinterpret_cast<uintptr_t>(a) & 15) == 0,
              "fvit_colsum: rows must be 16-byte aligned");
-  dim3 grid((unsigned)grid_cap(((long long)nrows + 63) / 64, 1, 16), (unsigned)((C + 255) / 256));
+  const unsigned gy = (unsigned)((C + 255) / 256);
+  long long gx = ((long long)num_sms() * 8 + gy - 1) / gy;
+  const long long gx_max = ((long long)nrows + 31) / 32;
+  if (gx > gx_max) gx = gx_max;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, gy);
   if (a_is_f16)
     colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
                                                              colmul, scalar, out, row_scale);
@@ -991,23 +1137,48 @@ int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const voi
   const bool vec = C % 8 == 0 && C <= 32 * 8 * LNB_MAXV && lddy % 8 == 0 && ldxh % 8 == 0 && ldg % 4 == 0;
   const int block = 256, wpb = 8;
   long long grid = ((long long)rows + wpb - 1) / wpb;
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (vec) {
+    const long long cap = (long long)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    const __half* dyh = (const __half*)dy16;
+    const __half* xhh = (const __half*)xhat16;
+    const int nvl = (C / 8 + 31) / 32;
+    if (nvl <= 1)
+      ln_bwd_dx_kernel<1><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, ldg,
+                                                            in_map, use_g, clear_moved);
+    else if (nvl <= 2)
+      ln_bwd_dx_kernel<2><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, ldg,
+                                                            in_map, use_g, clear_moved);
+    else if (nvl <= 4)
+      ln_bwd_dx_kernel<4><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, ldg,
+                                                            in_map, use_g, clear_moved);
+    else
+      ln_bwd_dx_kernel<LNB_MAXV><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g,
+                                                                   ldg, in_map, use_g, clear_moved);
+    int vpr = 1;
+    while (vpr < 32 && vpr < C / 8) vpr *= 2;
+    const unsigned gy = (unsigned)((C / 8 + vpr - 1) / vpr);
+    const int RL = 256 / vpr;
+    long long gx = ((long long)num_sms() * 8 + gy - 1) / gy;
+    const long long gx_max = ((long long)rows + RL * 4 - 1) / (RL * 4);
+    if (gx > gx_max) gx = gx_max;
+    if (gx < 1) gx = 1;
+    ln_bwd_param_kernel<<<dim3((unsigned)gx, gy), 256, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rows, C, vpr, scalar, dgamma,
+                                                                dbeta);
+    return post_launch("ln_bwd kernels");
+  }
   const long long cap = (long long)num_sms() * 8;
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)wpb * 2 * C * sizeof(float);
   static bool configured = false;
   if (smem > 48 * 1024 && !configured) {
-    FVIT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     FVIT_CUDA(cudaFuncSetAttribute(ln_bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  if (vec)
-    ln_bwd_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
-        (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
-        clear_moved, scalar, dgamma, dbeta);
-  else
-    ln_bwd_generic_kernel<<<(unsigned)grid, block, smem, (cudaStream_t)stream>>>(
-        (const __half*)dy16, lddy, dy_map, (const __half*)xhat16, ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
-        clear_moved, scalar, dgamma, dbeta);
+  ln_bwd_generic_kernel<<<(unsigned)grid, block, smem, st>>>((const __half*)dy16, lddy, dy_map, (const __half*)xhat16,
+                                                             ldxh, rstd, gamma, rows, C, g, ldg, in_map, use_g,
+                                                             clear_moved, scalar, dgamma, dbeta);
   return post_launch("ln_bwd_kernel");
 }
 
@@ -1097,6 +1268,37 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
   FVIT_CHECK(act == FVIT_ACT_NONE || act == FVIT_ACT_RELU, "fvit_bn_bwd: act must be NONE or RELU");
   FVIT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), (cudaStream_t)stream));
   FVIT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), (cudaStream_t)stream));
+  const cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = C % 4 == 0 && ldg % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(gin) % 16 == 0) && (reinterpret_cast<uintptr_t>(raw16) % 8 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out16) % 8 == 0);
+  if (vec) {
+    int vpr = 1;
+    while (vpr < 64 && vpr < C / 4) vpr *= 2;
+    const unsigned gy = (unsigned)((C / 4 + vpr - 1) / vpr);
+    const int RL = 256 / vpr;
+    long long gx = ((long long)num_sms() * 8 + gy - 1) / gy;
+    const long long gx_max = ((long long)nrows + RL * 4 - 1) / (RL * 4);
+    if (gx > gx_max) gx = gx_max;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, gy);
+    const float inv = 1.f / (float)nrows;
+    if (g_is_f16) {
+      bn_bwd_reduce_v4_kernel<1><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                       mean, rstd, w, b, act, colmul, s1, s2, row_scale);
+      bn_bwd_apply_v4_kernel<1><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                      inv, mean, rstd, w, b, act, colmul, s1, s2, scalar,
+                                                      (__half*)out16, ldo, o_rows, dw, db, row_scale);
+    } else {
+      bn_bwd_reduce_v4_kernel<0><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                       mean, rstd, w, b, act, colmul, s1, s2, row_scale);
+      bn_bwd_apply_v4_kernel<0><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                      inv, mean, rstd, w, b, act, colmul, s1, s2, scalar,
+                                                      (__half*)out16, ldo, o_rows, dw, db, row_scale);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return post_launch("bn_bwd v4 kernels");
+  }
   dim3 grid((unsigned)grid_cap(((long long)nrows + 15) / 16, 1, 24), (unsigned)((C + 63) / 64));
   const long long total = (long long)nrows * C;
   const int g2 = grid_cap(total, 256, 16);

@@ -562,6 +562,17 @@ class Plan:
                 raise L.FvitError(f"{name}: {lib.fvit_last_error().decode()}")
 
 
+    @staticmethod
+    def _op_desc(op) -> dict:
+        """Shape / epilogue summary of a fvit_gemm launch for the per-launch profile."""
+        if op[2] != "fvit_gemm":
+            return {}
+        g = op[1][0]._obj
+        ep = "".join(c for c, on in (("A", g.a_mn_major), ("B", g.b_mn_major), ("r", bool(g.resid)),
+                                     ("m", bool(g.row_map)), ("3", bool(g.out_f32)), ("h", bool(g.out_f16)),
+                                     ("s", bool(g.col_sum)), ("p", bool(g.out_pre16)), ("x", bool(g.aux))) if on)
+        return dict(shape=f"m{g.m} n{g.n} k{g.kc}x{g.ntaps} sk{g.split_k} act{g.act} {ep}")
+
     def profile(self, x: torch.Tensor) -> list[dict]:
         """Time every launch of one forward with CUDA events on the current stream (the GPU is kept busy
         by a spin kernel while the launches are enqueued, so the intervals are back-to-back device
@@ -574,8 +585,8 @@ class Plan:
             self.run_ops([op], x)
             evs[i + 1].record()
         torch.cuda.synchronize()
-        return [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=self.op_flops.get(i, 0.0))
-                for i, op in enumerate(self.ops)]
+        return [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=self.op_flops.get(i, 0.0),
+                     **self._op_desc(op)) for i, op in enumerate(self.ops)]
 
 
 class Engine:

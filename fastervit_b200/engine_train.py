@@ -217,7 +217,8 @@ class TrainPlan(Plan):
                 evs[i + 1].record()
             torch.cuda.synchronize()
             out += [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=flops.get(i, 0.0),
-                         phase="bwd" if ops is self.bwd_ops else "fwd") for i, op in enumerate(ops)]
+                         phase="bwd" if ops is self.bwd_ops else "fwd", **self._op_desc(op))
+                    for i, op in enumerate(ops)]
         return out
 
 
