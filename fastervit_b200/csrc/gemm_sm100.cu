@@ -49,6 +49,7 @@ struct GemmParams {
   int a_row_off, b_row_off;
   int tile_n;
   int tiles_m, tiles_n, split_k;
+  int b_ntaps, tiles_per_tap;  // >1: N tiles enumerate (tap, n tile); tap t reads B rows shifted by tap_shift[t]
   int atomic_out;  // split-K style accumulation: atomicAdd(alpha * acc) into out_f32
   int stages;
   int acc_stride, nacc;  // TMEM columns per accumulator stage and number of stages
@@ -80,14 +81,8 @@ struct GemmParams {
   long long ld_pre16;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
+__device__ __forceinline__ float gelu_erf(float x) { return fvit_gelu(x); }
+__device__ __forceinline__ float gelu_erf_grad(float x) { return fvit_gelu_grad(x); }
 
 __device__ __forceinline__ float load16_as_float(const void* base, long long idx, int bf16) {
   if (bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
@@ -162,6 +157,22 @@ enum : uint32_t {
   EF_CS2 = 1u << 11,
   EF_RS = 1u << 12,
 };
+// work unit -> (M tile, N tile, K split). Plain GEMMs keep the K splits of a tile adjacent; the tap-in-N mode
+// walks all tiles of one K range first so concurrently running CTAs share the A / B slices in L2.
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& tm, int& tn, int& split) {
+  int t;
+  if (p.b_ntaps > 1) {
+    const int nt = p.tiles_m * p.tiles_n;
+    split = w / nt;
+    t = w - split * nt;
+  } else {
+    split = w % p.split_k;
+    t = w / p.split_k;
+  }
+  tn = t % p.tiles_n;
+  tm = t / p.tiles_n;
+}
+
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -208,12 +219,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-        const int split = w % p.split_k;
-        const int t = w / p.split_k;
-        const int tn = t % p.tiles_n;
-        const int tm = t / p.tiles_n;
+        int tm, tn, split;
+        decode_work(p, w, tm, tn, split);
         const int m0 = tm * BM;
-        const int n0 = tn * p.tile_n;
+        int n0 = tn * p.tile_n;
+        int b_shift = p.b_row_off;
+        if (p.b_ntaps > 1) {
+          const int tap = tn / p.tiles_per_tap;
+          n0 = (tn - tap * p.tiles_per_tap) * p.tile_n;
+          b_shift += p.tap_shift[tap];
+        }
         const int kb0 = (int)((long long)p.num_kb * split / p.split_k);
         const int kb1 = (int)((long long)p.num_kb * (split + 1) / p.split_k);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -236,8 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
           } else {
             for (int j = 0; j < p.tile_n / 64; ++j)
-              tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64,
-                          kb * BK + p.b_row_off);
+              tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BK + b_shift);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -260,7 +274,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
       const uint32_t b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
       for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-        const int split = w % p.split_k;
+        int tm_, tn_, split;
+        decode_work(p, w, tm_, tn_, split);
         const int kb0 = (int)((long long)p.num_kb * split / p.split_k);
         const int kb1 = (int)((long long)p.num_kb * (split + 1) / p.split_k);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -330,12 +345,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
-      const int t = w / p.split_k;
-      const int tn = t % p.tiles_n;
-      const int tm = t / p.tiles_n;
+      int tm, tn, split_;
+      decode_work(p, w, tm, tn, split_);
       const int row_base = tm * BM + quad * 32;
-      const int n0 = tn * p.tile_n;
-      const int n_end = min(p.n, n0 + p.tile_n);
+      int n0 = tn * p.tile_n;
+      int n_end = min(p.n, n0 + p.tile_n);
+      if (p.b_ntaps > 1) {  // output columns [tap * n, (tap + 1) * n)
+        const int tap = tn / p.tiles_per_tap;
+        n0 = tap * p.n + (tn - tap * p.tiles_per_tap) * p.tile_n;
+        n_end = min((tap + 1) * p.n, n0 + p.tile_n);
+      }
       // output rows of the 8 tile rows this lane touches (4k + sub), fetched once per tile
       long long orow[8];
       {
@@ -351,7 +370,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
       for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 64) {
         const int nbase = n0 + c0;
-        if (nbase >= p.n) break;  // warp-uniform
+        if (nbase >= n_end) break;  // warp-uniform
         const int col = nbase + 4 * c4;            // first of this lane's 4 columns
         const bool cfull = col + 4 <= n_end;        // all 4 columns valid
         const bool cany = col < n_end;
@@ -637,6 +656,10 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   FVIT_CHECK(a->lda % 8 == 0 && a->ldb % 8 == 0, "fvit_gemm: lda/ldb must be multiples of 8");
   FVIT_CHECK(!(a->a_mn_major && a->ntaps != 1), "fvit_gemm: taps need a K-major A operand");
   FVIT_CHECK(a->out_f32 || a->out_f16 || a->out_pre16, "fvit_gemm: no output");
+  const int b_ntaps = a->b_ntaps > 1 ? a->b_ntaps : 1;
+  if (b_ntaps > 1)
+    FVIT_CHECK(b_ntaps <= 16 && a->a_mn_major && a->b_mn_major && a->ntaps == 1 && a->n % 4 == 0 && !a->col_sum,
+               "fvit_gemm: b_ntaps needs MN-major A and B, ntaps == 1, n %% 4 == 0");
   const int split_k = a->split_k > 1 ? a->split_k : 1;
   if (split_k > 1)
     FVIT_CHECK(a->out_f32 && !a->out_f16 && !a->col_sum, "fvit_gemm: split_k needs out_f32 only");
@@ -648,7 +671,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
 
   const int sms = num_sms();
   int tile_n = a->tile_n;
-  if (tile_n <= 0) tile_n = pick_tile_n(a->m, a->n, split_k, a->b_mn_major, sms);
+  if (tile_n <= 0) tile_n = pick_tile_n(a->m, a->n, split_k * b_ntaps, a->b_mn_major, sms);
   FVIT_CHECK(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "fvit_gemm: tile_n=%d invalid",
              tile_n);
   if (a->b_mn_major) FVIT_CHECK(tile_n % 64 == 0, "fvit_gemm: MN-major B needs tile_n %% 64 == 0");
@@ -666,6 +689,9 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.tile_n = tile_n;
   p.tiles_m = ceil_div(a->m, BM);
   p.tiles_n = ceil_div(a->n, tile_n);
+  p.b_ntaps = a->b_ntaps > 1 ? a->b_ntaps : 1;
+  p.tiles_per_tap = p.tiles_n;
+  p.tiles_n *= p.b_ntaps;
   p.split_k = split_k < p.num_kb ? split_k : p.num_kb;
   if (p.split_k < 1) p.split_k = 1;
   p.atomic_out = split_k > 1 ? 1 : 0;
@@ -679,7 +705,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.nacc = TMEM_COLS / p.acc_stride;
   p.idesc = make_idesc_f16(BM, tile_n, p.a_mn, p.b_mn, a->bf16 ? 1u : 0u);
   for (int i = 0; i < 16; ++i) {
-    p.tap_shift[i] = i < a->ntaps ? a->tap_shift[i] : 0;
+    p.tap_shift[i] = i < (b_ntaps > 1 ? b_ntaps : a->ntaps) ? a->tap_shift[i] : 0;
     p.tap_plane[i] = i < a->ntaps ? a->tap_plane[i] : 0;
   }
   p.alpha = a->alpha;

@@ -110,7 +110,7 @@ __global__ void affine_rows_kernel(const __half* __restrict__ x, long long ldx, 
       if (j + u < C) {
         float y = fmaf(v[u], scale[j + u], shift[j + u]);
         if (act == FVIT_ACT_RELU) y = fmaxf(y, 0.f);
-        else if (act == FVIT_ACT_GELU) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+        else if (act == FVIT_ACT_GELU) y = fvit_gelu(y);
         y *= rsc;
         if (resid) y += resid[row * ldr + j + u];
         v[u] = y;
@@ -909,8 +909,8 @@ bn_bwd_apply_v4_kernel(const void* __restrict__ gin, long long ldg, const int* _
   }
 }
 
-// conv weight gradient repack: dst[co][ci][tap] += src[tap][co][ci] (src ld = ld_ci)
-__global__ void unpack_conv_grad_kernel(const float* __restrict__ src, int ld_ci, float* __restrict__ dst, int cout,
+// conv weight gradient repack: dst[co][ci][tap] += src[co][tap * cin + ci] (src row stride ld)
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int cout,
                                         int cin) {
   const long long total = (long long)cout * cin * 9;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -918,7 +918,7 @@ __global__ void unpack_conv_grad_kernel(const float* __restrict__ src, int ld_ci
     const int tap = (int)(i % 9);
     const int ci = (int)((i / 9) % cin);
     const int co = (int)(i / (9LL * cin));
-    dst[i] += src[((long long)tap * cout + co) * ld_ci + ci];
+    dst[i] += src[(long long)co * ld + tap * cin + ci];
   }
 }
 

@@ -108,7 +108,7 @@ class TrainPlan(Plan):
 
     # symbolic-pointer aware GEMM emitter for the backward list
     def _bgemm(self, *, a, a_rows, lda, b, b_rows, ldb, m, n, kc, a_mn=False, b_mn=False, taps=None, a_planes=1,
-               a_plane_stride=0, b_row_off=0, split_k=1, alpha_ptr=None, act=L.ACT_NONE, aux=None, ld_aux=0,
+               a_plane_stride=0, b_row_off=0, b_taps=None, split_k=1, alpha_ptr=None, act=L.ACT_NONE, aux=None, ld_aux=0,
                out_f32=None, ld_o32=0, out_f16=None, ld_o16=0, row_map=None, resid=None, ld_resid=0, target=None,
                flops=None) -> None:
         g = L.GemmArgs()
@@ -120,6 +120,11 @@ class TrainPlan(Plan):
         for i, (s, p) in enumerate(taps):
             g.tap_shift[i], g.tap_plane[i] = s, p
         g.b_row_off = b_row_off
+        if b_taps is not None:   # conv weight gradient: taps folded into N (include/fvit.h: b_ntaps)
+            assert len(taps) == 1 and a_mn and b_mn
+            g.b_ntaps = len(b_taps)
+            for i, sft in enumerate(b_taps):
+                g.tap_shift[i] = sft
         g.split_k, g.alpha, g.act = split_k, 1.0, act
         g.aux, g.ld_aux, g.row_map = aux, ld_aux, row_map
         g.resid, g.ld_resid = resid, ld_resid
@@ -135,8 +140,8 @@ class TrainPlan(Plan):
         if lst is self.bwd_ops:
             self.bwd_flops[len(lst) - 1] = flops if flops is not None else 2.0 * m * n * kc * len(taps)
 
-    def _split_k(self, m: int, n: int, k_rows: int) -> int:
-        tiles = ((m + 127) // 128) * ((n + 255) // 256)
+    def _split_k(self, m: int, n: int, k_rows: int, ntaps: int = 1) -> int:
+        tiles = ((m + 127) // 128) * ((n + 255) // 256) * ntaps
         want = max(1, (2 * 148) // max(tiles, 1))
         return max(1, min(want, (k_rows + 63) // 64, 64))
 

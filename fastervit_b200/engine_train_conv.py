@@ -227,14 +227,15 @@ def _emit_downsample_train(self, i: int, src: dict, dst: dict) -> None:
 
 # ====================================================================================== backward
 def _conv_wgrad(self, *, dz, lddz, x, ldx, x_rows, rows, cout, cin, shifts, conv_weight, name: str) -> None:
-    """dW[co][ci][t] = sum_q dz[q][co] * x[q + shift_t][ci] as nine MN-major split-K GEMMs + repack."""
-    scr = ("scr", self._scratch(name + ".dWtaps", 9 * cout * cin))
-    sk = self._split_k(cout, cin, rows)
-    for t, off in enumerate(shifts):
-        self._bgemm(a=dz, a_rows=rows, lda=lddz, a_mn=True, b=x, b_rows=x_rows, ldb=ldx, b_mn=True, b_row_off=off, m=cout,
-                    n=cin, kc=rows, split_k=sk, alpha_ptr=("scal", 1), out_f32=("scr", scr[1] + t * cout * cin), ld_o32=cin,
-                    flops=2.0 * rows * cout * cin)
-    self._op(self.bwd_ops, "fvit_unpack_conv_grad", scr, cin, self.G(conv_weight), cout, cin)
+    """dW[co][ci][t] = sum_q dz[q][co] * x[q + shift_t][ci]: ONE MN-major split-K GEMM whose N dimension
+    enumerates (tap, ci) -- every dz tile is fetched once for the nine shifted views of x -- plus a repack."""
+    nt = len(shifts)
+    scr = ("scr", self._scratch(name + ".dWtaps", nt * cout * cin))
+    sk = self._split_k(cout, cin, rows, nt)
+    self._bgemm(a=dz, a_rows=rows, lda=lddz, a_mn=True, b=x, b_rows=x_rows, ldb=ldx, b_mn=True, b_taps=list(shifts), m=cout,
+                n=cin, kc=rows, split_k=sk, alpha_ptr=("scal", 1), out_f32=scr, ld_o32=nt * cin,
+                flops=2.0 * rows * cout * cin * nt)
+    self._op(self.bwd_ops, "fvit_unpack_conv_grad", scr, nt * cin, self.G(conv_weight), cout, cin)
 
 
 def _emit_downsample_bwd(self, ds: dict, src: dict, dst: dict) -> None:

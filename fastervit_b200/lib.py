@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("m", C.c_int32), ("n", C.c_int32), ("kc", C.c_int32), ("ntaps", C.c_int32),
         ("tap_shift", C.c_int32 * 16), ("tap_plane", C.c_int32 * 16),
         ("a_row_off", C.c_int32), ("b_row_off", C.c_int32),
-        ("split_k", C.c_int32), ("tile_n", C.c_int32),
+        ("split_k", C.c_int32), ("b_ntaps", C.c_int32), ("tile_n", C.c_int32),
         ("alpha", C.c_float), ("act", C.c_int32),
         ("col_scale", C.c_void_p), ("col_shift", C.c_void_p), ("col_scale2", C.c_void_p),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64),
@@ -146,7 +146,8 @@ def reset_launch_count() -> None:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | None = None,
          kc: int | None = None, a_mn: bool = False, b_mn: bool = False,
          taps: list[tuple[int, int]] | None = None, a_planes: int = 1, a_plane_stride: int = 0,
-         a_row_off: int = 0, b_row_off: int = 0, split_k: int = 1, tile_n: int = 0,
+         a_row_off: int = 0, b_row_off: int = 0, b_taps: list[int] | None = None, split_k: int = 1,
+         tile_n: int = 0,
          alpha: float = 1.0, act: int = ACT_NONE,
          col_scale=None, col_shift=None, col_scale2=None, aux=None, resid=None, row_map=None,
          out_f32=None, out_f16=None, col_sum=None, col_sumsq=None, alpha_ptr=None, row_scale=None,
@@ -187,6 +188,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
         g.tap_shift[i] = sh
         g.tap_plane[i] = pl
     g.a_row_off, g.b_row_off = a_row_off, b_row_off
+    if b_taps is not None:
+        g.b_ntaps = len(b_taps)
+        for i, sh in enumerate(b_taps):
+            g.tap_shift[i] = sh
     g.split_k, g.tile_n = split_k, tile_n
     g.alpha, g.act = alpha, act
     g.col_scale, g.col_shift, g.col_scale2 = ptr(col_scale), ptr(col_shift), ptr(col_scale2)

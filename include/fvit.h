@@ -82,6 +82,9 @@ typedef struct fvit_gemm_args {
   int32_t a_row_off;     /* extra row offset on A K-rows (MN-major) */
   int32_t b_row_off;     /* extra row offset on B K-rows (MN-major) */
   int32_t split_k;       /* >= 1 */
+  int32_t b_ntaps;       /* 0/1 = off. > 1 (conv weight gradient): the logical output has b_ntaps * n columns; column
+                            block t is A^T-style product with B's K rows shifted by tap_shift[t] (A and B MN-major,
+                            ntaps == 1): dW[co][t*n + ci] = sum_q dz[q][co] * x[q + tap_shift[t]][ci] */
   int32_t tile_n;        /* 0 = auto; else multiple of 16 in [16, 256] */
   /* epilogue */
   float alpha;
@@ -301,8 +304,9 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
                 const int32_t* r_rows, int32_t nrows, int32_t C, const float* mean, const float* rstd, const float* w,
                 const float* b, int32_t act, const float* colmul, float* s1, float* s2, const float* scalar, void* out16,
                 int64_t ldo, const int32_t* o_rows, float* dw, float* db, const float* row_scale, void* stream);
-/* dst[co][ci][tap] += src[tap][co][ci]: the 9 per-tap weight-gradient GEMM outputs -> nn.Conv2d layout. */
-int fvit_unpack_conv_grad(const float* src, int32_t ld_ci, float* dst, int32_t cout, int32_t cin, void* stream);
+/* dst[co][ci][tap] += src[co][tap * cin + ci] (row stride ld): the b_ntaps weight-gradient GEMM output ->
+ * nn.Conv2d layout. */
+int fvit_unpack_conv_grad(const float* src, int32_t ld, float* dst, int32_t cout, int32_t cin, void* stream);
 /* TokenInitializer backward (fv.py:733-738): gx[pixel rows] += d/dx, dw [C,9], dbias [C] from the carrier-row
  * gradients g[ct_row_map[...]]; x16 = fp16 copy of the level input tokens (same row layout as xs). */
 int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ldx, const int32_t* pix_map,

@@ -148,6 +148,27 @@ def test_gemm_split_k_and_row_offsets():
         assert _rel(out, A.float().t() @ Bs.float()) < 1e-4
 
 
+@pytest.mark.parametrize("cout,cin,k,sk", [(392, 392, 3000, 4), (196, 196, 9000, 16), (64, 32, 1000, 1), (640, 320, 700, 2)])
+def test_gemm_taps_in_n_weight_gradient(cout, cin, k, sk):
+    """b_ntaps: out[co][t*cin + ci] = sum_q dz[q][co] * x[q + shift_t][ci] (conv weight gradient in one launch)."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dz = torch.randn(k, cout, device="cuda", generator=g).half()
+    x = torch.randn(k, cin, device="cuda", generator=g).half()
+    shifts = [-31, -30, -29, -1, 0, 1, 29, 30, 31]
+    out = torch.zeros(cout, 9 * cin, device="cuda")
+    lib.gemm(dz, x, a_mn=True, b_mn=True, b_taps=shifts, split_k=sk, alpha=0.5, out_f32=out)
+    ref = torch.zeros_like(out)
+    for t, off in enumerate(shifts):
+        xs = torch.zeros_like(x)
+        if off >= 0:
+            xs[: k - off] = x[off:]
+        else:
+            xs[-off:] = x[: k + off]
+        ref[:, t * cin:(t + 1) * cin] = 0.5 * (dz.float().t() @ xs.float())
+    assert _rel(out, ref) < 1e-4
+
+
 @pytest.mark.parametrize("cin,cout,hw", [(64, 64, 14), (196, 208, 9), (128, 256, 28)])
 def test_gemm_conv3x3_taps(cin, cout, hw):
     """3x3/s1/p1 conv as 9 shifted-row taps over a zero-bordered NHWC matrix vs F.conv2d."""
