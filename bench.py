@@ -159,7 +159,8 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="fv0_fwd", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="fv4_train", choices=sorted(WORKLOADS),
+                    help="default: BASELINE.json configs[2]/[4] (the metric is fwd+bwd images/sec); fv0_fwd = configs[1]")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-e2e", action="store_true")
@@ -314,9 +315,6 @@ def main() -> None:
         with torch.no_grad():
             plan.profile(xs[0])
             prof = plan.profile(xs[1])
-        if mode == "train":
-            for r in prof:
-                r["name"] = r["name"] + "@fwd" if r["name"] != "fvit_gemm" else r["name"]
         by = {}
         for r in prof:
             d = by.setdefault(r["name"], dict(ms=0.0, n=0, flops=0.0))

@@ -51,10 +51,20 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // erf-GELU (nn.GELU default, fv.py Mlp / ConvBlock) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7):
 // one ex2 + one rcp + 7 FMAs instead of libdevice erff's branchy polynomial -- the GEMM epilogues that apply it
 // are instruction-issue bound. exp(-x^2/2) is shared between erf(x/sqrt2) and the normal pdf of the derivative.
+__device__ __forceinline__ float fvit_rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU (__frcp_rn is a subroutine call)
+  return r;
+}
+__device__ __forceinline__ float fvit_ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float fvit_erf_core(float x, float& e) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = __expf(-z * z);
+  const float t = fvit_rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  e = fvit_ex2_approx(-1.4426950408889634f * z * z);
   const float poly =
       fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
   return copysignf(fmaf(-poly, e, 1.0f), x);

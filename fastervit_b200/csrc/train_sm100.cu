@@ -617,36 +617,58 @@ __global__ void attn_bias_bwd_kernel(const float* __restrict__ dbias, const floa
 // Backward of fvit_cpb_mlp_fwd: dout [P, D] (fp32), hidden [P, 512] saved.
 //   kernel A (grid D): dw1[d][j] += sc * sum_p dout[p][d] * hid[p][j]        (thread per j, no atomics)
 //   kernel B (grid P): dhid[p][j] = (hid > 0) * sc * sum_d dout[p][d] w1[d][j]; dw0 / db0 via 3 atomics per j
-__global__ void cpb_mlp_bwd_w1_kernel(int P, const float* __restrict__ hidden, const float* __restrict__ dout, int D,
-                                      const float* __restrict__ scalar, float* __restrict__ dw1) {
+__global__ void __launch_bounds__(512)
+cpb_mlp_bwd_w1_kernel(int P, const float* __restrict__ hidden, const float* __restrict__ dout, int D,
+                      const float* __restrict__ scalar, float* __restrict__ dw1) {
+  extern __shared__ float sdo[];  // dout[:, d] (P values)
   const int d = blockIdx.x;
   const float sc = scalar ? __ldg(scalar) : 1.f;
-  for (int j = threadIdx.x; j < 512; j += blockDim.x) {
-    float a = 0.f;
-    for (int p = 0; p < P; ++p) a = fmaf(dout[(long long)p * D + d], hidden[(long long)p * 512 + j], a);
-    dw1[(long long)d * 512 + j] += a * sc;
-  }
-}
-__global__ void cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w1,
-                                   const float* __restrict__ hidden, const float* __restrict__ dout, int D,
-                                   const float* __restrict__ scalar, float* __restrict__ dw0,
-                                   float* __restrict__ db0) {
-  extern __shared__ float sd[];  // dout row [D]
-  const int p = blockIdx.x;
-  const float sc = scalar ? __ldg(scalar) : 1.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) sd[d] = dout[(long long)p * D + d] * sc;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) sdo[p] = dout[(long long)p * D + d] * sc;
   __syncthreads();
-  const float c0 = coords[2 * p], c1 = coords[2 * p + 1];
-  for (int j = threadIdx.x; j < 512; j += blockDim.x) {
-    const float hv = hidden[(long long)p * 512 + j];
-    if (hv > 0.f) {
-      float dh = 0.f;
-      for (int d = 0; d < D; ++d) dh = fmaf(sd[d], w1[(long long)d * 512 + j], dh);
-      atomicAdd(dw0 + 2 * j, dh * c0);
-      atomicAdd(dw0 + 2 * j + 1, dh * c1);
-      atomicAdd(db0 + j, dh);
-    }
+  const int j = threadIdx.x;  // 512 hidden units
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int p = 0;
+  for (; p + 4 <= P; p += 4) {
+    const float h0 = hidden[(long long)p * 512 + j], h1 = hidden[(long long)(p + 1) * 512 + j],
+                h2 = hidden[(long long)(p + 2) * 512 + j], h3 = hidden[(long long)(p + 3) * 512 + j];
+    a0 = fmaf(sdo[p], h0, a0), a1 = fmaf(sdo[p + 1], h1, a1), a2 = fmaf(sdo[p + 2], h2, a2),
+    a3 = fmaf(sdo[p + 3], h3, a3);
   }
+  for (; p < P; ++p) a0 = fmaf(sdo[p], hidden[(long long)p * 512 + j], a0);
+  dw1[(long long)d * 512 + j] += (a0 + a1) + (a2 + a3);
+}
+// dhid[p][j] = relu'(hidden) * sum_d dout[p][d] w1[d][j] -> dw0 / db0. grid (P, 4 j-chunks, D splits): the D
+// range is split because one thread's chain of dependent L2 loads is what bounds this tiny GEMV; partial
+// sums are linear in the ReLU mask, so every split accumulates its share with atomics.
+__global__ void __launch_bounds__(128)
+cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w1,
+                   const float* __restrict__ hidden, const float* __restrict__ dout, int D,
+                   const float* __restrict__ scalar, float* __restrict__ dw0, float* __restrict__ db0) {
+  extern __shared__ float sd[];  // this split's slice of the dout row
+  const int p = blockIdx.x;
+  const int j = blockIdx.y * 128 + threadIdx.x;
+  const int d0 = (int)((long long)D * blockIdx.z / gridDim.z), d1 = (int)((long long)D * (blockIdx.z + 1) / gridDim.z);
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int d = d0 + threadIdx.x; d < d1; d += blockDim.x) sd[d - d0] = dout[(long long)p * D + d] * sc;
+  __syncthreads();
+  const float hv = hidden[(long long)p * 512 + j];
+  if (hv <= 0.f) return;
+  const float* wp = w1 + (long long)d0 * 512 + j;
+  const int n = d1 - d0;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int d = 0;
+  for (; d + 8 <= n; d += 8) {
+    const float v0 = wp[(long long)d * 512], v1 = wp[(long long)(d + 1) * 512], v2 = wp[(long long)(d + 2) * 512],
+                v3 = wp[(long long)(d + 3) * 512], v4 = wp[(long long)(d + 4) * 512], v5 = wp[(long long)(d + 5) * 512],
+                v6 = wp[(long long)(d + 6) * 512], v7 = wp[(long long)(d + 7) * 512];
+    a0 = fmaf(sd[d], v0, a0), a1 = fmaf(sd[d + 1], v1, a1), a2 = fmaf(sd[d + 2], v2, a2), a3 = fmaf(sd[d + 3], v3, a3);
+    a0 = fmaf(sd[d + 4], v4, a0), a1 = fmaf(sd[d + 5], v5, a1), a2 = fmaf(sd[d + 6], v6, a2), a3 = fmaf(sd[d + 7], v7, a3);
+  }
+  for (; d < n; ++d) a0 = fmaf(sd[d], wp[(long long)d * 512], a0);
+  const float dh = (a0 + a1) + (a2 + a3);
+  atomicAdd(dw0 + 2 * j, dh * coords[2 * p]);
+  atomicAdd(dw0 + 2 * j + 1, dh * coords[2 * p + 1]);
+  atomicAdd(db0 + j, dh);
 }
 
 // Backward of the head: y[b,t,c] = xhat*w + beta with batch statistics, pooled[b,c] = mean_t y.
@@ -811,7 +833,7 @@ __device__ __forceinline__ float4 bn_load_h4(const __half* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 template <int G16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_v4_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
                         const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows, int nrows, int C,
                         int vpr, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -827,23 +849,46 @@ bn_bwd_reduce_v4_kernel(const void* __restrict__ gin, long long ldg, const int* 
     const float4 wc = *reinterpret_cast<const float4*>(w + c), bc = *reinterpret_cast<const float4*>(b + c);
     const float4 cm = colmul ? *reinterpret_cast<const float4*>(colmul + c) : make_float4(1.f, 1.f, 1.f, 1.f);
     const bool relu = act == FVIT_ACT_RELU;
-#pragma unroll 2
-    for (int r = blockIdx.x * RL + rl; r < nrows; r += gridDim.x * RL) {
-      const long long rg = g_rows ? g_rows[r] : r, rr = r_rows ? r_rows[r] : r;
-      float4 dy = bn_load_dy4<G16>(gin, rg * ldg + c);
-      const float4 x = bn_load_h4(raw + rr * ldr + c);
-      const float rsc = row_scale ? row_scale[rg] : 1.f;
-      const float xh0 = (x.x - mu.x) * rs.x, xh1 = (x.y - mu.y) * rs.y, xh2 = (x.z - mu.z) * rs.z,
-                  xh3 = (x.w - mu.w) * rs.w;
-      dy.x *= cm.x * rsc, dy.y *= cm.y * rsc, dy.z *= cm.z * rsc, dy.w *= cm.w * rsc;
-      if (relu) {
-        if (fmaf(xh0, wc.x, bc.x) <= 0.f) dy.x = 0.f;
-        if (fmaf(xh1, wc.y, bc.y) <= 0.f) dy.y = 0.f;
-        if (fmaf(xh2, wc.z, bc.z) <= 0.f) dy.z = 0.f;
-        if (fmaf(xh3, wc.w, bc.w) <= 0.f) dy.w = 0.f;
+    const bool same_rows = g_rows == r_rows;
+    const int rstep = gridDim.x * RL;
+    // 4 rows per trip: all index loads, then all data loads, then the math (memory-level parallelism)
+    for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += 4 * rstep) {
+      long long rg[4], rr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * rstep;
+        rg[u] = r < nrows ? (g_rows ? (long long)g_rows[r] : (long long)r) : -1;
+        rr[u] = same_rows ? rg[u] : (r < nrows ? (r_rows ? (long long)r_rows[r] : (long long)r) : -1);
       }
-      a1.x += dy.x, a1.y += dy.y, a1.z += dy.z, a1.w += dy.w;
-      a2.x += dy.x * xh0, a2.y += dy.y * xh1, a2.z += dy.z * xh2, a2.w += dy.w * xh3;
+      float4 dy[4], x[4];
+      float rsc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rg[u] >= 0) {
+          dy[u] = bn_load_dy4<G16>(gin, rg[u] * ldg + c);
+          x[u] = bn_load_h4(raw + rr[u] * ldr + c);
+          rsc[u] = row_scale ? row_scale[rg[u]] : 1.f;
+        } else {
+          dy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rsc[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float xh0 = (x[u].x - mu.x) * rs.x, xh1 = (x[u].y - mu.y) * rs.y, xh2 = (x[u].z - mu.z) * rs.z,
+                    xh3 = (x[u].w - mu.w) * rs.w;
+        float4 d = dy[u];
+        d.x *= cm.x * rsc[u], d.y *= cm.y * rsc[u], d.z *= cm.z * rsc[u], d.w *= cm.w * rsc[u];
+        if (relu) {
+          if (fmaf(xh0, wc.x, bc.x) <= 0.f) d.x = 0.f;
+          if (fmaf(xh1, wc.y, bc.y) <= 0.f) d.y = 0.f;
+          if (fmaf(xh2, wc.z, bc.z) <= 0.f) d.z = 0.f;
+          if (fmaf(xh3, wc.w, bc.w) <= 0.f) d.w = 0.f;
+        }
+        a1.x += d.x, a1.y += d.y, a1.z += d.z, a1.w += d.w;
+        a2.x += d.x * xh0, a2.y += d.y * xh1, a2.z += d.z * xh2, a2.w += d.w * xh3;
+      }
     }
   }
   red[0][threadIdx.x] = a1;
@@ -860,7 +905,7 @@ bn_bwd_reduce_v4_kernel(const void* __restrict__ gin, long long ldg, const int* 
   }
 }
 template <int G16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_v4_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
                        const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows, int nrows, int C,
                        int vpr, float inv_count, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -880,27 +925,52 @@ bn_bwd_apply_v4_kernel(const void* __restrict__ gin, long long ldg, const int* _
   const float m2x = t2.x * inv_count, m2y = t2.y * inv_count, m2z = t2.z * inv_count, m2w = t2.w * inv_count;
   const float kx = wc.x * rs.x, ky = wc.y * rs.y, kz = wc.z * rs.z, kw = wc.w * rs.w;
   const bool relu = act == FVIT_ACT_RELU;
-#pragma unroll 2
-  for (int r = blockIdx.x * RL + rl; r < nrows; r += gridDim.x * RL) {
-    const long long rg = g_rows ? g_rows[r] : r, rr = r_rows ? r_rows[r] : r, ro = o_rows ? o_rows[r] : r;
-    float4 dy = bn_load_dy4<G16>(gin, rg * ldg + c);
-    const float4 x = bn_load_h4(raw + rr * ldr + c);
-    const float rsc = row_scale ? row_scale[rg] : 1.f;
-    const float xh0 = (x.x - mu.x) * rs.x, xh1 = (x.y - mu.y) * rs.y, xh2 = (x.z - mu.z) * rs.z,
-                xh3 = (x.w - mu.w) * rs.w;
-    dy.x *= cm.x * rsc, dy.y *= cm.y * rsc, dy.z *= cm.z * rsc, dy.w *= cm.w * rsc;
-    if (relu) {
-      if (fmaf(xh0, wc.x, bc.x) <= 0.f) dy.x = 0.f;
-      if (fmaf(xh1, wc.y, bc.y) <= 0.f) dy.y = 0.f;
-      if (fmaf(xh2, wc.z, bc.z) <= 0.f) dy.z = 0.f;
-      if (fmaf(xh3, wc.w, bc.w) <= 0.f) dy.w = 0.f;
+  const bool same_rows = g_rows == r_rows, same_out = o_rows == g_rows;
+  const int rstep = gridDim.x * RL;
+  for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += 4 * rstep) {
+    long long rg[4], rr[4], ro[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * rstep;
+      const bool ok = r < nrows;
+      rg[u] = ok ? (g_rows ? (long long)g_rows[r] : (long long)r) : -1;
+      rr[u] = same_rows ? rg[u] : (ok ? (r_rows ? (long long)r_rows[r] : (long long)r) : -1);
+      ro[u] = same_out ? rg[u] : (ok ? (o_rows ? (long long)o_rows[r] : (long long)r) : -1);
     }
-    const __half2 o0 = __floats2half2_rn(kx * (dy.x - m1x - xh0 * m2x), ky * (dy.y - m1y - xh1 * m2y));
-    const __half2 o1 = __floats2half2_rn(kz * (dy.z - m1z - xh2 * m2z), kw * (dy.w - m1w - xh3 * m2w));
-    uint2 u;
-    u.x = *reinterpret_cast<const uint32_t*>(&o0);
-    u.y = *reinterpret_cast<const uint32_t*>(&o1);
-    *reinterpret_cast<uint2*>(out + ro * ldo + c) = u;
+    float4 dy[4], x[4];
+    float rsc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (rg[u] >= 0) {
+        dy[u] = bn_load_dy4<G16>(gin, rg[u] * ldg + c);
+        x[u] = bn_load_h4(raw + rr[u] * ldr + c);
+        rsc[u] = row_scale ? row_scale[rg[u]] : 1.f;
+      } else {
+        dy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rsc[u] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (rg[u] < 0) continue;
+      const float xh0 = (x[u].x - mu.x) * rs.x, xh1 = (x[u].y - mu.y) * rs.y, xh2 = (x[u].z - mu.z) * rs.z,
+                  xh3 = (x[u].w - mu.w) * rs.w;
+      float4 d = dy[u];
+      d.x *= cm.x * rsc[u], d.y *= cm.y * rsc[u], d.z *= cm.z * rsc[u], d.w *= cm.w * rsc[u];
+      if (relu) {
+        if (fmaf(xh0, wc.x, bc.x) <= 0.f) d.x = 0.f;
+        if (fmaf(xh1, wc.y, bc.y) <= 0.f) d.y = 0.f;
+        if (fmaf(xh2, wc.z, bc.z) <= 0.f) d.z = 0.f;
+        if (fmaf(xh3, wc.w, bc.w) <= 0.f) d.w = 0.f;
+      }
+      const __half2 o0 = __floats2half2_rn(kx * (d.x - m1x - xh0 * m2x), ky * (d.y - m1y - xh1 * m2y));
+      const __half2 o1 = __floats2half2_rn(kz * (d.z - m1z - xh2 * m2z), kw * (d.w - m1w - xh3 * m2w));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&o0);
+      o.y = *reinterpret_cast<const uint32_t*>(&o1);
+      *reinterpret_cast<uint2*>(out + ro[u] * ldo + c) = o;
+    }
   }
   if (blockIdx.x == 0 && rl == 0) {
     const float sc = scalar ? __ldg(scalar) : 1.f;
@@ -1223,11 +1293,13 @@ int fvit_attn_bias_bwd(const float* dbias, const float* bias, const int64_t* ind
 int fvit_cpb_mlp_bwd(const float* coords, int32_t P, const float* w1, const float* hidden, const float* dout,
                      int32_t D, const float* scalar, float* dw0, float* db0, float* dw1, void* stream) {
   FVIT_CHECK(coords && w1 && hidden && dout && dw0 && db0 && dw1 && P > 0 && D > 0, "fvit_cpb_mlp_bwd: bad arguments");
-  cpb_mlp_bwd_w1_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(P, hidden, dout, D, scalar, dw1);
+  cpb_mlp_bwd_w1_kernel<<<D, 512, P * sizeof(float), (cudaStream_t)stream>>>(P, hidden, dout, D, scalar, dw1);
   int rc = post_launch("cpb_mlp_bwd_w1_kernel");
   if (rc) return rc;
-  cpb_mlp_bwd_kernel<<<P, 256, D * sizeof(float), (cudaStream_t)stream>>>(coords, P, w1, hidden, dout, D, scalar, dw0,
-                                                                         db0);
+  int splits = D >= 512 ? 8 : (D >= 128 ? 4 : 1);
+  const size_t smem = ((size_t)(D + splits - 1) / splits + 1) * sizeof(float);
+  cpb_mlp_bwd_kernel<<<dim3((unsigned)P, 4, (unsigned)splits), 128, smem, (cudaStream_t)stream>>>(coords, P, w1, hidden,
+                                                                                                   dout, D, scalar, dw0, db0);
   return post_launch("cpb_mlp_bwd_kernel");
 }
 

@@ -154,7 +154,9 @@ def test_gemm_taps_in_n_weight_gradient(cout, cin, k, sk):
     lib = _lib()
     g = torch.Generator(device="cuda").manual_seed(5)
     dz = torch.randn(k, cout, device="cuda", generator=g).half()
-    x = torch.randn(k, cin, device="cuda", generator=g).half()
+    ldx = (cin + 7) // 8 * 8
+    x = torch.randn(k, ldx, device="cuda", generator=g).half()[:, :cin]
+    dz = torch.randn(k, (cout + 7) // 8 * 8, device="cuda", generator=g).half()[:, :cout]
     shifts = [-31, -30, -29, -1, 0, 1, 29, 30, 31]
     out = torch.zeros(cout, 9 * cin, device="cuda")
     lib.gemm(dz, x, a_mn=True, b_mn=True, b_taps=shifts, split_k=sk, alpha=0.5, out_f32=out)
