@@ -325,12 +325,18 @@ def main() -> None:
         gm = by.get("fvit_gemm")
         prof_table = {k: dict(ms=round(v["ms"], 4), launches=v["n"], share=round(v["ms"] / tot, 4),
                               gflop=round(v["flops"] / 1e9, 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
+        traffic = None   # DRAM bytes per GEMM launch from the committed ncu launch list of this workload
+        tf = ROOT / "profiles" / "r01b_traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(args.workload, {}).get("gemm_dram_bytes_per_launch")
         if gm:
             ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
             roofline = {"kernel": "gemm_tcgen05_kernel (fvit_gemm: conv taps + linear layers; fwd, dgrad and wgrad launches)",
                         "bound": "tensor",
                         "achieved": round(ach, 2), "peak": pk["tensor"], "unit": "TFLOP/s",
-                        "frac": round(ach / pk["tensor"], 4), "traffic": None,
+                        "frac": round(ach / pk["tensor"], 4),
+                        "traffic": None if traffic is None else round(traffic),
+                        "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r01b_traffic.json)",
                         "peak_source": f"{pk['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
                         "launches_per_step": gm["n"], "avg_launch_ms": round(gm["ms"] / gm["n"], 5),
                         "alg_gflop_per_launch": round(gm["flops"] / gm["n"] / 1e9, 3),

@@ -36,22 +36,27 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def launches(path: Path, tag: str) -> None:
     lines = [l for l in path.read_text().splitlines(True) if not l.startswith("==")]
-    agg = collections.defaultdict(lambda: [0, 0.0])
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])   # launches, us, dram bytes
     for row in csv.DictReader(io.StringIO("".join(lines))):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
         name = row["Kernel Name"].split("(")[0][-70:]
+        metric = row.get("Metric Name")
         v = float(row["Metric Value"].replace(",", ""))
-        us = v / 1e3 if row["Metric Unit"] in ("ns", "nsecond") else v
-        agg[name][0] += 1
-        agg[name][1] += us
+        unit = row["Metric Unit"]
+        if metric == "gpu__time_duration.sum":
+            us = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
+            agg[name][0] += 1
+            agg[name][1] += us
+        elif metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+            agg[name][2] += v * mult
     tot = sum(v[1] for k, v in agg.items() if "spin_kernel" not in k)
-    out = [f"# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none` ({path.name})",
+    out = [f"# per-kernel device time from `ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --clock-control none` ({path.name})",
            "# cold-cache, serialised launches: compare SHARES with bench.py's live CUDA-event table, not absolutes",
            f"# total (excluding torch's spin kernel): {tot / 1e3:.3f} ms", ""]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         share = v[1] / tot if "spin_kernel" not in k else float("nan")
-        out.append(f"{k:72s} {v[0]:6d} launches {v[1] / 1e3:10.3f} ms  share {share:.4f}")
+        dram = f"  dram {v[2] / v[0] / 1e6:9.2f} MB/launch {v[2] / max(v[1], 1e-9) / 1e3:8.1f} GB/s" if v[2] else ""
+        out.append(f"{k:72s} {v[0]:6d} launches {v[1] / 1e3:10.3f} ms  share {share:.4f}{dram}")
     (OUT / f"{tag}_launches_summary.txt").write_text("\n".join(out) + "\n")
     with gzip.open(OUT / f"{tag}_launches.csv.gz", "wt") as f:
         f.write("".join(lines))
