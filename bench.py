@@ -254,6 +254,17 @@ def main() -> None:
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = t.item()
+    grad_sync = None
+    if mode == "train" and dist is not None:
+        # after the all-reduce every rank must hold the same averaged gradient although the inputs differ
+        loss = torch.nn.functional.cross_entropy(model(xs[0]), targets)
+        loss.backward()
+        digest = torch.stack([torch.cat([p.grad.flatten()[:64] for p in model.parameters()]).double().sum(),
+                              sum(p.grad.double().abs().sum() for p in model.parameters())])
+        both = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(both, digest)
+        grad_sync = bool(all(torch.allclose(b, both[0], rtol=1e-6, atol=0) for b in both))
+        model.zero_grad(set_to_none=True)
     value = batch * world * args.steps / (ms_total / 1e3)
 
     # ------------------------------------------------------------------ end to end (host buffers)
@@ -358,7 +369,7 @@ def main() -> None:
                 "dtype": "fp16 operands, fp32 accumulate / residual / statistics", "data": "synthetic",
                 "config": config, "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "per_kernel": prof_table,
+                "cpu_baseline": cpu, "per_kernel": prof_table, "grad_sync_check": grad_sync,
                 "model_tflops": round(value * alg / 1e12, 2),
                 "model_frac_of_tensor_peak": round(value / world * alg / 1e12 / pk["tensor"], 4)}
         print(json.dumps(line))

@@ -211,6 +211,7 @@ class Plan:
         sN, tN = self._fold("norm", nf, m.norm)
         T = prev["H"] * prev["W"]
         pooled = nb.new("head.pooled", (B, _ru(nf, 8)), torch.float16)
+        self.pooled = pooled
         self._op(self.ops, "fvit_pool_affine_fwd", prev["xs"].data_ptr(), nf, prev["crop_map"].data_ptr(), B, T,
                  nf, sN.data_ptr(), tN.data_ptr(), pooled.data_ptr(), pooled.stride(0))
         if isinstance(m.head, nn.Linear):
@@ -221,7 +222,6 @@ class Plan:
                        out_f32=self.logits.data_ptr(), ld_o32=m.num_classes)
         else:
             self.logits = None
-            self.pooled = pooled
 
     # ---- geometry helpers -----------------------------------------------------------------------
     def _s2_taps(self, Wo: int) -> list[tuple[int, int]]:
@@ -556,6 +556,11 @@ class Plan:
             elif fn == "zero":
                 args.zero_()
                 continue
+            elif fn == "bucket":   # gradient slice [lo, hi) of the flat buffer is final (engine_train.py)
+                red = getattr(self, "_ar_active", None)
+                if red is not None:
+                    red.reduce(*args)
+                continue
             else:
                 rc = fn(*args, st)
             if rc != 0:
@@ -623,7 +628,8 @@ class Engine:
         plan = self._plan(x)
         if plan.training:
             if features_only:
-                raise L.FvitError("forward_features is not wired yet; use forward()")
+                raise L.FvitError("forward_features is an inference helper (call model.eval()); the autograd "
+                                  "training path is forward()")
             from .engine_train import _FasterViTFunction
             with torch.cuda.device(x.device):
                 if torch.is_grad_enabled() and any(p.requires_grad for p in plan.params):
@@ -635,9 +641,29 @@ class Engine:
                 plan.run_ops(plan.prep_ops, None)
                 self._prepped[id(plan)] = wk
             plan.run_ops(plan.ops, x)
-        if features_only:
-            raise L.FvitError("forward_features is not wired yet; use forward()")
+        if features_only or plan.logits is None:
+            # pooled features (fv.py:949-958); held as the fp16 operand of the classifier GEMM
+            return plan.pooled[:, :self.model.num_features].float()
         return plan.logits.clone()
 
     def forward_head(self, feats: torch.Tensor) -> torch.Tensor:
-        raise L.FvitError("forward_head on external features is not wired yet; use forward()")
+        """`self.head(feats)` (fv.py:960) on caller-provided pooled features, eval mode: one fvit_gemm."""
+        m = self.model
+        if not isinstance(m.head, torch.nn.Linear):
+            return feats
+        if m.training and torch.is_grad_enabled():
+            raise L.FvitError("forward_head is an inference helper; the autograd training path is forward()")
+        if not feats.is_cuda or feats.dim() != 2 or feats.shape[1] != m.num_features:
+            raise L.FvitError(f"forward_head expects a CUDA [B, {m.num_features}] tensor, got {tuple(feats.shape)} on "
+                              f"{feats.device}")
+        with torch.cuda.device(feats.device):
+            nf, Bf = m.num_features, feats.shape[0]
+            ld = _ru(nf, 8)
+            f32 = feats.float().contiguous()
+            a16 = torch.zeros(Bf, ld, dtype=torch.float16, device=feats.device)
+            w16 = torch.zeros(m.num_classes, ld, dtype=torch.float16, device=feats.device)
+            L.call("fvit_cast_pad_f16", f32.data_ptr(), nf, a16.data_ptr(), ld, Bf, nf, ld)
+            L.call("fvit_cast_pad_f16", m.head.weight.data_ptr(), nf, w16.data_ptr(), ld, m.num_classes, nf, ld)
+            out = torch.empty(Bf, m.num_classes, dtype=torch.float32, device=feats.device)
+            L.gemm(a16, w16, kc=nf, col_shift=m.head.bias, out_f32=out)
+        return out

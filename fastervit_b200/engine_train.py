@@ -198,10 +198,19 @@ class TrainPlan(Plan):
 
     def run_backward(self, dlogits: torch.Tensor) -> None:
         self._bwd_start(dlogits)
-        self.run_ops(self.bwd_ops, None)
         grp = getattr(self.model, "_grad_allreduce", None)
-        if grp is not None:
-            allreduce_mean_(self.gflat, None if grp is True else grp)
+        if grp is None:
+            self.run_ops(self.bwd_ops, None)
+            return
+        # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients
+        # are enqueued, so NCCL (its own stream) overlaps the rest of the backward pass
+        red = GradBucketReducer(self.gflat, None if grp is True else grp)
+        self._ar_active = red
+        try:
+            self.run_ops(self.bwd_ops, None)
+        finally:
+            self._ar_active = None
+        red.finish(self.grad_buckets)
 
     def profile(self, x: torch.Tensor) -> list[dict]:
         """Per-launch CUDA-event timing of one training step (forward list, then backward list with the
@@ -225,6 +234,38 @@ class TrainPlan(Plan):
                          phase="bwd" if ops is self.bwd_ops else "fwd", **self._op_desc(op))
                     for i, op in enumerate(ops)]
         return out
+
+
+class GradBucketReducer:
+    """Asynchronous mean all-reduce of slices of the flat gradient buffer (train.py:542-551's DDP, restated for
+    a single autograd node): `reduce(lo, hi)` is called from the backward launch list at the points where the
+    slice [lo, hi) is final; `finish` reduces whatever was not covered and waits for all of them."""
+
+    def __init__(self, flat: torch.Tensor, group=None):
+        import torch.distributed as dist
+        if not dist.is_available() or not dist.is_initialized():
+            raise L.FvitError("enable_grad_allreduce() needs an initialised torch.distributed process group")
+        self.dist, self.flat, self.group = dist, flat, group
+        self.world = dist.get_world_size(group)
+        self.avg = dist.get_backend(group) == "nccl"   # gloo has no AVG
+        self.pending: list = []
+        self.done: list[tuple[int, int]] = []
+
+    def reduce(self, lo: int, hi: int) -> None:
+        if self.world == 1 or hi <= lo:
+            return
+        op = self.dist.ReduceOp.AVG if self.avg else self.dist.ReduceOp.SUM
+        self.pending.append(self.dist.all_reduce(self.flat[lo:hi], op=op, group=self.group, async_op=True))
+        self.done.append((lo, hi))
+
+    def finish(self, buckets: list[tuple[int, int]]) -> None:
+        for lo, hi in buckets:
+            if (lo, hi) not in self.done:
+                self.reduce(lo, hi)
+        for w in self.pending:
+            w.wait()
+        if not self.avg and self.world > 1:
+            self.flat.div_(self.world)
 
 
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:

@@ -320,14 +320,31 @@ def _emit_head_train(self, prev: dict) -> None:
 # ====================================================================================== backward
 def _build_backward(self) -> None:
     m = self.model
+    # gradient buckets of the data-parallel all-reduce, in completion order. The flat buffer follows
+    # .parameters() order (patch_embed, levels.0 .. levels.n, norm, head); the backward pass finishes
+    # [levels.n, norm, head] first, then one transformer level at a time, then the conv part.
+    first = {}
+    for name, p in m.named_parameters():
+        if name.startswith("levels."):
+            first.setdefault(int(name.split(".")[1]), self._goff[id(p)])
+    total = self.gflat.numel()
+    self.grad_buckets = []
     self._emit_head_bwd(self.feat)
     toks = [lv for lv in self.lv]
+    n_conv = len(m.levels) - len(toks)
+    hi = total
     for idx in range(len(toks) - 1, -1, -1):
         tl = toks[idx]
         self._emit_token_level_bwd(tl)
+        lo = first.get(n_conv + idx, hi)
+        self.grad_buckets.append((lo, hi))
+        self.bwd_ops.append(("bucket", (lo, hi), "grad_bucket"))
+        hi = lo
         src = toks[idx - 1] if idx > 0 else self.conv_out
         self._emit_downsample_bwd(tl["ds"], src, tl)
     self._emit_conv_part_bwd()
+    self.grad_buckets.append((0, hi))
+    self.bwd_ops.append(("bucket", (0, hi), "grad_bucket"))
 
 
 def _emit_head_bwd(self, feat: dict) -> None:

@@ -294,6 +294,7 @@ def forward(sd: dict, cfg: dict, x: torch.Tensor, *, training: bool = False,
     x = _bn(x, sd, "norm", 1e-5, training, bn_stats)  # fv.py:953 (layer_norm_last=False everywhere)
     cap("norm", x)
     x = x.mean(dim=(2, 3))  # AdaptiveAvgPool2d(1) + flatten (fv.py:957-958)
+    cap("pooled", x)
     return _linear(x, sd["head.weight"], sd["head.bias"], quant)
 
 

@@ -37,6 +37,16 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     allreduce_mean_(flat)
     expect = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     ok = torch.allclose(flat, expect)
+    # the bucketed reducer used by the backward launch list: slices issued out of order + a remainder
+    from fastervit_b200.engine_train import GradBucketReducer
+    flat2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    cuts = [0, n // 5, n // 2, n]
+    buckets = [(cuts[2], cuts[3]), (cuts[1], cuts[2]), (cuts[0], cuts[1])]   # completion order of the backward
+    red = GradBucketReducer(flat2)
+    red.reduce(*buckets[0])
+    red.reduce(*buckets[1])
+    red.finish(buckets)
+    ok = ok and torch.allclose(flat2, expect)
     # parameters of both replicas are bit-identical (what the gradient-only exchange relies on)
     digest = float(sum(p.double().sum() for p in model.parameters()))
     gathered = [None] * world

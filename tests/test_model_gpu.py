@@ -54,3 +54,21 @@ def test_batch_independence():
         full = model(x3)
         singles = torch.cat([model(x3[i:i + 1]) for i in range(3)], 0)
     assert (full - singles).abs().max().item() <= 1e-5 * full.abs().max().item()
+
+
+def test_forward_features_and_head_split():
+    """forward == forward_head(forward_features(x)) (fv.py:949-965) and num_classes=0 returns pooled features."""
+    g, model, x = _setup("tiny_a")
+    with torch.no_grad():
+        full = model(x)
+        feats = model.forward_features(x)
+        assert feats.shape == (x.shape[0], model.num_features) and feats.dtype == torch.float32
+        again = model.forward_head(feats)
+    assert (again - full).abs().max().item() <= 1e-3 * full.abs().max().item()
+    # oracle check of the pooled features themselves
+    from oracle import fastervit_oracle as O
+    sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    cap = {}
+    O.forward(sd, g["cfg"], x.cpu().double(), capture=cap)
+    ref = cap["pooled"]
+    assert ((feats.cpu().double() - ref).abs().max() / ref.abs().max()).item() < 2e-3

@@ -136,3 +136,24 @@ def test_stochastic_depth_matches_oracle_with_explicit_masks():
         want = ref_grads[k]
         err = (p.grad.double().cpu() - want).norm().item() / max(want.norm().item(), 1e-3 * gmax * want.numel() ** 0.5)
         assert err < 4e-2, (k, err)
+
+
+def test_gradient_buckets_partition_the_flat_buffer():
+    """The data-parallel buckets (issued as the backward pass finishes them) tile the flat gradient buffer, fall
+    on parameter boundaries and are listed last-level-first."""
+    g, tr, model, logits, loss = _run("tiny_a")
+    plan = next(p for p in model._get_engine().plans.values() if p.training)
+    total = sum(p.numel() for p in model.parameters())
+    assert sorted(plan.grad_buckets) == sorted(set(plan.grad_buckets))
+    covered = sorted(plan.grad_buckets)
+    assert covered[0][0] == 0 and covered[-1][1] == total
+    for (a0, a1), (b0, b1) in zip(covered, covered[1:]):
+        assert a1 == b0
+    offs = set()
+    o = 0
+    for p in model.parameters():
+        offs.add(o)
+        o += p.numel()
+    offs.add(o)
+    assert all(lo in offs and hi in offs for lo, hi in plan.grad_buckets)
+    assert plan.grad_buckets[0][1] == total and plan.grad_buckets[-1][0] == 0
