@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int b_stage_bytes = p.tile_n * BK * 2;
+  // MN-major B is staged as whole 64-column atoms (the MMA reads the first tile_n columns of them)
+  const int b_stage_bytes = (p.b_mn ? ((p.tile_n + 63) & ~63) : p.tile_n) * BK * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint8_t* ctrl = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (!p.b_mn) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
           } else {
-            for (int j = 0; j < p.tile_n / 64; ++j)
+            for (int j = 0; j < (p.tile_n + 63) / 64; ++j)
               tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BK + b_shift);
           }
           if (++stage == p.stages) {
@@ -459,10 +460,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             v.x *= alpha, v.y *= alpha, v.z *= alpha, v.w *= alpha;
             if (ok) {
               float* o = p.out_f32 + orow[k] * p.ld_o32 + col;
-              atomicAdd(o, v.x);
-              if (col + 1 < n_end) atomicAdd(o + 1, v.y);
-              if (col + 2 < n_end) atomicAdd(o + 2, v.z);
-              if (col + 3 < n_end) atomicAdd(o + 3, v.w);
+              if (cfull && p.vec_ok) {  // one 16-byte reduction instead of four (L2 atomic throughput bound)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z),
+                             "f"(v.w)
+                             : "memory");
+              } else {
+                atomicAdd(o, v.x);
+                if (col + 1 < n_end) atomicAdd(o + 1, v.y);
+                if (col + 2 < n_end) atomicAdd(o + 2, v.z);
+                if (col + 3 < n_end) atomicAdd(o + 3, v.w);
+              }
             }
             continue;
           }
@@ -584,7 +591,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 // ------------------------------------------------------------------------------------------ host
 static int pick_tile_n(int m, int n, int split_k, int b_mn, int sms) {
   const int tiles_m = ceil_div(m, BM);
-  const int step = b_mn ? 64 : 16;
+  const int step = 16;  // MMA N granularity (MN-major B is staged in 64-column atoms, any multiple of 16 is legal)
+  (void)b_mn;
   int best = 0;
   double best_cost = 1e30;
   for (int bn = step; bn <= 256; bn += step) {
@@ -674,7 +682,6 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (tile_n <= 0) tile_n = pick_tile_n(a->m, a->n, split_k * b_ntaps, a->b_mn_major, sms);
   FVIT_CHECK(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "fvit_gemm: tile_n=%d invalid",
              tile_n);
-  if (a->b_mn_major) FVIT_CHECK(tile_n % 64 == 0, "fvit_gemm: MN-major B needs tile_n %% 64 == 0");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -695,7 +702,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.split_k = split_k < p.num_kb ? split_k : p.num_kb;
   if (p.split_k < 1) p.split_k = 1;
   p.atomic_out = split_k > 1 ? 1 : 0;
-  const int stage_bytes = A_STAGE_BYTES + tile_n * BK * 2;
+  const int stage_bytes = A_STAGE_BYTES + (a->b_mn_major ? ((tile_n + 63) & ~63) : tile_n) * BK * 2;
   const int stats_bytes = a->col_sum ? SMEM_STATS_BYTES : 0;
   int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK - SMEM_STG_BYTES - stats_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;

@@ -1016,14 +1016,14 @@ __global__ void token_init_bwd_kernel(const float* __restrict__ g, long long ldg
         const int cy = y - r + 1, cx = x - s + 1;
         if (cy < 0 || cy >= Hp || cx < 0 || cx >= Wp) continue;
         const float wt = w[c * 9 + r * 3 + s] * inv;
-        for (int y0 = 0; y0 < oh; ++y0) {
-          if (cy < y0 * sh || cy >= y0 * sh + kh) continue;
-          for (int x0 = 0; x0 < ow; ++x0) {
-            if (cx < x0 * sw || cx >= x0 * sw + kw) continue;
+        // pooled outputs covering conv pixel (cy, cx): y0*sh <= cy < y0*sh + kh
+        const int y0lo = cy - kh + sh >= 0 ? (cy - kh + sh) / sh : 0, y0hi = min(oh - 1, cy / sh);
+        const int x0lo = cx - kw + sw >= 0 ? (cx - kw + sw) / sw : 0, x0hi = min(ow - 1, cx / sw);
+        for (int y0 = y0lo; y0 <= y0hi; ++y0)
+          for (int x0 = x0lo; x0 <= x0hi; ++x0) {
             const int crow = ct_row_map[((long long)b * oh + y0) * ow + x0];
             acc = fmaf(wt, g[(long long)crow * ldg + c], acc);
           }
-        }
       }
     gx[(long long)row * ldgx + c] += acc;
   }
@@ -1034,34 +1034,51 @@ __global__ void token_init_wgrad_kernel(const float* __restrict__ g, long long l
                                         const int* __restrict__ ct_row_map, int B, int Hp, int Wp, int C, int kh,
                                         int kw, int sh, int sw, int oh, int ow, const float* __restrict__ scalar,
                                         float* __restrict__ dw, float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float red[3][10][128];
+  const int cl = threadIdx.x & 127, lane_p = threadIdx.x >> 7;  // 128 channels x 4 position lanes
+  const int c = blockIdx.x * 128 + cl;
   const float inv = 1.f / (float)(kh * kw);
   float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   float ab = 0.f;
-  for (long long pos = blockIdx.y; pos < (long long)B * oh * ow; pos += gridDim.y) {
-    const int x0 = (int)(pos % ow), y0 = (int)((pos / ow) % oh), b = (int)(pos / ((long long)ow * oh));
-    const float gv = g[(long long)ct_row_map[pos] * ldg + c];
-    ab += gv;
-    for (int py = 0; py < kh; ++py)
-      for (int px = 0; px < kw; ++px) {
-        const int cy = y0 * sh + py, cx = x0 * sw + px;
+  if (c < C) {
+    for (long long pos = blockIdx.y * 4 + lane_p; pos < (long long)B * oh * ow; pos += gridDim.y * 4) {
+      const int x0 = (int)(pos % ow), y0 = (int)((pos / ow) % oh), b = (int)(pos / ((long long)ow * oh));
+      const float gv = g[(long long)ct_row_map[pos] * ldg + c];
+      ab += gv;
+      // dw[tap] += gv/(kh kw) * sum over the pool window of x[conv pixel + tap - 1]: walk the (kh+2) x (kw+2) input
+      // patch once and add each pixel to the (up to 9) taps that see it
+      for (int py = -1; py <= kh; ++py) {
+        const int iy = y0 * sh + py;
+        if (iy < 0 || iy >= Hp) continue;
+        for (int px = -1; px <= kw; ++px) {
+          const int ix = x0 * sw + px;
+          if (ix < 0 || ix >= Wp) continue;
+          const int row = pix_map[((long long)b * Hp + iy) * Wp + ix];
+          if (row < 0) continue;
+          const float xv = gv * inv * __half2float(xs[(long long)row * ldx + c]);
+          // input pixel offset py = conv offset (py - r + 1) must lie in [0, kh): r in [py - kh + 2, py + 1]
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int iy = cy + r - 1, ix = cx + s - 1;
-            if (iy >= 0 && iy < Hp && ix >= 0 && ix < Wp) {
-              const int row = pix_map[((long long)b * Hp + iy) * Wp + ix];
-              if (row >= 0) acc[r * 3 + s] = fmaf(gv * inv, __half2float(xs[(long long)row * ldx + c]), acc[r * 3 + s]);
-            }
-          }
+            for (int s = 0; s < 3; ++s)
+              if (py - r + 1 >= 0 && py - r + 1 < kh && px - s + 1 >= 0 && px - s + 1 < kw) acc[r * 3 + s] += xv;
+        }
       }
+    }
   }
-  const float sc = scalar ? __ldg(scalar) : 1.f;
+  if (lane_p > 0) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t) atomicAdd(dw + c * 9 + t, acc[t] * sc);
-  atomicAdd(dbias + c, ab * sc);
+    for (int t9 = 0; t9 < 9; ++t9) red[lane_p - 1][t9][cl] = acc[t9];
+    red[lane_p - 1][9][cl] = ab;
+  }
+  __syncthreads();
+  if (lane_p == 0 && c < C) {
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9)
+      atomicAdd(dw + c * 9 + t9, (acc[t9] + red[0][t9][cl] + red[1][t9][cl] + red[2][t9][cl]) * sc);
+    atomicAdd(dbias + c, (ab + red[0][9][cl] + red[1][9][cl] + red[2][9][cl]) * sc);
+  }
 }
 
 // Backward of fvit_propagate_fwd (x[r] += gamma * x[src[r]]): g[src[r]] += gamma * g[r] (atomics: a carrier
@@ -1403,8 +1420,9 @@ int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ld
                         int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t oh, int32_t ow, const float* scalar,
                         float* gx, int64_t ldgx, float* dw, float* dbias, void* stream) {
   FVIT_CHECK(g && x16 && pix_map && ct_row_map && w && gx && dw && dbias, "fvit_token_init_bwd: null argument");
-  dim3 gw((unsigned)((C + 127) / 128), (unsigned)(B * oh * ow < 256 ? B * oh * ow : 256));
-  token_init_wgrad_kernel<<<gw, 128, 0, (cudaStream_t)stream>>>(g, ldg, (const __half*)x16, ldx, pix_map, ct_row_map, B, Hp, Wp, C, kh, kw,
+  const int npos4 = (B * oh * ow + 3) / 4;
+  dim3 gw((unsigned)((C + 127) / 128), (unsigned)(npos4 < 512 ? npos4 : 512));
+  token_init_wgrad_kernel<<<gw, 512, 0, (cudaStream_t)stream>>>(g, ldg, (const __half*)x16, ldx, pix_map, ct_row_map, B, Hp, Wp, C, kh, kw,
                                                                 sh, sw, oh, ow, scalar, dw, dbias);
   int rc = post_launch("token_init_wgrad_kernel");
   if (rc) return rc;

@@ -142,8 +142,15 @@ class TrainPlan(Plan):
 
     def _split_k(self, m: int, n: int, k_rows: int, ntaps: int = 1) -> int:
         tiles = ((m + 127) // 128) * ((n + 255) // 256) * ntaps
-        want = max(1, (2 * 148) // max(tiles, 1))
-        return max(1, min(want, (k_rows + 63) // 64, 64))
+        kb = (k_rows + 63) // 64
+        best, best_cost = 1, float("inf")
+        for sk in range(1, max(1, min(64, kb // 8)) + 1):
+            # time model (us): waves of CTAs x (K blocks of one unit x 0.26 us per 128x256x64 block + epilogue);
+            # the split-K epilogue is a pass of fp32 vector reductions into L2 (~10 us per tile, measured)
+            cost = -(-tiles * sk // 148) * (kb / sk * 0.26 + (10.0 if sk > 1 else 3.0))
+            if cost < best_cost - 1e-9:
+                best, best_cost = sk, cost
+        return best
 
     # ------------------------------------------------------------------------------ linear layer backward
     def _linear_bwd(self, *, lin, w16, ldw, x16, ldx, dz16, lddz, rows, n_out, k_in, br, gW=None, gW_ld=None,

@@ -127,6 +127,22 @@ def test_gemm_mn_major(a_mn, b_mn, m, n, k):
     assert _rel(out, A.float() @ B.float().t()) < 2e-5
 
 
+@pytest.mark.parametrize("tile_n", [16, 80, 208])
+def test_gemm_mn_major_b_partial_atom_tiles(tile_n):
+    """MN-major B is staged in 64-column atoms; the MMA N (tile_n) may be any multiple of 16."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(tile_n)
+    m, n, k = 300, 392, 1000
+    A = torch.randn(k, m + 4, device="cuda", generator=g).half()[:, :m]
+    B = torch.randn(k, n, device="cuda", generator=g).half()
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(A, B, a_mn=True, b_mn=True, tile_n=tile_n, out_f32=out)
+    assert _rel(out, A.float().t() @ B.float()) < 2e-5
+    A2 = torch.randn(m, k, device="cuda", generator=g).half()
+    lib.gemm(A2, B, b_mn=True, tile_n=tile_n, out_f32=out)
+    assert _rel(out, A2.float() @ B.float()) < 2e-5
+
+
 def test_gemm_split_k_and_row_offsets():
     lib = _lib()
     g = torch.Generator(device="cuda").manual_seed(21)

@@ -143,17 +143,16 @@ def test_gradient_buckets_partition_the_flat_buffer():
     on parameter boundaries and are listed last-level-first."""
     g, tr, model, logits, loss = _run("tiny_a")
     plan = next(p for p in model._get_engine().plans.values() if p.training)
-    total = sum(p.numel() for p in model.parameters())
+    total = plan.gflat.numel()     # parameter slices are padded to 256-byte boundaries
     assert sorted(plan.grad_buckets) == sorted(set(plan.grad_buckets))
     covered = sorted(plan.grad_buckets)
     assert covered[0][0] == 0 and covered[-1][1] == total
     for (a0, a1), (b0, b1) in zip(covered, covered[1:]):
         assert a1 == b0
-    offs = set()
-    o = 0
-    for p in model.parameters():
-        offs.add(o)
-        o += p.numel()
-    offs.add(o)
+    offs = set(plan._goff.values()) | {total}
     assert all(lo in offs and hi in offs for lo, hi in plan.grad_buckets)
     assert plan.grad_buckets[0][1] == total and plan.grad_buckets[-1][0] == 0
+    # every parameter's slice lies inside exactly one bucket
+    for p in model.parameters():
+        o = plan._goff[id(p)]
+        assert sum(1 for lo, hi in plan.grad_buckets if lo <= o and o + p.numel() <= hi) == 1
