@@ -207,6 +207,8 @@ def main() -> None:
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line contract)
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)

@@ -67,7 +67,8 @@ def test_forward_features_and_head_split():
     assert (again - full).abs().max().item() <= 1e-3 * full.abs().max().item()
     # oracle check of the pooled features themselves
     from oracle import fastervit_oracle as O
-    sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    sd = {k: (v.detach().cpu().double() if v.is_floating_point() else v.detach().cpu())
+          for k, v in model.state_dict().items()}
     cap = {}
     O.forward(sd, g["cfg"], x.cpu().double(), capture=cap)
     ref = cap["pooled"]
