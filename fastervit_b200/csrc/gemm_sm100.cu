@@ -79,6 +79,10 @@ struct GemmParams {
   const float* row_scale;   // optional fp32 [m] factor applied with col_scale2 (after act)
   void* out_pre16;          // optional fp16 copy of the value before col_scale2 / row_scale / resid
   long long ld_pre16;
+  const float* aux_scale;   // optional per-column affine applied to aux before the activation derivative
+  const float* aux_shift;
+  float* osum;              // optional: osum[c] += *osum_alpha * sum over rows of the rounded out_f16 values
+  const float* osum_alpha;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return fvit_gelu(x); }
@@ -156,6 +160,7 @@ enum : uint32_t {
   EF_ALPHAPTR = 1u << 10,
   EF_CS2 = 1u << 11,
   EF_RS = 1u << 12,
+  EF_OSUM = 1u << 13,        // per-column sum of the rounded 16-bit output (bias gradient of the next layer)
 };
 // work unit -> (M tile, N tile, K split). Plain GEMMs keep the K splits of a tile adjacent; the tap-in-N mode
 // walks all tiles of one K range first so concurrently running CTAs share the A / B slices in L2.
@@ -338,11 +343,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool has_rs = GENERIC ? (p.row_scale != nullptr) : ((FEAT & EF_RS) != 0);
     const bool has_pre = GENERIC ? (p.out_pre16 != nullptr) : ((FEAT & EF_PRE) != 0);
     const bool has_aptr = GENERIC ? (p.alpha_ptr != nullptr) : ((FEAT & EF_ALPHAPTR) != 0);
+    const bool osum = GENERIC ? (p.osum != nullptr) : ((FEAT & EF_OSUM) != 0);
     const float alpha = has_aptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     if (stats) {
       for (int i = threadIdx.x - 64; i < 2 * p.n; i += GEMM_THREADS - 64) stat_s[i] = 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
     }
+    if (osum) {  // tile-local column sums: stat_s[0 .. tile_n)
+      stat_s[threadIdx.x - 64] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const float osum_alpha = (osum && p.osum_alpha) ? __ldg(p.osum_alpha) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
@@ -422,6 +433,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (has_cs2) cs2 = ld_vec4_guard(p.col_scale2 + col, n_end - col, 1.f);
         }
         cs.x *= alpha, cs.y *= alpha, cs.z *= alpha, cs.w *= alpha;  // fold alpha
+        float4 asc = make_float4(1.f, 1.f, 1.f, 1.f), ash = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (use_aux && p.aux_scale && cany) {
+          asc = ld_vec4_guard(p.aux_scale + col, n_end - col, 1.f);
+          ash = ld_vec4_guard(p.aux_shift + col, n_end - col, 0.f);
+        }
         // ---- 2. accumulators: TMEM -> registers -> staging tile
         if (!waited) {
           mbar_wait(&acc_full[acc], acc_phase);
@@ -499,6 +515,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           } else if (use_aux) {
             float a[4];
             unpack4_16(av[k], p.bf16, a);
+            if (p.aux_scale) {  // aux holds the raw convolution output: pre-activation = raw * scale + shift (BatchNorm)
+              a[0] = fmaf(a[0], asc.x, ash.x), a[1] = fmaf(a[1], asc.y, ash.y), a[2] = fmaf(a[2], asc.z, ash.z),
+              a[3] = fmaf(a[3], asc.w, ash.w);
+            }
             if (act == FVIT_ACT_GELU_BWD) {
               v.x *= gelu_erf_grad(a[0]), v.y *= gelu_erf_grad(a[1]), v.z *= gelu_erf_grad(a[2]),
               v.w *= gelu_erf_grad(a[3]);
@@ -535,9 +555,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if (col + 2 < n_end) o[2] = (uint16_t)(hi & 0xFFFF);
               if (col + 3 < n_end) o[3] = (uint16_t)(hi >> 16);
             }
+            if (osum) {
+              float r4[4];
+              unpack4_16(make_uint2(lo, hi), p.bf16, r4);
+              s1.x += r4[0], s1.y += r4[1], s1.z += r4[2], s1.w += r4[3];
+            }
           }
         }
         __syncwarp();
+        if (osum) {
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o), s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o), s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+          }
+          if (sub == 0 && cany) {
+            const int lc = c0 + 4 * c4;  // column within the tile
+            atomicAdd(stat_s + lc, s1.x);
+            if (col + 1 < n_end) atomicAdd(stat_s + lc + 1, s1.y);
+            if (col + 2 < n_end) atomicAdd(stat_s + lc + 2, s1.z);
+            if (col + 3 < n_end) atomicAdd(stat_s + lc + 3, s1.w);
+          }
+        }
         if (stats) {
           // lanes sharing c4 (lane, lane^8, lane^16, lane^24) hold partial sums of the same 4 columns
 #pragma unroll
@@ -558,6 +597,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (!waited) {  // this warp had no chunk in the tile: still consume the phase
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
+      }
+      if (osum) {  // flush this tile's column sums: one global atomic per column per tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int lc = threadIdx.x - 64;
+        if (lc < p.tile_n && n0 + lc < n_end) {
+          const float a = stat_s[lc];
+          if (a != 0.f) atomicAdd(p.osum + n0 + lc, a * osum_alpha);
+        }
+        stat_s[lc] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       // hand the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -676,6 +725,9 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   FVIT_CHECK((a->col_sum == nullptr) == (a->col_sumsq == nullptr),
              "fvit_gemm: col_sum and col_sumsq go together");
   FVIT_CHECK(!a->col_sum || a->n <= STATS_MAX_N, "fvit_gemm: statistics support n <= %d", STATS_MAX_N);
+  FVIT_CHECK((a->aux_scale == nullptr) == (a->aux_shift == nullptr), "fvit_gemm: aux_scale and aux_shift go together");
+  FVIT_CHECK(!a->out_colsum || (a->out_f16 && !a->col_sum && split_k == 1 && b_ntaps == 1),
+             "fvit_gemm: out_colsum needs out_f16, no BN statistics, no split-K");
 
   const int sms = num_sms();
   int tile_n = a->tile_n;
@@ -703,7 +755,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (p.split_k < 1) p.split_k = 1;
   p.atomic_out = split_k > 1 ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + (a->b_mn_major ? ((tile_n + 63) & ~63) : tile_n) * BK * 2;
-  const int stats_bytes = a->col_sum ? SMEM_STATS_BYTES : 0;
+  const int stats_bytes = a->col_sum ? SMEM_STATS_BYTES : (a->out_colsum ? 256 * 4 : 0);
   int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK - SMEM_STG_BYTES - stats_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   FVIT_CHECK(stages >= 2, "fvit_gemm: not enough shared memory for 2 stages");
@@ -736,6 +788,10 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.row_scale = a->row_scale;
   p.out_pre16 = a->out_pre16;
   p.ld_pre16 = a->ld_out_pre16;
+  p.aux_scale = a->aux_scale;
+  p.aux_shift = a->aux_shift;
+  p.osum = a->out_colsum;
+  p.osum_alpha = a->out_colsum_alpha;
   // vector path: every touched row segment must be 16-byte aligned
   bool vec = true;
   if (a->out_f32)
@@ -785,6 +841,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (a->alpha_ptr) feat |= EF_ALPHAPTR;
   if (a->col_scale2) feat |= EF_CS2;
   if (a->row_scale) feat |= EF_RS;
+  if (a->out_colsum) feat |= EF_OSUM;
   const bool needs_generic = false;
 #define FVIT_GEMM_LAUNCH(F)                                                                            \
   do {                                                                                                 \
@@ -823,6 +880,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
       case FVIT_ACTF(0) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O16 | EF_ALPHAPTR);   // dgrad
       case FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR);   // dgrad * gelu'
       case FVIT_ACTF(3) | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16);                               // conv dgrad * gelu'
+      case FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR | EF_OSUM:
+        FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR | EF_OSUM);                                  // fc2 dgrad * gelu' + fc1 bias gradient
       default: break;
     }
   }

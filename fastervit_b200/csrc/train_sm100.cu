@@ -282,6 +282,73 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Entry of a residual-branch backward (x += gamma * f(LN(x)), fv.py:637-655) in one pass over the fp32 stream
+// gradient g: dz16 = half(g * gamma * s * row_scale) (tensor-core operand of the branch's last Linear),
+// dbias[c] += *bias_alpha * sum_r dz (that Linear's bias gradient) and dgamma[c] += *gamma_alpha * sum_r g * u * row_scale
+// (layer-scale gradient, u = saved branch output). Replaces cast_scale_f16 + two colsum launches.
+__global__ void __launch_bounds__(256)
+branch_grad_kernel(const float* __restrict__ g, long long ldg, int rows, int C, const float* __restrict__ colmul,
+                   const float* __restrict__ scalar, const float* __restrict__ row_scale, __half* __restrict__ dz,
+                   long long lddz, const float* __restrict__ bias_alpha, float* __restrict__ dbias,
+                   const __half* __restrict__ u, long long ldu, const float* __restrict__ gamma_alpha,
+                   float* __restrict__ dgamma) {
+  __shared__ float red[8][32][17];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (blockIdx.y * 32 + cg) * 8;
+  float ab[8], ag[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ab[k] = 0.f, ag[k] = 0.f;
+  if (c0 < C) {
+    float cm[8];
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cm[k] = (colmul ? colmul[c0 + k] : 1.f) * sc;
+#pragma unroll 2
+    for (int r = blockIdx.x * 8 + rl; r < rows; r += gridDim.x * 8) {
+      const float4 p0 = *reinterpret_cast<const float4*>(g + (long long)r * ldg + c0);
+      const float4 p1 = *reinterpret_cast<const float4*>(g + (long long)r * ldg + c0 + 4);
+      uint4 uk = make_uint4(0u, 0u, 0u, 0u);
+      if (u) uk = *reinterpret_cast<const uint4*>(u + (long long)r * ldu + c0);
+      const float rs = row_scale ? row_scale[r] : 1.f;
+      float v[8] = {p0.x * rs, p0.y * rs, p0.z * rs, p0.w * rs, p1.x * rs, p1.y * rs, p1.z * rs, p1.w * rs};
+      if (u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&uk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ag[2 * k] = fmaf(v[2 * k], __low2float(h[k]), ag[2 * k]);
+          ag[2 * k + 1] = fmaf(v[2 * k + 1], __high2float(h[k]), ag[2 * k + 1]);
+        }
+      }
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2 hv = __floats2half2_rn(v[2 * k] * cm[2 * k], v[2 * k + 1] * cm[2 * k + 1]);
+        ow[k] = *reinterpret_cast<const uint32_t*>(&hv);
+        ab[2 * k] += __low2float(hv), ab[2 * k + 1] += __high2float(hv);   // sum of the rounded operand values
+      }
+      *reinterpret_cast<uint4*>(dz + (long long)r * lddz + c0) = o;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg][k] = ab[k], red[rl][cg][8 + k] = ag[k];
+  __syncthreads();
+  // 32 column groups x 16 sums per block: one thread per (group, sum)
+  for (int o = threadIdx.x; o < 32 * 16; o += 256) {
+    const int grp = o >> 4, k = o & 15;
+    const int c = (blockIdx.y * 32 + grp) * 8 + (k & 7);
+    if (c >= C) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][grp][k];
+    if (k < 8) {
+      if (dbias) atomicAdd(dbias + c, s * (bias_alpha ? __ldg(bias_alpha) : 1.f));
+    } else if (dgamma && u) {
+      atomicAdd(dgamma + c, s * (gamma_alpha ? __ldg(gamma_alpha) : 1.f));
+    }
+  }
+}
+
 // out[(t - skip)][c] += *scalar * sum_w a[w*group + t][c]  for skip <= t < group (gradient of a
 // positional embedding that was broadcast-added to every group; fp32 input)
 __global__ void group_sum_kernel(const float* __restrict__ a, long long lda, int ngroups, int group, int skip,
@@ -1204,6 +1271,24 @@ int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_r
     colsum_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, a_rows, (const __half*)b16, ldb, nrows, C,
                                                              colmul, scalar, out, row_scale);
   return post_launch("colsum_kernel");
+}
+
+int fvit_branch_grad(const float* g, int64_t ldg, int32_t rows, int32_t C, const float* colmul, const float* scalar,
+                     const float* row_scale, void* dz16, int64_t lddz, const float* bias_alpha, float* dbias,
+                     const void* u16, int64_t ldu, const float* gamma_alpha, float* dgamma, void* stream) {
+  FVIT_CHECK(g && dz16 && rows > 0 && C > 0 && C % 8 == 0 && ldg % 4 == 0 && lddz % 8 == 0 && (!u16 || ldu % 8 == 0) &&
+                 (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz16) & 15) == 0 &&
+                 (!u16 || (reinterpret_cast<uintptr_t>(u16) & 15) == 0),
+             "fvit_branch_grad: needs C %% 8 == 0 and 16-byte aligned rows");
+  const unsigned gy = (unsigned)((C + 255) / 256);
+  long long gx = ((long long)num_sms() * 8 + gy - 1) / gy;
+  const long long gx_max = ((long long)rows + 31) / 32;
+  if (gx > gx_max) gx = gx_max;
+  if (gx < 1) gx = 1;
+  branch_grad_kernel<<<dim3((unsigned)gx, gy), 256, 0, (cudaStream_t)stream>>>(
+      g, ldg, rows, C, colmul, scalar, row_scale, (__half*)dz16, lddz, bias_alpha, dbias, (const __half*)u16, ldu,
+      gamma_alpha, dgamma);
+  return post_launch("branch_grad_kernel");
 }
 
 int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, int32_t skip, int32_t C,

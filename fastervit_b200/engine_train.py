@@ -92,7 +92,7 @@ class TrainPlan(Plan):
                 if isinstance(args, tuple):
                     lst[i] = (fn, tuple(res(a) for a in args), name)
         for g in self._gemm_keep:
-            for f in ("alpha_ptr", "out_f32", "col_sum", "col_sumsq"):
+            for f in ("alpha_ptr", "out_f32", "col_sum", "col_sumsq", "out_colsum", "out_colsum_alpha"):
                 v = getattr(g, "_sym_" + f, None)
                 if v is not None:
                     setattr(g, f, res(v))
@@ -110,7 +110,7 @@ class TrainPlan(Plan):
     def _bgemm(self, *, a, a_rows, lda, b, b_rows, ldb, m, n, kc, a_mn=False, b_mn=False, taps=None, a_planes=1,
                a_plane_stride=0, b_row_off=0, b_taps=None, split_k=1, alpha_ptr=None, act=L.ACT_NONE, aux=None, ld_aux=0,
                out_f32=None, ld_o32=0, out_f16=None, ld_o16=0, row_map=None, resid=None, ld_resid=0, target=None,
-               flops=None) -> None:
+               flops=None, out_colsum=None, out_colsum_alpha=None, aux_scale=None, aux_shift=None) -> None:
         g = L.GemmArgs()
         g.a, g.a_rows, g.lda, g.a_plane_stride, g.a_planes, g.a_mn_major = a, a_rows, lda, a_plane_stride, a_planes, int(a_mn)
         g.b, g.b_rows, g.ldb, g.b_mn_major = b, b_rows, ldb, int(b_mn)
@@ -127,9 +127,11 @@ class TrainPlan(Plan):
                 g.tap_shift[i] = sft
         g.split_k, g.alpha, g.act = split_k, 1.0, act
         g.aux, g.ld_aux, g.row_map = aux, ld_aux, row_map
+        g.aux_scale, g.aux_shift = aux_scale, aux_shift
         g.resid, g.ld_resid = resid, ld_resid
         g.out_f16, g.ld_out_f16, g.ld_out_f32 = out_f16, ld_o16, ld_o32
-        for f, v in (("alpha_ptr", alpha_ptr), ("out_f32", out_f32)):
+        for f, v in (("alpha_ptr", alpha_ptr), ("out_f32", out_f32), ("out_colsum", out_colsum),
+                     ("out_colsum_alpha", out_colsum_alpha)):
             if isinstance(v, tuple):
                 setattr(g, "_sym_" + f, v)
             elif v is not None:
@@ -155,7 +157,7 @@ class TrainPlan(Plan):
     # ------------------------------------------------------------------------------ linear layer backward
     def _linear_bwd(self, *, lin, w16, ldw, x16, ldx, dz16, lddz, rows, n_out, k_in, br, gW=None, gW_ld=None,
                     dx16=None, lddx=0, dx_act=L.ACT_NONE, dx_aux=None, ld_aux=0, dx_alpha=None, bias_to=None,
-                    flops_k=None, want_dgrad=True) -> None:
+                    flops_k=None, want_dgrad=True, bias_done=False, dx_colsum=None) -> None:
         """dW[n_out, k_in] += alpha_w * dz16^T @ x16 ; db += alpha_w * colsum(dz16) ; dx16 = alpha_d * dz16 @ W."""
         gW = self.G(lin.weight) if gW is None else gW
         gW_ld = k_in if gW_ld is None else gW_ld
@@ -163,13 +165,15 @@ class TrainPlan(Plan):
         self._bgemm(a=dz16, a_rows=rows, lda=lddz, a_mn=True, b=x16, b_rows=rows, ldb=ldx, b_mn=True, m=n_out, n=k_in,
                     kc=rows, split_k=self._split_k(n_out, k_in, rows), alpha_ptr=br["w_alpha"], out_f32=gW,
                     ld_o32=gW_ld, flops=2.0 * rows * n_out * fk)
-        if lin.bias is not None or bias_to is not None:
+        if (lin.bias is not None or bias_to is not None) and not bias_done:
             dst = bias_to if bias_to is not None else self.G(lin.bias)
             self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst, None)
         if want_dgrad:
             self._bgemm(a=dz16, a_rows=rows, lda=lddz, b=w16, b_rows=n_out, ldb=ldw, b_mn=True, m=rows, n=k_in, kc=n_out,
                         alpha_ptr=dx_alpha if dx_alpha is not None else br["inv_s"], act=dx_act, aux=dx_aux,
-                        ld_aux=ld_aux, out_f16=dx16, ld_o16=lddx, flops=2.0 * rows * n_out * fk)
+                        ld_aux=ld_aux, out_f16=dx16, ld_o16=lddx, flops=2.0 * rows * n_out * fk,
+                        out_colsum=dx_colsum[0] if dx_colsum else None,
+                        out_colsum_alpha=dx_colsum[1] if dx_colsum else None)
 
     # ------------------------------------------------------------------------------ plan construction
     def _build(self) -> None:

@@ -117,8 +117,6 @@ def _conv_level_train_buffers(self, i: int, Cc: int, Hc: int, Wc: int, depth: in
              pix=nb.i32(f"l{i}.pix", ident[:, 1:-1, 1:-1].reshape(-1)),
              x32=nb.new(f"l{i}.x32", (rows, Cc), torch.float32),
              x16s=[nb.new(f"l{i}.x16.{j}", (rows, ld), torch.float16) for j in range(depth + 1)],
-             h16=nb.new(f"l{i}.h16", (rows, ld), torch.float16),
-             pre16=nb.new(f"l{i}.pre16", (rows, ld), torch.float16),
              dzA=nb.new(f"l{i}.dzA", (rows, ld), torch.float16), dzB=nb.new(f"l{i}.dzB", (rows, ld), torch.float16),
              dyA=nb.new(f"l{i}.dyA", (rows, ld), torch.float16),
              g=nb.new(f"l{i}.g", (rows + 1, Cc), torch.float32), zero_row=rows)
@@ -143,6 +141,7 @@ def _emit_conv_blocks_train(self, i: int, level, lv: dict) -> None:
         w2, ld2 = self._pack_conv(nm + ".conv2", blk.conv2)
         rawA = nb.new(nm + ".rawA", (rows, ld), torch.float16)
         rawB = nb.new(nm + ".rawB", (rows, ld), torch.float16)
+        h16 = nb.new(nm + ".h16", (rows, ld), torch.float16)   # kept for the conv2 weight gradient (zero borders)
         bnA = _bn_train(self, nm + ".bn1", blk.norm1, npix)
         bnB = _bn_train(self, nm + ".bn2", blk.norm2, npix)
         xin, xout = lv["x16s"][j], lv["x16s"][j + 1]
@@ -151,8 +150,8 @@ def _emit_conv_blocks_train(self, i: int, level, lv: dict) -> None:
                    out_f16=rawA.data_ptr(), ld_o16=ld, col_sum=bnA["st"][0].data_ptr(), col_sumsq=bnA["st"][1].data_ptr())
         _bn_finalize(self, bnA)
         self._op(self.ops, "fvit_affine_rows", rawA.data_ptr(), ld, lv["pix"].data_ptr(), npix, Cc, bnA["sc"].data_ptr(),
-                 bnA["sh"].data_ptr(), L.ACT_GELU, None, 0, None, 0, lv["h16"].data_ptr(), ld, None)
-        self._gemm(a=lv["h16"].data_ptr(), a_rows=rows, lda=ld, b=w2.data_ptr(), ldb=ld2, m=rows, n=Cc, kc=Cc, taps=taps,
+                 bnA["sh"].data_ptr(), L.ACT_GELU, None, 0, None, 0, h16.data_ptr(), ld, None)
+        self._gemm(a=h16.data_ptr(), a_rows=rows, lda=ld, b=w2.data_ptr(), ldb=ld2, m=rows, n=Cc, kc=Cc, taps=taps,
                    m_alg=npix, col_shift=blk.conv2.bias.data_ptr(), row_map=lv["interior"].data_ptr(),
                    out_f16=rawB.data_ptr(), ld_o16=ld, col_sum=bnB["st"][0].data_ptr(), col_sumsq=bnB["st"][1].data_ptr())
         _bn_finalize(self, bnB)
@@ -163,7 +162,8 @@ def _emit_conv_blocks_train(self, i: int, level, lv: dict) -> None:
         wT2 = nb.new(nm + ".conv2.wT16", (Cc, 9 * _ru(Cc, 64)), torch.float16)
         self._op(self.prep_ops, "fvit_pack_conv3x3_f16", blk.conv1.weight.data_ptr(), wT1.data_ptr(), Cc, Cc, _ru(Cc, 64), 1)
         self._op(self.prep_ops, "fvit_pack_conv3x3_f16", blk.conv2.weight.data_ptr(), wT2.data_ptr(), Cc, Cc, _ru(Cc, 64), 1)
-        lv["blocks_sv"].append(dict(blk=blk, rawA=rawA, rawB=rawB, bnA=bnA, bnB=bnB, xin=xin, wT1=wT1, wT2=wT2, rs=rs))
+        lv["blocks_sv"].append(dict(blk=blk, rawA=rawA, rawB=rawB, h16=h16, bnA=bnA, bnB=bnB, xin=xin, wT1=wT1, wT2=wT2,
+                                    rs=rs))
 
 
 def _emit_downsample_train(self, i: int, src: dict, dst: dict) -> None:
@@ -273,16 +273,15 @@ def _emit_conv_blocks_bwd(self, lv: dict) -> None:
                  bnB["rs"].data_ptr(), blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr(), L.ACT_NONE, None,
                  bnB["s12"][0].data_ptr(), bnB["s12"][1].data_ptr(), inv, lv["dzB"].data_ptr(), ld, pix,
                  self.G(blk.norm2.weight), self.G(blk.norm2.bias), sv["rs"])
-        # recompute h = GELU(pre), pre = BN1(rawA) from the saved raw output
-        self._op(ops, "fvit_affine_rows", sv["rawA"].data_ptr(), ld, pix, npix, Cc, bnA["sc"].data_ptr(), bnA["sh"].data_ptr(),
-                 L.ACT_GELU, None, 0, None, 0, lv["h16"].data_ptr(), ld, None)
-        self._op(ops, "fvit_affine_rows", sv["rawA"].data_ptr(), ld, pix, npix, Cc, bnA["sc"].data_ptr(), bnA["sh"].data_ptr(),
-                 L.ACT_NONE, None, 0, None, 0, lv["pre16"].data_ptr(), ld, None)
-        _conv_wgrad(self, dz=lv["dzB"].data_ptr(), lddz=ld, x=lv["h16"].data_ptr(), ldx=ld, x_rows=rows, rows=rows, cout=Cc,
+        # h = GELU(BN1(rawA)) was kept by the forward; the pre-activation BN1(rawA) is re-derived inside the dgrad
+        # epilogue from rawA and the batch-statistics affine (aux_scale / aux_shift).
+        # conv biases sit in front of a batch-statistics BatchNorm: their gradient sum_rows(dz) is identically zero
+        # (BN backward removes the per-channel mean), so it is left at the zero the buffer was cleared to.
+        _conv_wgrad(self, dz=lv["dzB"].data_ptr(), lddz=ld, x=sv["h16"].data_ptr(), ldx=ld, x_rows=rows, rows=rows, cout=Cc,
                     cin=Cc, shifts=shifts, conv_weight=blk.conv2.weight, name="convB")
-        self._op(ops, "fvit_colsum", lv["dzB"].data_ptr(), 1, ld, None, None, 0, rows, Cc, None, inv, self.G(blk.conv2.bias), None)
         self._bgemm(a=lv["dzB"].data_ptr(), a_rows=rows, lda=ld, b=sv["wT2"].data_ptr(), b_rows=Cc, ldb=9 * _ru(Cc, 64),
-                    m=rows, n=Cc, kc=Cc, taps=lv["taps"], act=L.ACT_GELU_BWD, aux=lv["pre16"].data_ptr(), ld_aux=ld,
+                    m=rows, n=Cc, kc=Cc, taps=lv["taps"], act=L.ACT_GELU_BWD, aux=sv["rawA"].data_ptr(), ld_aux=ld,
+                    aux_scale=bnA["sc"].data_ptr(), aux_shift=bnA["sh"].data_ptr(),
                     row_map=interior, out_f16=lv["dyA"].data_ptr(), ld_o16=ld, flops=2.0 * npix * Cc * Cc * 9)
         self._op(ops, "fvit_bn_bwd", lv["dyA"].data_ptr(), 1, ld, pix, sv["rawA"].data_ptr(), ld, pix, npix, Cc,
                  bnA["mu"].data_ptr(), bnA["rs"].data_ptr(), blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(), L.ACT_NONE,
@@ -290,7 +289,6 @@ def _emit_conv_blocks_bwd(self, lv: dict) -> None:
                  self.G(blk.norm1.weight), self.G(blk.norm1.bias), None)
         _conv_wgrad(self, dz=lv["dzA"].data_ptr(), lddz=ld, x=sv["xin"].data_ptr(), ldx=ld, x_rows=rows, rows=rows, cout=Cc,
                     cin=Cc, shifts=shifts, conv_weight=blk.conv1.weight, name="convA")
-        self._op(ops, "fvit_colsum", lv["dzA"].data_ptr(), 1, ld, None, None, 0, rows, Cc, None, inv, self.G(blk.conv1.bias), None)
         # g += conv1 data gradient
         self._bgemm(a=lv["dzA"].data_ptr(), a_rows=rows, lda=ld, b=sv["wT1"].data_ptr(), b_rows=Cc, ldb=9 * _ru(Cc, 64),
                     m=rows, n=Cc, kc=Cc, taps=lv["taps"], row_map=interior, resid=g, ld_resid=Cc, out_f32=g, ld_o32=Cc,

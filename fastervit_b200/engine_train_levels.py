@@ -409,17 +409,27 @@ def _mlp_bwd(self, tl: dict, ms: dict, gamma, g_ptr: int, rows: int, ln: nn.Laye
     Cc, hid = mlp.fc1.weight.shape[1], mlp.fc1.weight.shape[0]
     br = self._branch(gamma)
     dz, dp, dy = tl["dz"], tl["dp"], tl["dy"]
-    self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, ms["rs"])
-    if br["gamma"] is not None:
-        self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, ms["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
-                 self.G(gamma), ms["rs"])
+    fused = Cc % 8 == 0 and mlp.fc2.bias is not None
+    if fused:   # operand cast + fc2 bias gradient + layer-scale gradient in one pass over g
+        has_g = br["gamma"] is not None
+        self._op(ops, "fvit_branch_grad", g_ptr, Cc, rows, Cc, P(br["gamma"]), br["s"], ms["rs"], dz.data_ptr(), Cc,
+                 br["w_alpha"], self.G(mlp.fc2.bias), ms["u16"].data_ptr() if has_g else None, Cc, ("scal", 1),
+                 self.G(gamma) if has_g else None)
+    else:
+        self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, ms["rs"])
+        if br["gamma"] is not None:
+            self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, ms["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
+                     self.G(gamma), ms["rs"])
     # fc2: dW2, db2, dp = (dz W2) o gelu'(p)
     self._linear_bwd(lin=mlp.fc2, w16=ms["w2"].data_ptr(), ldw=ms["ld2"], x16=ms["h16"].data_ptr(), ldx=hid,
                      dz16=dz.data_ptr(), lddz=Cc, rows=rows, n_out=Cc, k_in=hid, br=br, dx16=dp.data_ptr(), lddx=hid,
-                     dx_act=L.ACT_GELU_BWD, dx_aux=ms["p16"].data_ptr(), ld_aux=hid)
+                     dx_act=L.ACT_GELU_BWD, dx_aux=ms["p16"].data_ptr(), ld_aux=hid, bias_done=fused,
+                     dx_colsum=(self.G(mlp.fc1.bias), ("scal", 1)) if mlp.fc1.bias is not None else None)
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
+    # (fc1's bias gradient = column sums of dp, taken in the epilogue of the GEMM that produced dp)
     self._linear_bwd(lin=mlp.fc1, w16=ms["w1"].data_ptr(), ldw=ms["ld1"], x16=ms["y16"].data_ptr(), ldx=Cc,
-                     dz16=dp.data_ptr(), lddz=hid, rows=rows, n_out=hid, k_in=Cc, br=one, dx16=dy.data_ptr(), lddx=Cc)
+                     dz16=dp.data_ptr(), lddz=hid, rows=rows, n_out=hid, k_in=Cc, br=one, dx16=dy.data_ptr(), lddx=Cc,
+                     bias_done=mlp.fc1.bias is not None)
     self._op(ops, "fvit_ln_bwd", dy.data_ptr(), Cc, None, xh.data_ptr(), Cc, rs.data_ptr(), ln.weight.data_ptr(), rows, Cc,
              g_ptr, Cc, in_map, 1, 0, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
 
@@ -434,10 +444,17 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     br = self._branch(gamma)
     dz, dy, dao, dqkv = tl["dz"], tl["dy"], tl["dao"], tl["dqkv"]
     padded = hdp != hd
-    self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, at["rs"])
-    if br["gamma"] is not None:
-        self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, at["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
-                 self.G(gamma), at["rs"])
+    fused = Cc % 8 == 0 and attn.proj.bias is not None
+    if fused:   # operand cast + proj bias gradient + layer-scale gradient in one pass over g
+        has_g = br["gamma"] is not None
+        self._op(ops, "fvit_branch_grad", g_ptr, Cc, rows, Cc, P(br["gamma"]), br["s"], at["rs"], dz.data_ptr(), Cc,
+                 br["w_alpha"], self.G(attn.proj.bias), at["u16"].data_ptr() if has_g else None, Cc, ("scal", 1),
+                 self.G(gamma) if has_g else None)
+    else:
+        self._op(ops, "fvit_cast_scale_f16", g_ptr, Cc, None, rows, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, at["rs"])
+        if br["gamma"] is not None:
+            self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, at["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
+                     self.G(gamma), at["rs"])
     # proj
     if padded:
         gWp = ("scr", self._scratch("dWproj_pad", Cc * Cp))
@@ -445,7 +462,7 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
         gWp = self.G(attn.proj.weight)
     self._linear_bwd(lin=attn.proj, w16=at["wp"].data_ptr(), ldw=at["ldp"], x16=at["ao"].data_ptr(), ldx=Cp,
                      dz16=dz.data_ptr(), lddz=Cc, rows=rows, n_out=Cc, k_in=Cp, br=br, gW=gWp, gW_ld=Cp,
-                     dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc)
+                     dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc, bias_done=fused)
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
     # attention core
@@ -524,14 +541,22 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
     br = self._branch(blk.gamma1)
     dz, dy, dao, dqkv = tl["dz"], tl["dy"], tl["dao"], tl["dqkv"]
     padded = hdp != hd
-    self._op(ops, "fvit_cast_scale_f16", gc_ptr, Cc, None, rows_c, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc, at["rs"])
-    if br["gamma"] is not None:
-        self._op(ops, "fvit_colsum", gc_ptr, 0, Cc, None, at["u16"].data_ptr(), Cc, rows_c, Cc, None, ("scal", 1),
-                 self.G(blk.gamma1), at["rs"])
+    fused = Cc % 8 == 0 and attn.proj.bias is not None
+    if fused:
+        has_g = br["gamma"] is not None
+        self._op(ops, "fvit_branch_grad", gc_ptr, Cc, rows_c, Cc, P(br["gamma"]), br["s"], at["rs"], dz.data_ptr(), Cc,
+                 br["w_alpha"], self.G(attn.proj.bias), at["u16"].data_ptr() if has_g else None, Cc, ("scal", 1),
+                 self.G(blk.gamma1) if has_g else None)
+    else:
+        self._op(ops, "fvit_cast_scale_f16", gc_ptr, Cc, None, rows_c, Cc, P(br["gamma"]), br["s"], dz.data_ptr(), Cc,
+                 at["rs"])
+        if br["gamma"] is not None:
+            self._op(ops, "fvit_colsum", gc_ptr, 0, Cc, None, at["u16"].data_ptr(), Cc, rows_c, Cc, None, ("scal", 1),
+                     self.G(blk.gamma1), at["rs"])
     gWp = ("scr", self._scratch("dWproj_pad_c", Cc * Cp)) if padded else self.G(attn.proj.weight)
     self._linear_bwd(lin=attn.proj, w16=at["wp"].data_ptr(), ldw=at["ldp"], x16=at["ao"].data_ptr(), ldx=Cp,
                      dz16=dz.data_ptr(), lddz=Cc, rows=rows_c, n_out=Cc, k_in=Cp, br=br, gW=gWp, gW_ld=Cp,
-                     dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc)
+                     dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc, bias_done=fused)
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
     self._op(ops, _attn_bwd_entry(n_ct, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, B, n_ct, h, hd,

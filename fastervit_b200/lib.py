@@ -41,6 +41,8 @@ class GemmArgs(C.Structure):
         ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p),
         ("alpha_ptr", C.c_void_p), ("row_scale", C.c_void_p),
         ("out_pre16", C.c_void_p), ("ld_out_pre16", C.c_int64),
+        ("out_colsum", C.c_void_p), ("out_colsum_alpha", C.c_void_p),
+        ("aux_scale", C.c_void_p), ("aux_shift", C.c_void_p),
     ]
 
 
@@ -102,6 +104,7 @@ _OP_SIGS: dict[str, list] = {
     "fvit_cast_scale_f16": [_P, _L, _P, _I, _I, _P, _P, _P, _L, _P, _P],
     "fvit_colsum": [_P, _I, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P],
     "fvit_group_sum": [_P, _L, _I, _I, _I, _I, _P, _P, _P],
+    "fvit_branch_grad": [_P, _L, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _P],
     "fvit_ln_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _P, _L, _P, _I, _I, _P, _P, _P, _P],
     "fvit_attn_tc_bwd": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
     "fvit_attn_core_bwd": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _F, _P, _L, _P, _P],
@@ -151,7 +154,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
          alpha: float = 1.0, act: int = ACT_NONE,
          col_scale=None, col_shift=None, col_scale2=None, aux=None, resid=None, row_map=None,
          out_f32=None, out_f16=None, col_sum=None, col_sumsq=None, alpha_ptr=None, row_scale=None,
-         out_pre16=None) -> None:
+         out_pre16=None, out_colsum=None, out_colsum_alpha=None, aux_scale=None,
+         aux_shift=None) -> None:
     """Thin functional wrapper over fvit_gemm for 2-D (strided) torch tensors.
 
     K-major operands are [rows, K] tensors, MN-major operands are [K, rows] tensors; only the row
@@ -208,6 +212,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
     g.alpha_ptr, g.row_scale = ptr(alpha_ptr), ptr(row_scale)
     if out_pre16 is not None:
         g.out_pre16, g.ld_out_pre16 = out_pre16.data_ptr(), out_pre16.stride(0)
+    g.out_colsum, g.out_colsum_alpha = ptr(out_colsum), ptr(out_colsum_alpha)
+    g.aux_scale, g.aux_shift = ptr(aux_scale), ptr(aux_shift)
     check(lib.fvit_gemm(C.byref(g), stream_ptr()))
 
 

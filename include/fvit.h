@@ -110,6 +110,11 @@ typedef struct fvit_gemm_args {
   void* out_pre16;        /* fp16 [m, n] (indexed by m): value after scale/shift, before act / col_scale2 /
                              row_scale / resid (pre-GELU activations; un-scaled branch outputs) */
   int64_t ld_out_pre16;
+  float* out_colsum;      /* optional fp32 [n]: += *out_colsum_alpha * sum over rows of the rounded out_f16 values
+                             (dgrad GEMM producing dZ of the previous Linear -> that Linear's bias gradient) */
+  const float* out_colsum_alpha; /* device scalar, NULL = 1 */
+  const float* aux_scale; /* optional fp32 [n] pair: the *_BWD activations see aux * aux_scale + aux_shift (aux = saved raw */
+  const float* aux_shift; /* convolution output, scale/shift = that BatchNorm's batch-statistics affine) */
 } fvit_gemm_args;
 
 int fvit_gemm(const fvit_gemm_args* args, void* stream);
@@ -254,6 +259,13 @@ int fvit_cast_scale_f16(const float* x, int64_t ldx, const int32_t* rows, int32_
 int fvit_colsum(const void* a, int32_t a_is_f16, int64_t lda, const int32_t* a_rows, const void* b16, int64_t ldb,
                 int32_t nrows, int32_t C, const float* colmul, const float* scalar, float* out, const float* row_scale,
                 void* stream);
+/* Entry of a residual-branch backward x += gamma * f(LN(x)) (fv.py:637-655) in one pass over the fp32 gradient
+ * g [rows, C]: dz16 = half(g * colmul * *scalar * row_scale) (operand of the branch's last Linear), dbias[c] +=
+ * *bias_alpha * sum_r dz16 (its bias gradient), dgamma[c] += *gamma_alpha * sum_r g * u16 * row_scale (layer-scale
+ * gradient; u16 = saved branch output). dbias / u16+dgamma optional. Needs C % 8 == 0. */
+int fvit_branch_grad(const float* g, int64_t ldg, int32_t rows, int32_t C, const float* colmul, const float* scalar,
+                     const float* row_scale, void* dz16, int64_t lddz, const float* bias_alpha, float* dbias,
+                     const void* u16, int64_t ldu, const float* gamma_alpha, float* dgamma, void* stream);
 /* out[t - skip][c] += *scalar * sum_w a[w*group + t][c], skip <= t < group: gradient of a positional
  * embedding broadcast-added to every window (fv.py:366). */
 int fvit_group_sum(const float* a, int64_t lda, int32_t ngroups, int32_t group, int32_t skip, int32_t C,

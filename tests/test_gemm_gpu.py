@@ -255,3 +255,26 @@ def test_gemm_gelu_bwd_epilogue():
     torch.nn.functional.gelu(p).sum().backward()
     ref = (a.float() @ b.float().t()) * p.grad
     assert _rel(o16, ref) < 1e-3
+
+
+@pytest.mark.parametrize("m,n", [(512, 256), (1000, 3136), (130, 200)])
+def test_gemm_output_column_sums(m, n):
+    """out_colsum: per-column sum of the rounded fp16 output, scaled by a device scalar (bias gradient of the
+    previous Linear taken in the epilogue of the dgrad GEMM)."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    k = 192
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = (torch.randn(k, n, device="cuda", generator=g) * 0.1).half()   # MN-major B like a dgrad weight
+    pre = torch.randn(m, n, device="cuda", generator=g).half()
+    o16 = torch.zeros(m, n, device="cuda").half()
+    alpha = torch.full((1,), 0.5, device="cuda")
+    osum = torch.ones(n, device="cuda")        # accumulates on top of existing content
+    one = torch.ones(1, device="cuda")
+    lib.gemm(a, b, b_mn=True, act=lib.ACT_GELU_BWD, aux=pre, alpha_ptr=one, out_f16=o16, out_colsum=osum,
+             out_colsum_alpha=alpha)
+    ref = 1.0 + 0.5 * o16.float().sum(0)
+    assert (osum - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    p = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p).sum().backward()
+    assert _rel(o16, (a.float() @ b.float()) * p.grad) < 1e-3
