@@ -226,10 +226,23 @@ class TrainPlan(Plan):
     def profile(self, x: torch.Tensor) -> list[dict]:
         """Per-launch CUDA-event timing of one training step (forward list, then backward list with the
         gradient of sum(logits)/B as a stand-in loss gradient)."""
+        def timed(name, fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(2e8))
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return dict(name=name, ms=e0.elapsed_time(e1), flops=0.0, phase="step")
+
         for t in self.fwd_zero:
             t.zero_()
-        self.run_ops(self.prep_ops, None)
-        out = []
+        # per-step work around the two launch lists: weight re-packing (parameters change every optimizer step),
+        # accumulator clears, the copy that hands the flat gradient buffer to autograd
+        out = [timed("prep: repack weights to fp16 operands", lambda: self.run_ops(self.prep_ops, None)),
+               timed("backward prologue: clear gradient buffers", lambda: self.run_ops(self._bwd_prologue, None)),
+               timed("gradient hand-off copy", lambda: self.grad_views())]
         for ops, flops, tag in ((self.ops, self.op_flops, ""), (self.bwd_ops, self.bwd_flops, "")):
             if ops is self.bwd_ops:
                 self._bwd_start(torch.full_like(self._dlogits, 1.0 / self.B))
