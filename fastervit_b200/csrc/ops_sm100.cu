@@ -95,6 +95,74 @@ __global__ void cast_headpad_kernel(const float* __restrict__ src, long long lds
     dst[r * ldd + c] = __float2half_rn(ok ? src[sr * lds + sc] : 0.f);
   }
 }
+
+// 8 elements per thread (two 16-byte loads, one 16-byte store) for the common aligned case
+__global__ void __launch_bounds__(256)
+cast_pad_vec8_kernel(const float* __restrict__ src, long long lds, __half* __restrict__ dst, long long ldd, int rows,
+                     int cols, int cols_pad) {
+  const unsigned nv = (unsigned)cols_pad >> 3;
+  const unsigned total = (unsigned)rows * nv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / nv, c = (i - r * nv) << 3;
+    float v[8];
+    if (c + 8 <= (unsigned)cols) {
+      const float4 a = *reinterpret_cast<const float4*>(src + (long long)r * lds + c);
+      const float4 b = *reinterpret_cast<const float4*>(src + (long long)r * lds + c + 4);
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c + k < (unsigned)cols ? src[(long long)r * lds + c + k] : 0.f;
+    }
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+      ow[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)r * ldd + c) = o;
+  }
+}
+__global__ void __launch_bounds__(256)
+cast_headpad_vec8_kernel(const float* __restrict__ src, long long lds, __half* __restrict__ dst, long long ldd,
+                         int rows_dst, int cols_dst, int hd, int hdp, int pad_rows, int pad_cols) {
+  const unsigned nv = (unsigned)cols_dst >> 3;
+  const unsigned total = (unsigned)rows_dst * nv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / nv, c = (i - r * nv) << 3;
+    bool row_ok = true;
+    unsigned sr = r;
+    if (pad_rows) {
+      const unsigned d = r % (unsigned)hdp;
+      row_ok = d < (unsigned)hd;
+      sr = (r / (unsigned)hdp) * hd + d;
+    }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (row_ok) {
+      if (!pad_cols) {
+        const float4 a = *reinterpret_cast<const float4*>(src + (long long)sr * lds + c);
+        const float4 b = *reinterpret_cast<const float4*>(src + (long long)sr * lds + c + 4);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+      } else {
+        // 8 destination columns lie inside one padded head (hdp % 8 == 0): d .. d+7 of head c / hdp
+        const unsigned d0 = c % (unsigned)hdp, sc0 = (c / (unsigned)hdp) * hd + d0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (d0 + k < (unsigned)hd) v[k] = src[(long long)sr * lds + sc0 + k];
+      }
+    }
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+      ow[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)r * ldd + c) = o;
+  }
+}
 __global__ void vec_headpad_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_dst, int hd,
                                    int hdp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,8 +665,14 @@ int fvit_cast_pad_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int
   FVIT_CHECK(src && dst && rows > 0 && cols > 0 && cols_pad >= cols && ldd >= cols_pad,
              "fvit_cast_pad_f16: bad arguments");
   const long long total = (long long)rows * cols_pad;
-  cast_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, lds, (__half*)dst, ldd, rows, cols, cols_pad);
+  const bool vec = cols_pad % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0 && cols % 4 == 0 && total / 8 < (1LL << 31) &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (vec)
+    cast_pad_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (__half*)dst, ldd, rows,
+                                                                                     cols, cols_pad);
+  else
+    cast_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (__half*)dst, ldd, rows, cols,
+                                                                            cols_pad);
   return post_launch("cast_pad_kernel");
 }
 
@@ -608,8 +682,15 @@ int fvit_cast_headpad_f16(const float* src, int64_t lds, void* dst, int64_t ldd,
   FVIT_CHECK(src && dst && rows_dst > 0 && cols_dst > 0 && hd > 0 && hdp >= hd && ldd >= cols_dst,
              "fvit_cast_headpad_f16: bad arguments");
   const long long total = (long long)rows_dst * cols_dst;
-  cast_headpad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, lds, (__half*)dst, ldd, rows_dst, cols_dst, hd, hdp, pad_rows, pad_cols);
+  const bool vec = cols_dst % 8 == 0 && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+                   total / 8 < (1LL << 31) &&
+                   (pad_cols ? hdp % 8 == 0 : (lds % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0));
+  if (vec)
+    cast_headpad_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, lds, (__half*)dst, ldd, rows_dst, cols_dst, hd, hdp, pad_rows, pad_cols);
+  else
+    cast_headpad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, lds, (__half*)dst, ldd, rows_dst, cols_dst, hd, hdp, pad_rows, pad_cols);
   return post_launch("cast_headpad_kernel");
 }
 

@@ -1066,13 +1066,13 @@ __global__ void token_init_bwd_kernel(const float* __restrict__ g, long long ldg
                                       const int* __restrict__ ct_row_map, int B, int Hp, int Wp, int C,
                                       const float* __restrict__ w, int kh, int kw, int sh, int sw, int oh, int ow,
                                       float* __restrict__ gx, long long ldgx) {
-  const long long total = (long long)B * Hp * Wp * C;
+  // blockIdx.x / threadIdx.x walk channels, blockIdx.y walks pixels: 32-bit index math only
   const float inv = 1.f / (float)(kh * kw);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long pos = i / C;
-    const int x = (int)(pos % Wp), y = (int)((pos / Wp) % Hp), b = (int)(pos / ((long long)Wp * Hp));
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int npos = B * Hp * Wp;
+  for (int pos = blockIdx.y; pos < npos; pos += gridDim.y) {
+    const int x = pos % Wp, y = (pos / Wp) % Hp, b = pos / (Wp * Hp);
     const int row = pix_map[pos];
     if (row < 0) continue;
     float acc = 0.f;
@@ -1511,9 +1511,11 @@ int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ld
                                                                 sh, sw, oh, ow, scalar, dw, dbias);
   int rc = post_launch("token_init_wgrad_kernel");
   if (rc) return rc;
-  const long long total = (long long)B * Hp * Wp * C;
-  token_init_bwd_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(g, ldg, pix_map, ct_row_map, B, Hp, Wp,
-                                                                                   C, w, kh, kw, sh, sw, oh, ow, gx, ldgx);
+  const int cb = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  const long long npos = (long long)B * Hp * Wp;
+  dim3 gd((unsigned)((C + cb - 1) / cb), (unsigned)(npos < 65535 ? npos : 65535));
+  token_init_bwd_kernel<<<gd, cb, 0, (cudaStream_t)stream>>>(g, ldg, pix_map, ct_row_map, B, Hp, Wp, C, w, kh, kw, sh, sw,
+                                                             oh, ow, gx, ldgx);
   return post_launch("token_init_bwd_kernel");
 }
 
