@@ -536,6 +536,44 @@ __global__ void cpb_mlp_kernel(const float* __restrict__ coords, int P, const fl
   }
 }
 
+// Wide-output variant (D >= 64: the additive token embeddings, D = C up to 1568 with only P = 16..169 points).
+// One warp per output channel d keeps its w1 row in registers (16 values per lane, j = lane + 32 i) next to the
+// matching w0 / b0 entries, re-derives the hidden activations of every point on the fly (3 instructions each)
+// and reduces over the lanes; w1 is read exactly once overall instead of once per point. The summation order
+// (lane-strided partial sums, then the xor tree) and the hidden formula are those of cpb_mlp_kernel, so the two
+// variants agree bit for bit.
+__global__ void __launch_bounds__(256)
+cpb_mlp_wide_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w0,
+                    const float* __restrict__ b0, const float* __restrict__ w1, int D,
+                    float* __restrict__ out, float* __restrict__ hidden_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (hidden_out) {  // saved for the backward pass: grid-strided so every CTA writes a slice
+    const int total = P * 512;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int p = i >> 9, j = i & 511;
+      hidden_out[i] = fmaxf(fmaf(__ldg(w0 + 2 * j), __ldg(coords + 2 * p),
+                                 fmaf(__ldg(w0 + 2 * j + 1), __ldg(coords + 2 * p + 1), __ldg(b0 + j))), 0.f);
+    }
+  }
+  const int d = blockIdx.x * 8 + warp;
+  if (d >= D) return;
+  float wa[16], wb[16], bb[16], w1r[16];
+  const float* wr = w1 + (long long)d * 512;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int j = lane + 32 * i;
+    wa[i] = __ldg(w0 + 2 * j), wb[i] = __ldg(w0 + 2 * j + 1), bb[i] = __ldg(b0 + j), w1r[i] = __ldg(wr + j);
+  }
+  for (int p = 0; p < P; ++p) {
+    const float c0 = __ldg(coords + 2 * p), c1 = __ldg(coords + 2 * p + 1);
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a = fmaf(fmaxf(fmaf(wa[i], c0, fmaf(wb[i], c1, bb[i])), 0.f), w1r[i], a);
+    a = warp_sum(a);
+    if (lane == 0) out[(long long)p * D + d] = a;
+  }
+}
+
 // bias[h][r][c] = (r >= ng && c >= ng) ? 16*sigmoid(table[index[(r-ng)*L + (c-ng)]][h]) : 0
 // with L = ws*ws local tokens and ng = S - L carrier tokens on the top/left (fv.py:276-299).
 __global__ void attn_bias_kernel(const float* __restrict__ table, const long long* __restrict__ index,
@@ -824,6 +862,10 @@ int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, 
 int fvit_cpb_mlp_fwd(const float* coords, int32_t P, const float* w0, const float* b0, const float* w1,
                      int32_t D, float* out, float* hidden_out, void* stream) {
   FVIT_CHECK(coords && w0 && b0 && w1 && out && P > 0 && D > 0, "fvit_cpb_mlp_fwd: bad arguments");
+  if (D >= 64) {  // token embeddings: few points, many channels -> parallelise over channels
+    cpb_mlp_wide_kernel<<<(D + 7) / 8, 256, 0, (cudaStream_t)stream>>>(coords, P, w0, b0, w1, D, out, hidden_out);
+    return post_launch("cpb_mlp_wide_kernel");
+  }
   cpb_mlp_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(coords, P, w0, b0, w1, D, out, hidden_out);
   return post_launch("cpb_mlp_kernel");
 }

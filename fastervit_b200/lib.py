@@ -82,7 +82,7 @@ def _bind_ops(lib) -> None:
         fn.restype = C.c_int
 
 
-_P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_P, _I, _L, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _OP_SIGS: dict[str, list] = {
     "fvit_cast_pad_f16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "fvit_pack_conv3x3_f16": [_P, _P, _I, _I, _I, _I, _P],
@@ -122,6 +122,14 @@ _OP_SIGS: dict[str, list] = {
     "fvit_token_init_fwd": [_P, _L, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
     "fvit_propagate_fwd": [_P, _L, _P, _I, _I, _P, _P],
     "fvit_pool_affine_fwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _L, _P],
+    # optimizer step (include/fvit.h "optimizer step on the flat gradient buffer")
+    "fvit_optim_gather_f32": [_P, _I, _P, _P, _P, _P],
+    "fvit_optim_sqnorm": [_P, _I, _P, _P, _P, _P],
+    "fvit_optim_prepare": [_P, _I, _P, _P, _F, _F, _D, _D, _P, _P],
+    "fvit_optim_adamw": [_P, _I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _F, _P],
+    "fvit_optim_lamb_stage1": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P],
+    "fvit_optim_lamb_stage2": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P],
+    "fvit_optim_ema": [_P, _I, _P, _P, _F, _P],
 }
 
 

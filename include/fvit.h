@@ -329,6 +329,50 @@ int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ld
 int fvit_propagate_bwd(float* g, int64_t ldg, const float* xs, int64_t ldx, const int32_t* src_map, int32_t rows, int32_t C,
                        const float* gamma, const float* scalar, float* dgamma, void* stream);
 
+/* ---- optimizer step on the flat gradient buffer (train.py:879-899) -----------------------
+ * Replaces, for the training loop either side of loss.backward(): GradScaler.unscale_ + the non-finite check,
+ * dispatch_clip_grad(..., mode='norm') (`--clip-grad 5.0`), optimizer.step() for `--opt adamw` / `--opt lamb`
+ * (TRAINING.md:28,105) and ModelEmaV2.update (train.py:898-899).
+ *
+ * Every parameter is a segment s: gradients and moments live in flat fp32 buffers at element offset seg_off[s]
+ * (the layout the backward pass produces), parameters / EMA copies are addressed through per-segment device
+ * pointer tables (seg_p / seg_ema: int64 addresses). `chunks` is a device int32 [nchunks][4] table
+ * {segment, first element within the segment, element count (<= 2^31), 0}; one CTA per chunk. seg_hp is fp32
+ * [nseg][2] = {lr, weight_decay}. scal is a persistent device fp32 [8] block: [0] gradient norm, [1] skip flag
+ * (non-finite gradients), [2] gradient multiplier (unscale * clip), [3] steps taken, [4] 1-beta1^t, [5] 1-beta2^t. */
+/* flat[seg_off[s] + i] = ((float*)seg_src[s])[i]: gathers per-tensor gradients that are not already flat. */
+int fvit_optim_gather_f32(const int32_t* chunks, int32_t nchunks, const int64_t* seg_src, const int64_t* seg_off,
+                          float* flat, void* stream);
+/* partials[2c] = sum of squares of chunk c of g, partials[2c+1] = count of non-finite values. */
+int fvit_optim_sqnorm(const int32_t* chunks, int32_t nchunks, const int64_t* seg_off, const float* g, float* partials,
+                      void* stream);
+/* Reduces the partials (nchunks may be 0: no norm) and updates scal: norm = sqrt(sum)/ *grad_scale; skip if any
+ * non-finite or *found_inf != 0; multiplier = (1 / *grad_scale) * min(1, max_norm / (norm + clip_eps)) (max_norm <= 0:
+ * no clipping; clip_eps = 1e-6 is torch.nn.utils.clip_grad_norm_, 0 is timm Lamb's max_grad_norm); the step
+ * counter and bias corrections advance unless skipped. grad_scale / found_inf: optional device scalars
+ * (torch.amp.GradScaler's). */
+int fvit_optim_prepare(const float* partials, int32_t nchunks, const float* grad_scale, const float* found_inf,
+                       float max_norm, float clip_eps, double beta1, double beta2, float* scal, void* stream);
+/* torch.optim.AdamW step (decoupled weight decay, bias correction); seg_ema != NULL additionally applies
+ * ema = ema_decay * ema + (1 - ema_decay) * p_new in the same pass. */
+int fvit_optim_adamw(const int32_t* chunks, int32_t nchunks, const int64_t* seg_p, const int64_t* seg_off,
+                     const float* seg_hp, const float* g, float* m, float* v, float beta1, float beta2, float eps,
+                     const float* scal, const int64_t* seg_ema, float ema_decay, void* stream);
+/* timm.optim.Lamb step in two passes: stage 1 updates the moments, writes the un-trusted update u (own flat
+ * buffer) and accumulates per-segment sum p^2 / sum u^2 into seg_norms [nseg][2] (zeroed by the caller);
+ * stage 2 applies p -= lr * trust * u with trust = ||p||/||u|| (segments with weight decay, or all with
+ * always_adapt; min(trust, 1) with trust_clip) and the optional fused EMA. */
+int fvit_optim_lamb_stage1(const int32_t* chunks, int32_t nchunks, const int64_t* seg_p, const int64_t* seg_off,
+                           const float* seg_hp, const float* g, float* u, float* m, float* v, float beta1,
+                           float beta2, float eps, const float* scal, float* seg_norms, void* stream);
+int fvit_optim_lamb_stage2(const int32_t* chunks, int32_t nchunks, const int64_t* seg_p, const int64_t* seg_off,
+                           const float* seg_hp, const float* u, const float* seg_norms, int32_t trust_clip,
+                           int32_t always_adapt, const float* scal, const int64_t* seg_ema, float ema_decay,
+                           void* stream);
+/* ModelEmaV2.update: ((float*)seg_ema[s])[i] = decay * ema + (1 - decay) * ((float*)seg_src[s])[i]. */
+int fvit_optim_ema(const int32_t* chunks, int32_t nchunks, const int64_t* seg_ema, const int64_t* seg_src, float decay,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
