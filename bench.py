@@ -154,6 +154,56 @@ def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float =
                 ms_per_step=1e3 * dt / n, steps_done=n, batch=bs)
 
 
+def optimizer_leg(model, x, targets, pk) -> dict:
+    """Time the fused optimizer step that follows backward in the reference loop (train.py:879-899): clip-grad-norm
+    + LAMB (fv4-6) or AdamW (fv0-3) + ModelEmaV2, on the gradients of one real backward pass, CUDA events over
+    10 steps after 3 warm-ups. Algorithmic bytes per parameter: sqnorm 4 + AdamW 28 (+8 fused EMA) or LAMB 40
+    (+8); compared with the measured HBM peak."""
+    from fastervit_b200 import optim as FO
+    from fastervit_b200 import lib as L
+    n_params = sum(p.numel() for p in model.parameters())
+    use_lamb = n_params > 100e6   # TRAINING.md: `--opt lamb` for FasterViT-4/5/6, `--opt adamw` below
+    out = {}
+    for fused_ema in (True, False):
+        opt = (FO.FusedLamb(model, lr=5e-3, weight_decay=0.12, max_grad_norm=1.0) if use_lamb
+               else FO.FusedAdamW(model, lr=5e-4, weight_decay=0.05, max_grad_norm=5.0))
+        ema = FO.FlatEma(model, decay=0.9998)
+        if fused_ema:
+            opt.attach_ema(ema, model)
+        loss = torch.nn.functional.cross_entropy(model(x), targets)
+        loss.backward()
+
+        def one():
+            opt.step()
+            ema.update(model)
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        L.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        torch.cuda._sleep(int(3e8))   # ~150 ms spin: the 10 steps are enqueued behind it, so e0..e1 is device time
+        e0.record()
+        for _ in range(10):
+            one()
+        e1.record()
+        host_ms = (time.perf_counter() - t0) * 1e3 / 10   # host enqueue cost per step (step() + ema.update())
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        bytes_per = 4 + (40 if use_lamb else 28) + (8 if fused_ema else 12)
+        gbs = n_params * bytes_per / (ms / 1e3) / 1e9
+        out["fused_ema" if fused_ema else "separate_ema"] = {
+            "ms": round(ms, 4), "host_enqueue_ms": round(host_ms, 4), "launches": L.launch_count() / 10,
+            "alg_bytes_per_param": bytes_per,
+            "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / pk["hbm"], 4),
+            "zero_copy_grads": opt._lay["gstage"] is None}
+        model.zero_grad(set_to_none=True)
+        del opt, ema
+    return {"what": ("clip-grad-norm + " + ("LAMB" if use_lamb else "AdamW") + " + ModelEmaV2 update on the flat "
+                     "gradient buffer (train.py:879-899), after the timed fwd+bwd steps; not part of `value`"),
+            "params": n_params, "bound": "hbm", "peak_gbs": pk["hbm"], **out}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -357,6 +407,15 @@ def main() -> None:
         if args.profile_out:
             Path(args.profile_out).write_text(json.dumps({"per_kernel": prof_table, "launches": prof}, indent=1))
 
+    # ------------------------------------------------------------------ optimizer step, reported
+    # beside the metric (the BASELINE metric is fwd+bwd; the optimizer is NOT inside `value` / `e2e`)
+    opt_info = None
+    if rank == 0 and mode == "train" and world == 1:   # (with N > 1 a lone backward would wait on the all-reduce)
+        try:
+            opt_info = optimizer_leg(model, xs[0], targets, pk)
+        except Exception as exc:  # the headline line must survive a failure of this side measurement
+            opt_info = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1)
     cpu = None
     if rank == 0 and world == 1:
@@ -371,7 +430,8 @@ def main() -> None:
                 "dtype": "fp16 operands, fp32 accumulate / residual / statistics", "data": "synthetic",
                 "config": config, "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "per_kernel": prof_table, "grad_sync_check": grad_sync,
+                "cpu_baseline": cpu, "optimizer_step": opt_info, "per_kernel": prof_table,
+                "grad_sync_check": grad_sync,
                 "model_tflops": round(value * alg / 1e12, 2),
                 "model_frac_of_tensor_peak": round(value / world * alg / 1e12 / pk["tensor"], 4)}
         print(json.dumps(line))

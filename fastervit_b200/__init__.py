@@ -6,5 +6,7 @@
 """
 from .registry import create_model, list_models, is_model, model_entrypoint, load_checkpoint  # noqa: F401
 from .model import FasterViT  # noqa: F401
+from .optim import FusedAdamW, FusedLamb, FlatEma, param_groups_weight_decay  # noqa: F401
 
-__all__ = ["create_model", "list_models", "is_model", "model_entrypoint", "load_checkpoint", "FasterViT"]
+__all__ = ["create_model", "list_models", "is_model", "model_entrypoint", "load_checkpoint", "FasterViT",
+           "FusedAdamW", "FusedLamb", "FlatEma", "param_groups_weight_decay"]

@@ -509,6 +509,100 @@ __global__ void attn_core_simt_kernel(const __half* __restrict__ qkv, long long 
   }
 }
 
+// Streaming variant for windows whose score matrix does not fit in shared memory (the 21k fine-tuned
+// FasterViT-4 models: window 14 / 24 / 32 / 48 -> S = 196 .. 2304, fv.py:1253-1418): one CTA per (64-query
+// tile, group, head) walks the keys in tiles of 64 with the running max / running sum recurrence
+//   m' = max(m, rowmax(s)) ; l' = l e^(m-m') + sum e^(s-m') ; O' = O e^(m-m') + e^(s-m') V ,
+// so only a 64 x 64 score tile is ever resident. Same operand layout and fp32 math as attn_core_simt_kernel.
+constexpr int ATT_QT = 64, ATT_KT = 64;
+__global__ void __launch_bounds__(256)
+attn_stream_simt_kernel(const __half* __restrict__ qkv, long long ldq, int S, int hd, int heads, int C,
+                        const float* __restrict__ bias, float scale, __half* __restrict__ out, long long ldo) {
+  extern __shared__ float sm[];
+  const int hdp = hd + 1;
+  float* sq = sm;                          // [QT][hd+1]  (pre-scaled queries)
+  float* sk = sq + ATT_QT * hdp;           // [KT][hd+1]
+  float* sv = sk + ATT_KT * hdp;           // [KT][hd+1]
+  float* so = sv + ATT_KT * hdp;           // [QT][hd+1]  running output
+  float* ss = so + ATT_QT * hdp;           // [QT][KT+1]  scores -> un-normalised probabilities
+  float* sm_ = ss + ATT_QT * (ATT_KT + 1); // [QT] running max
+  float* sl = sm_ + ATT_QT;                // [QT] running sum
+  float* sa = sl + ATT_QT;                 // [QT] rescale factor of this step
+  const int g = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int q0 = blockIdx.x * ATT_QT;
+  const long long row0 = (long long)g * S;
+  const int nq = min(ATT_QT, S - q0);
+  for (int i = threadIdx.x; i < ATT_QT * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    sq[t * hdp + d] = t < nq ? __half2float(qkv[(row0 + q0 + t) * ldq + h * hd + d]) * scale : 0.f;
+    so[t * hdp + d] = 0.f;
+  }
+  for (int i = threadIdx.x; i < ATT_QT; i += blockDim.x) {
+    sm_[i] = -INFINITY;
+    sl[i] = 0.f;
+  }
+  const float* bh = bias ? bias + (long long)h * S * S : nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int k0 = 0; k0 < S; k0 += ATT_KT) {
+    const int nk = min(ATT_KT, S - k0);
+    __syncthreads();  // previous tile fully consumed (and the prologue stores are visible)
+    for (int i = threadIdx.x; i < ATT_KT * hd; i += blockDim.x) {
+      const int t = i / hd, d = i % hd;
+      float kv = 0.f, vv = 0.f;
+      if (t < nk) {
+        const __half* base = qkv + (row0 + k0 + t) * ldq + h * hd + d;
+        kv = __half2float(base[C]);
+        vv = __half2float(base[2 * C]);
+      }
+      sk[t * hdp + d] = kv;
+      sv[t * hdp + d] = vv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ATT_QT * ATT_KT; i += blockDim.x) {
+      const int r = i / ATT_KT, c = i % ATT_KT;
+      float a = -INFINITY;
+      if (r < nq && c < nk) {
+        a = 0.f;
+        for (int d = 0; d < hd; ++d) a = fmaf(sq[r * hdp + d], sk[c * hdp + d], a);
+        if (bh) a += bh[(long long)(q0 + r) * S + k0 + c];
+      }
+      ss[r * (ATT_KT + 1) + c] = a;
+    }
+    __syncthreads();
+    for (int r = warp; r < nq; r += nwarps) {
+      float* pr = ss + r * (ATT_KT + 1);
+      float m = fmaxf(pr[lane], pr[lane + 32]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float m_old = sm_[r];
+      const float m_new = fmaxf(m_old, m);   // finite: every key tile holds at least one valid key
+      const float e0 = __expf(pr[lane] - m_new), e1 = __expf(pr[lane + 32] - m_new);  // exp(-inf) = 0 for masked keys
+      pr[lane] = e0;
+      pr[lane + 32] = e1;
+      const float sum = warp_sum(e0 + e1);
+      if (lane == 0) {
+        const float alpha = __expf(m_old - m_new);  // 0 on the first tile (m_old = -inf)
+        sa[r] = alpha;
+        sl[r] = sl[r] * alpha + sum;
+        sm_[r] = m_new;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq * hd; i += blockDim.x) {
+      const int r = i / hd, d = i % hd;
+      const float* pr = ss + r * (ATT_KT + 1);
+      float a = so[r * hdp + d] * sa[r];
+      for (int c = 0; c < nk; ++c) a = fmaf(pr[c], sv[c * hdp + d], a);
+      so[r * hdp + d] = a;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nq * hd; i += blockDim.x) {
+    const int r = i / hd, d = i % hd;
+    out[(row0 + q0 + r) * ldo + h * hd + d] = __float2half_rn(so[r * hdp + d] / sl[r]);
+  }
+}
+
 // ------------------------------------------------------------------------------ positional MLPs
 // out[p][d] = sum_j relu(w0[j][0]*c[p][0] + w0[j][1]*c[p][1] + b0[j]) * w1[d][j]   (hidden = 512)
 // (cpb_mlp of PosEmbMLPSwinv1D / PosEmbMLPSwinv2D, fv.py:223-225, 322-324). One CTA per point p;
@@ -845,8 +939,24 @@ int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, 
              "fvit_attn_core_fwd: bad arguments");
   const int C = heads * head_dim;
   const size_t smem = ((size_t)3 * S * (head_dim + 1) + (size_t)S * (S + 1)) * sizeof(float);
-  FVIT_CHECK(smem <= 227 * 1024, "fvit_attn_core_fwd: S=%d head_dim=%d needs %zu B of shared memory", S,
-             head_dim, smem);
+  if (smem > 227 * 1024) {  // large windows (21k models): stream the keys, 64 x 64 score tiles
+    FVIT_CHECK(probs_out == nullptr, "fvit_attn_core_fwd: probs_out is not available for S=%d (streaming kernel)", S);
+    const size_t sm2 = ((size_t)(2 * ATT_QT + 2 * ATT_KT) * (head_dim + 1) + (size_t)ATT_QT * (ATT_KT + 1) +
+                        3 * ATT_QT) * sizeof(float);
+    FVIT_CHECK(sm2 <= 227 * 1024, "fvit_attn_core_fwd: head_dim=%d needs %zu B of shared memory", head_dim, sm2);
+    FVIT_CHECK((long long)groups * heads <= 65535, "fvit_attn_core_fwd: groups*heads=%lld exceeds the grid limit",
+               (long long)groups * heads);
+    static bool stream_configured = false;
+    if (!stream_configured) {
+      FVIT_CUDA(cudaFuncSetAttribute(attn_stream_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+      stream_configured = true;
+    }
+    attn_stream_simt_kernel<<<dim3((unsigned)((S + ATT_QT - 1) / ATT_QT), (unsigned)(groups * heads)), 256, sm2,
+                              (cudaStream_t)stream>>>((const __half*)qkv, ldq, S, head_dim, heads, C, bias, scale,
+                                                      (__half*)out, ldo);
+    return post_launch("attn_stream_simt_kernel");
+  }
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     FVIT_CUDA(cudaFuncSetAttribute(attn_core_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

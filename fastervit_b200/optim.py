@@ -381,7 +381,10 @@ class FusedLamb(_FlatOptimizer):
 class FlatEma(nn.Module):
     """timm.utils.ModelEmaV2 (train.py:519-523, 898-899) with the update as one launch: `.module` is a deep copy of
     the model in eval mode; `update(model)` applies ema = decay * ema + (1 - decay) * model to every floating entry of
-    the state_dict (integer buffers follow ModelEmaV2's arithmetic through a cast)."""
+    the state_dict (integer buffers follow ModelEmaV2's float arithmetic and cast back, as `copy_` does there).
+
+    Host cost per update is a pointer sweep over the state (~1 k data_ptr() calls): the (owner module, attribute)
+    slots are resolved once per model, and the device tables are reused while no tensor was re-allocated."""
 
     def __init__(self, model: nn.Module, decay: float = 0.9999, device=None):
         super().__init__()
@@ -391,42 +394,45 @@ class FlatEma(nn.Module):
         self.device = device
         if device is not None:
             self.module.to(device=device)
-        self._tables = {}
+        self._slot_cache = None
         self._fused_into = None
         self._fused_steps = 0
 
-    def _pairs(self, model: nn.Module):
-        ev, mv = self.module.state_dict(), model.state_dict()
-        if list(ev.keys()) != list(mv.keys()):
+    # ---- state_dict entries as (owner module, attribute name) slots, resolved once per model ------------------
+    def _slots(self, model: nn.Module) -> dict:
+        c = self._slot_cache
+        if c is not None and c["model"] is model:
+            return c
+        ekeys, mkeys = list(self.module.state_dict().keys()), list(model.state_dict().keys())
+        if ekeys != mkeys:
             raise L.FvitError("FlatEma: the model's state_dict keys differ from the EMA copy's")
-        return [(ev[k], mv[k], k) for k in ev]
 
-    @torch.no_grad()
-    def _launch(self, slot: str, fl: list, decay: float) -> None:
-        if not fl:
-            return
-        dev = fl[0][0].device
-        key = (tuple(e.data_ptr() for e, _ in fl), tuple(m.data_ptr() for _, m in fl))
-        t = self._tables.get(slot)
-        if t is None or t["key"] != key:
-            tb = _DeviceTables([e.numel() for e, _ in fl], dev)
-            t = self._tables[slot] = dict(key=key, tb=tb, seg_e=tb.i64(key[0]), seg_m=tb.i64(key[1]))
-        with _device_guard(dev):
-            L.call("fvit_optim_ema", t["tb"].chunks.data_ptr(), t["tb"].nchunks, t["seg_e"].data_ptr(),
-                   t["seg_m"].data_ptr(), float(decay))
+        def owner(root: nn.Module, key: str):
+            path, _, name = key.rpartition(".")
+            return (root.get_submodule(path) if path else root), name
+        c = dict(model=model, keys=ekeys, e=[owner(self.module, k) for k in ekeys], m=[owner(model, k) for k in ekeys],
+                 pnames={n for n, _ in model.named_parameters()}, plans={})
+        self._slot_cache = c
+        return c
 
-    @torch.no_grad()
-    def _blend(self, model: nn.Module, decay: float, skip_params: bool) -> None:
-        pairs = self._pairs(model)
-        pnames = {n for n, _ in model.named_parameters()} if skip_params else set()
+    @staticmethod
+    def _read(slots) -> list[torch.Tensor]:
+        out = []
+        for mod, name in slots:
+            t = mod._parameters.get(name)
+            out.append(t if t is not None else mod._buffers[name])
+        return out
+
+    def _plan(self, c: dict, ev, mv, skip_params: bool) -> dict:
         # ModelEmaV2 walks state_dict().values(): a tensor registered under two names (the tokenizer's depthwise
         # conv, fv.py:727-731) is blended once per name. The first occurrences go into one launch; the repeats
         # follow in a second launch (same stream, so the order of the reference's loop is kept, without two CTAs
         # racing on one tensor). Parameters fused into the optimizer's kernel were already blended once there.
         seen: set[int] = set()
-        first, repeats = [], []
-        for e, m, k in pairs:
+        first, repeats, ints = [], [], []
+        for e, m, k in zip(ev, mv, c["keys"]):
             if not e.is_floating_point():
+                ints.append((e, m))
                 continue
             _require_cuda(e, "FlatEma")
             _require_cuda(m, "FlatEma")
@@ -437,13 +443,34 @@ class FlatEma(nn.Module):
                 repeats.append((e, m))
                 continue
             seen.add(e.data_ptr())
-            if k not in pnames:
+            if not (skip_params and k in c["pnames"]):
                 first.append((e, m))
-        self._launch("first", first, decay)
-        self._launch("repeats", repeats, decay)
-        for e, m, _ in pairs:   # num_batches_tracked & co.: ModelEmaV2's float arithmetic, cast back by copy_
-            if not e.is_floating_point():
-                e.copy_(decay * e + (1.0 - decay) * m)
+        launches = []
+        for fl in (first, repeats):
+            if fl:
+                tb = _DeviceTables([e.numel() for e, _ in fl], fl[0][0].device)
+                launches.append(dict(tb=tb, dev=fl[0][0].device, seg_e=tb.i64([e.data_ptr() for e, _ in fl]),
+                                     seg_m=tb.i64([m.data_ptr() for _, m in fl])))
+        return dict(launches=launches, ie=[e for e, _ in ints], im=[m for _, m in ints])
+
+    @torch.no_grad()
+    def _blend(self, model: nn.Module, decay: float, skip_params: bool) -> None:
+        c = self._slots(model)
+        ev, mv = self._read(c["e"]), self._read(c["m"])
+        key = (tuple(t.data_ptr() for t in ev), tuple(t.data_ptr() for t in mv), skip_params)
+        plan = c["plans"].get(key)
+        if plan is None:
+            if len(c["plans"]) >= 4:
+                c["plans"].clear()
+            plan = c["plans"][key] = self._plan(c, ev, mv, skip_params)
+        for t in plan["launches"]:
+            with _device_guard(t["dev"]):
+                L.call("fvit_optim_ema", t["tb"].chunks.data_ptr(), t["tb"].nchunks, t["seg_e"].data_ptr(),
+                       t["seg_m"].data_ptr(), float(decay))
+        if plan["ie"]:   # num_batches_tracked & co.: ModelEmaV2's float arithmetic, cast back to integers by copy_
+            acc = torch._foreach_mul(plan["ie"], decay)
+            torch._foreach_add_(acc, torch._foreach_mul(plan["im"], 1.0 - decay))
+            torch._foreach_copy_(plan["ie"], acc)
 
     def update(self, model: nn.Module) -> None:
         fused = self._fused_into is not None and self._fused_steps > 0

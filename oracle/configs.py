@@ -33,6 +33,11 @@ CASES = {
         dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 5, 6],
         ct_size=2, mlp_ratio=4, resolution=[240, 336], hat=[False, False, True, False],
         do_propagation=False, any_res=True)),
+    # 21k fine-tuned family reduced (fv.py:1253-1418): no carrier tokens anywhere (hat all False), layer scale,
+    # one 24 x 24 window at level 2 (S = 576: the streaming attention kernel) and 12 x 12 at level 3 (S = 144)
+    "tiny_21k": ("faster_vit_4_21k_384", dict(dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 24, 12],
+        ct_size=2, mlp_ratio=4, resolution=384, hat=[False, False, False, False], do_propagation=True)),
 }
 
 

@@ -21,7 +21,7 @@ def _setup(case):
     return g, model.cuda(), x.cuda()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "fv0", "fv4", "ar0"])
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_21k", "fv0", "fv4", "ar0"])
 def test_eval_logits_match_reference(case):
     g, model, x = _setup(case)
     with torch.no_grad():

@@ -78,8 +78,8 @@ def test_adamw_matches_oracle(flat):
     assert float(opt.state[ps[0]]["step"]) == 5.0
     for p, q, q0, m, v in zip(ps, p64, start, ms, vs):
         _close_update(p.detach(), q0, q, q0, steps=5)
-        torch.testing.assert_close(opt.state[p]["exp_avg"].double().cpu(), m, rtol=2e-5, atol=1e-9)
-        torch.testing.assert_close(opt.state[p]["exp_avg_sq"].double().cpu(), v, rtol=2e-5, atol=1e-12)
+        torch.testing.assert_close(opt.state[p]["exp_avg"].double().cpu(), m, rtol=2e-5, atol=5e-7)   # |g| ~ 1
+        torch.testing.assert_close(opt.state[p]["exp_avg_sq"].double().cpu(), v, rtol=2e-5, atol=1e-9)
 
 
 def test_adamw_matches_torch_cuda_adamw_with_external_clipping():

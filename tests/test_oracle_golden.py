@@ -36,7 +36,7 @@ def _sample(t, n=512):
     return f[::stride].float()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "fv0"])
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_21k", "fv0"])
 def test_oracle_eval_matches_reference_fp64(case):
     g = _load(case)
     sd = _state_dict(g, torch.float64)
