@@ -738,6 +738,80 @@ cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, const float* __restr
   atomicAdd(db0 + j, dh);
 }
 
+// Blocked variants of the two kernels above: the token-embedding MLPs have few points (P = 16 .. 169) and many
+// channels (D = C up to 1568), so the versions above re-read `hidden` once per channel and `w1` once per point
+// through L2 (80-160 MB per call). Here a CTA covers 8 channels (dW1) resp. all points (d hidden), and each
+// operand is read once.
+//   dw1[d][j] += sc * sum_p dout[p][d] * hid[p][j] for the 8 channels d0 .. d0+7 of the CTA; thread = hidden unit j
+__global__ void __launch_bounds__(512)
+cpb_mlp_bwd_w1x8_kernel(int P, const float* __restrict__ hidden, const float* __restrict__ dout, int D,
+                        const float* __restrict__ scalar, float* __restrict__ dw1) {
+  extern __shared__ float sdo8[];  // [8][P] dout columns of this CTA (scaled)
+  const int d0 = blockIdx.x * 8;
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  for (int i = threadIdx.x; i < 8 * P; i += blockDim.x) {
+    const int dd = i / P, pp = i - dd * P;
+    sdo8[i] = d0 + dd < D ? dout[(long long)pp * D + d0 + dd] * sc : 0.f;
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int pp = 0; pp < P; ++pp) {
+    const float hv = hidden[(long long)pp * 512 + j];
+#pragma unroll
+    for (int dd = 0; dd < 8; ++dd) acc[dd] = fmaf(sdo8[dd * P + pp], hv, acc[dd]);
+  }
+#pragma unroll
+  for (int dd = 0; dd < 8; ++dd)
+    if (d0 + dd < D) dw1[(long long)(d0 + dd) * 512 + j] += acc[dd];
+}
+//   dhid[p][j] = relu'(hid[p][j]) * sc * sum_d dout[p][d] w1[d][j] -> dw0[j][:] += dhid * coords[p][:], db0[j] += dhid.
+//   grid (4 chunks of 128 hidden units, splits of the channel range); a thread keeps the partial sums of up to 64
+//   points in registers while it streams its w1 column once; three atomics per thread at the end.
+constexpr int CPB_PB = 64, CPB_DC = 32;
+__global__ void __launch_bounds__(128)
+cpb_mlp_bwd_hid_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w1,
+                       const float* __restrict__ hidden, const float* __restrict__ dout, int D,
+                       const float* __restrict__ scalar, float* __restrict__ dw0, float* __restrict__ db0) {
+  __shared__ float sd[CPB_PB * CPB_DC];  // [point][channel of the current chunk]
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int d0 = (int)((long long)D * blockIdx.y / gridDim.y), d1 = (int)((long long)D * (blockIdx.y + 1) / gridDim.y);
+  const float sc = scalar ? __ldg(scalar) : 1.f;
+  float s0 = 0.f, s1 = 0.f, sb = 0.f;
+  for (int pb = 0; pb < P; pb += CPB_PB) {
+    const int np = min(CPB_PB, P - pb);
+    float acc[CPB_PB];
+#pragma unroll
+    for (int i = 0; i < CPB_PB; ++i) acc[i] = 0.f;
+    for (int dc = d0; dc < d1; dc += CPB_DC) {
+      const int nd = min(CPB_DC, d1 - dc);
+      __syncthreads();
+      for (int i = threadIdx.x; i < CPB_PB * CPB_DC; i += blockDim.x) {
+        const int pp = i / CPB_DC, dd = i - pp * CPB_DC;
+        sd[i] = (pp < np && dd < nd) ? dout[(long long)(pb + pp) * D + dc + dd] * sc : 0.f;
+      }
+      __syncthreads();
+      for (int dd = 0; dd < nd; ++dd) {
+        const float wv = w1[(long long)(dc + dd) * 512 + j];
+#pragma unroll
+        for (int pp = 0; pp < CPB_PB; ++pp) acc[pp] = fmaf(sd[pp * CPB_DC + dd], wv, acc[pp]);
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < CPB_PB; ++pp) {
+      if (pp < np && hidden[(long long)(pb + pp) * 512 + j] > 0.f) {
+        const float dh = acc[pp];
+        s0 = fmaf(dh, coords[2 * (pb + pp)], s0);
+        s1 = fmaf(dh, coords[2 * (pb + pp) + 1], s1);
+        sb += dh;
+      }
+    }
+  }
+  atomicAdd(dw0 + 2 * j, s0);
+  atomicAdd(dw0 + 2 * j + 1, s1);
+  atomicAdd(db0 + j, sb);
+}
+
 // Backward of the head: y[b,t,c] = xhat*w + beta with batch statistics, pooled[b,c] = mean_t y.
 // reduce: s1[c] = sum_b dp[b,c] ; s2[c] = sum_b dp[b,c]/T * sum_t xhat[b,t,c]   (dp = d pooled, scaled)
 __global__ void pool_bn_bwd_reduce_kernel(const float* __restrict__ xs, long long ldx, const int* __restrict__ rows,
@@ -1095,6 +1169,59 @@ __global__ void token_init_bwd_kernel(const float* __restrict__ g, long long ldg
     gx[(long long)row * ldgx + c] += acc;
   }
 }
+// Same result for maps that fit in shared memory (every 224-class model: 14 x 14 pixels, 4 x 4 carriers): one CTA
+// per (image, 32 channels) stages the carrier gradients, forms the average-pool backward d conv[pixel] once
+// (instead of once per tap: 36 gathers per element in the kernel above) and applies the 9-tap transpose of the
+// depthwise convolution out of shared memory. Thread = (channel lane, pixel lane): 128-byte row accesses.
+__global__ void __launch_bounds__(256)
+token_init_bwd_tile_kernel(const float* __restrict__ g, long long ldg, const int* __restrict__ pix_map,
+                           const int* __restrict__ ct_row_map, int Hp, int Wp, int C, const float* __restrict__ w,
+                           int kh, int kw, int sh, int sw, int oh, int ow, float* __restrict__ gx, long long ldgx) {
+  extern __shared__ float tsm[];
+  float* sg = tsm;                 // [oh*ow][32] carrier-row gradients of this image
+  float* sd = tsm + oh * ow * 32;  // [Hp*Wp][32] d loss / d conv output
+  const int b = blockIdx.y, cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const bool cok = c < C;
+  const int nout = oh * ow, npix = Hp * Wp;
+  for (int o = pl; o < nout; o += 8)
+    sg[o * 32 + cl] = cok ? g[(long long)ct_row_map[b * nout + o] * ldg + c] : 0.f;
+  __syncthreads();
+  const float inv = 1.f / (float)(kh * kw);
+  for (int p = pl; p < npix; p += 8) {
+    const int cy = p / Wp, cx = p - cy * Wp;
+    // pooled outputs covering conv pixel (cy, cx): y0*sh <= cy < y0*sh + kh
+    const int y0lo = cy - kh + sh >= 0 ? (cy - kh + sh) / sh : 0, y0hi = min(oh - 1, cy / sh);
+    const int x0lo = cx - kw + sw >= 0 ? (cx - kw + sw) / sw : 0, x0hi = min(ow - 1, cx / sw);
+    float a = 0.f;
+    for (int y0 = y0lo; y0 <= y0hi; ++y0)
+      for (int x0 = x0lo; x0 <= x0hi; ++x0) a += sg[(y0 * ow + x0) * 32 + cl];
+    sd[p * 32 + cl] = a * inv;
+  }
+  __syncthreads();
+  if (!cok) return;
+  float wl[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wl[t] = __ldg(w + c * 9 + t);
+  for (int p = pl; p < npix; p += 8) {
+    const int y = p / Wp, x = p - y * Wp;
+    const int row = pix_map[b * npix + p];
+    if (row < 0) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int cy = y - r + 1;
+      if (cy < 0 || cy >= Hp) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int cx = x - s2 + 1;
+        if (cx < 0 || cx >= Wp) continue;
+        acc = fmaf(wl[r * 3 + s2], sd[(cy * Wp + cx) * 32 + cl], acc);
+      }
+    }
+    gx[(long long)row * ldgx + c] += acc;
+  }
+}
 // dw[c][tap] += sc * sum_{b,y0,x0} gct * mean_pool x[.. + tap - 1] ; dbias[c] += sc * sum gct
 __global__ void token_init_wgrad_kernel(const float* __restrict__ g, long long ldg, const __half* __restrict__ xs,
                                         long long ldx, const int* __restrict__ pix_map,
@@ -1395,6 +1522,17 @@ int fvit_attn_bias_bwd(const float* dbias, const float* bias, const int64_t* ind
 int fvit_cpb_mlp_bwd(const float* coords, int32_t P, const float* w1, const float* hidden, const float* dout,
                      int32_t D, const float* scalar, float* dw0, float* db0, float* dw1, void* stream) {
   FVIT_CHECK(coords && w1 && hidden && dout && dw0 && db0 && dw1 && P > 0 && D > 0, "fvit_cpb_mlp_bwd: bad arguments");
+  if (D >= 64 && (size_t)8 * P * sizeof(float) <= 48 * 1024) {  // token embeddings: every operand read once
+    cpb_mlp_bwd_w1x8_kernel<<<(D + 7) / 8, 512, (size_t)8 * P * sizeof(float), (cudaStream_t)stream>>>(P, hidden, dout, D,
+                                                                                                       scalar, dw1);
+    int rc8 = post_launch("cpb_mlp_bwd_w1x8_kernel");
+    if (rc8) return rc8;
+    int sp = D / 32;   // channel splits: enough CTAs to cover the SMs, at least one 32-channel chunk each
+    sp = sp < 1 ? 1 : (sp > 40 ? 40 : sp);
+    cpb_mlp_bwd_hid_kernel<<<dim3(4, (unsigned)sp), 128, 0, (cudaStream_t)stream>>>(coords, P, w1, hidden, dout, D, scalar,
+                                                                                    dw0, db0);
+    return post_launch("cpb_mlp_bwd_hid_kernel");
+  }
   cpb_mlp_bwd_w1_kernel<<<D, 512, P * sizeof(float), (cudaStream_t)stream>>>(P, hidden, dout, D, scalar, dw1);
   int rc = post_launch("cpb_mlp_bwd_w1_kernel");
   if (rc) return rc;
@@ -1511,6 +1649,13 @@ int fvit_token_init_bwd(const float* g, int64_t ldg, const void* x16, int64_t ld
                                                                 sh, sw, oh, ow, scalar, dw, dbias);
   int rc = post_launch("token_init_wgrad_kernel");
   if (rc) return rc;
+  const size_t tile_smem = ((size_t)oh * ow + (size_t)Hp * Wp) * 32 * sizeof(float);
+  if (tile_smem <= 48 * 1024 && B <= 65535) {  // the whole map of one image fits: pool backward formed once per pixel
+    dim3 gt((unsigned)((C + 31) / 32), (unsigned)B);
+    token_init_bwd_tile_kernel<<<gt, 256, tile_smem, (cudaStream_t)stream>>>(g, ldg, pix_map, ct_row_map, Hp, Wp, C, w, kh,
+                                                                             kw, sh, sw, oh, ow, gx, ldgx);
+    return post_launch("token_init_bwd_tile_kernel");
+  }
   const int cb = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   const long long npos = (long long)B * Hp * Wp;
   dim3 gd((unsigned)((C + cb - 1) / cb), (unsigned)(npos < 65535 ? npos : 65535));

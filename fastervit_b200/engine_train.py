@@ -157,14 +157,14 @@ class TrainPlan(Plan):
     # ------------------------------------------------------------------------------ linear layer backward
     def _linear_bwd(self, *, lin, w16, ldw, x16, ldx, dz16, lddz, rows, n_out, k_in, br, gW=None, gW_ld=None,
                     dx16=None, lddx=0, dx_act=L.ACT_NONE, dx_aux=None, ld_aux=0, dx_alpha=None, bias_to=None,
-                    flops_k=None, want_dgrad=True, bias_done=False, dx_colsum=None) -> None:
+                    flops_k=None, want_dgrad=True, bias_done=False, dx_colsum=None, gW_row_map=None) -> None:
         """dW[n_out, k_in] += alpha_w * dz16^T @ x16 ; db += alpha_w * colsum(dz16) ; dx16 = alpha_d * dz16 @ W."""
         gW = self.G(lin.weight) if gW is None else gW
         gW_ld = k_in if gW_ld is None else gW_ld
         fk = k_in if flops_k is None else flops_k
         self._bgemm(a=dz16, a_rows=rows, lda=lddz, a_mn=True, b=x16, b_rows=rows, ldb=ldx, b_mn=True, m=n_out, n=k_in,
                     kc=rows, split_k=self._split_k(n_out, k_in, rows), alpha_ptr=br["w_alpha"], out_f32=gW,
-                    ld_o32=gW_ld, flops=2.0 * rows * n_out * fk)
+                    ld_o32=gW_ld, row_map=gW_row_map, flops=2.0 * rows * n_out * fk)
         if (lin.bias is not None or bias_to is not None) and not bias_done:
             dst = bias_to if bias_to is not None else self.G(lin.bias)
             self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst, None)

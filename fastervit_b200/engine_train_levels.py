@@ -472,21 +472,32 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     _bias_bwd(self, at["bias"])
     # qkv
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
-    if padded:
-        gWq = ("scr", self._scratch("dWqkv_pad", 3 * Cp * Cc))
+    gWq, gbq = self.G(attn.qkv.weight), (self.G(attn.qkv.bias) if attn.qkv.bias is not None else None)
+    if padded:   # dW rows are head-padded: the GEMM epilogue scatters them through a row map, only the bias is un-padded
         gbq = ("scr", self._scratch("dbqkv_pad", 3 * Cp))
-    else:
-        gWq, gbq = self.G(attn.qkv.weight), (self.G(attn.qkv.bias) if attn.qkv.bias is not None else None)
     self._linear_bwd(lin=attn.qkv, w16=at["wq"].data_ptr(), ldw=at["ldq"], x16=at["y16"].data_ptr(), ldx=Cc,
                      dz16=dqkv.data_ptr(), lddz=3 * Cp, rows=rows, n_out=3 * Cp, k_in=Cc, br=one, gW=gWq, gW_ld=Cc,
+                     gW_row_map=_unpad_row_map(self, 3 * h, hd, hdp) if padded else None,
                      bias_to=gbq, dx16=dy.data_ptr(), lddx=Cc, flops_k=Cc * (3 * Cc) / (3 * Cp))
     if padded:
-        self._op(ops, "fvit_unpad_heads_f32", gWq, Cc, self.G(attn.qkv.weight), Cc, 3 * Cp, Cc, hd, hdp, 1, 0, None)
         if attn.qkv.bias is not None:
             self._op(ops, "fvit_unpad_heads_f32", gbq, 1, self.G(attn.qkv.bias), 1, 3 * Cp, 1, hd, hdp, 1, 0, None)
     # LayerNorm (with the gather routing of the forward)
     self._op(ops, "fvit_ln_bwd", dy.data_ptr(), Cc, None, xh.data_ptr(), Cc, rs.data_ptr(), ln.weight.data_ptr(), rows, Cc,
              g_ptr, Cc, in_map, 1, 1 if clear_moved else 0, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
+
+
+def _unpad_row_map(self, heads3: int, hd: int, hdp: int) -> int:
+    """device int32 map: row r of a head-padded [heads3 * hdp, .] matrix -> row of the un-padded [heads3 * hd, .]
+    parameter layout, -1 for padding rows (lets the qkv weight-gradient GEMM scatter straight into the flat gradient
+    buffer instead of writing a padded scratch matrix that a second pass un-pads)."""
+    cache = self.__dict__.setdefault("_unpad_maps", {})
+    key = (heads3, hd, hdp)
+    if key not in cache:
+        r = torch.arange(heads3 * hdp)
+        m = torch.where(r % hdp < hd, (r // hdp) * hd + r % hdp, torch.full_like(r, -1))
+        cache[key] = self.bufs.i32(f"unpad_rows.{heads3}.{hd}.{hdp}", m)
+    return cache[key].data_ptr()
 
 
 def _emit_token_level_bwd(self, tl: dict) -> None:
@@ -563,16 +574,14 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
              hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
     _bias_bwd(self, at["bias"])
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
+    gWq, gbq = self.G(attn.qkv.weight), (self.G(attn.qkv.bias) if attn.qkv.bias is not None else None)
     if padded:
-        gWq = ("scr", self._scratch("dWqkv_pad_c", 3 * Cp * Cc))
         gbq = ("scr", self._scratch("dbqkv_pad_c", 3 * Cp))
-    else:
-        gWq, gbq = self.G(attn.qkv.weight), (self.G(attn.qkv.bias) if attn.qkv.bias is not None else None)
     self._linear_bwd(lin=attn.qkv, w16=at["wq"].data_ptr(), ldw=at["ldq"], x16=at["y16"].data_ptr(), ldx=Cc,
                      dz16=dqkv.data_ptr(), lddz=3 * Cp, rows=rows_c, n_out=3 * Cp, k_in=Cc, br=one, gW=gWq, gW_ld=Cc,
+                     gW_row_map=_unpad_row_map(self, 3 * h, hd, hdp) if padded else None,
                      bias_to=gbq, dx16=dy.data_ptr(), lddx=Cc)
     if padded:
-        self._op(ops, "fvit_unpad_heads_f32", gWq, Cc, self.G(attn.qkv.weight), Cc, 3 * Cp, Cc, hd, hdp, 1, 0, None)
         if attn.qkv.bias is not None:
             self._op(ops, "fvit_unpad_heads_f32", gbq, 1, self.G(attn.qkv.bias), 1, 3 * Cp, 1, hd, hdp, 1, 0, None)
     # hat_norm1: rows r of the raster buffer = level rows ctr0 + r; gradient at (ct + hat_pe) first
