@@ -73,3 +73,25 @@ def test_forward_features_and_head_split():
     O.forward(sd, g["cfg"], x.cpu().double(), capture=cap)
     ref = cap["pooled"]
     assert ((feats.cpu().double() - ref).abs().max() / ref.abs().max()).item() < 2e-3
+
+
+def test_21k_large_window_model_runs_and_training_fails_loudly():
+    """faster_vit_4_21k_224 (window 14: S = 196, head_dim 49, fv.py:1253-1290) runs through the streaming attention
+    kernel at full size; its parity is pinned on the reduced tiny_21k golden above. Training of windows beyond
+    the backward kernels' reach must raise, not fall back."""
+    import fastervit_b200 as F
+    from fastervit_b200.lib import FvitError
+    torch.manual_seed(0)
+    model = F.create_model("faster_vit_4_21k_224").cuda().eval()
+    x = torch.randn(2, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        out = model(x)
+        one = model(x[:1])
+    assert out.shape == (2, 1000) and torch.isfinite(out).all()
+    assert (out[:1] - one).abs().max().item() <= 1e-4 * out.abs().max().item() + 1e-6
+    del model
+    g, tiny, xt = _setup("tiny_21k")
+    tiny.train()
+    with pytest.raises(FvitError):
+        loss = tiny(xt).sum()
+        loss.backward()
