@@ -73,6 +73,14 @@ __device__ __forceinline__ float fvit_gelu(float x) {
   float e;
   return 0.5f * x * (1.0f + fvit_erf_core(x, e));
 }
+// gelu(x) and gelu'(x) from one erf evaluation (the fc1 epilogue of the training forward saves gelu' so that the
+// fc2 data-gradient epilogue only multiplies); the returned value is bit-identical to fvit_gelu(x)
+__device__ __forceinline__ float fvit_gelu_both(float x, float& grad) {
+  float e;
+  const float cdf = 0.5f * (1.0f + fvit_erf_core(x, e));
+  grad = fmaf(x * 0.39894228040143267794f, e, cdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float fvit_gelu_grad(float x) {
   float e;
   const float cdf = 0.5f * (1.0f + fvit_erf_core(x, e));

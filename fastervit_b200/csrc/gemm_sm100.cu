@@ -83,6 +83,7 @@ struct GemmParams {
   const float* aux_shift;
   float* osum;              // optional: osum[c] += *osum_alpha * sum over rows of the rounded out_f16 values
   const float* osum_alpha;
+  int pre_is_grad;          // GELU epilogue stores gelu'(v) through out_pre16 instead of v
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return fvit_gelu(x); }
@@ -161,6 +162,7 @@ enum : uint32_t {
   EF_CS2 = 1u << 11,
   EF_RS = 1u << 12,
   EF_OSUM = 1u << 13,        // per-column sum of the rounded 16-bit output (bias gradient of the next layer)
+  EF_PREGRAD = 1u << 14,     // out_pre16 receives gelu'(v) (consumed by FVIT_ACT_MUL_AUX in the backward pass)
 };
 // work unit -> (M tile, N tile, K split). Plain GEMMs keep the K splits of a tile adjacent; the tap-in-N mode
 // walks all tiles of one K range first so concurrently running CTAs share the A / B slices in L2.
@@ -335,13 +337,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool atomic_out = GENERIC ? (p.atomic_out != 0) : ((FEAT & EF_ATOMIC) != 0);
     const bool use_resid = GENERIC ? (p.resid != nullptr && !p.atomic_out) : ((FEAT & EF_RESID) != 0);
     const int act = GENERIC ? p.act : ACT;
-    const bool use_aux = (act == FVIT_ACT_GELU_BWD || act == FVIT_ACT_RELU_BWD) && !atomic_out;
+    const bool use_aux = (act == FVIT_ACT_GELU_BWD || act == FVIT_ACT_RELU_BWD || act == FVIT_ACT_MUL_AUX) && !atomic_out;
     const bool out32 = GENERIC ? (p.out_f32 != nullptr) : ((FEAT & EF_O32) != 0);
     const bool out16 = GENERIC ? (p.out_f16 != nullptr) : ((FEAT & EF_O16) != 0);
     const bool stats = GENERIC ? (p.col_sum != nullptr && !p.atomic_out) : ((FEAT & EF_STATS) != 0);
     const bool has_cs2 = GENERIC ? (p.col_scale2 != nullptr) : ((FEAT & EF_CS2) != 0);
     const bool has_rs = GENERIC ? (p.row_scale != nullptr) : ((FEAT & EF_RS) != 0);
     const bool has_pre = GENERIC ? (p.out_pre16 != nullptr) : ((FEAT & EF_PRE) != 0);
+    const bool pregrad = GENERIC ? (p.pre_is_grad != 0) : ((FEAT & EF_PREGRAD) != 0);
     const bool has_aptr = GENERIC ? (p.alpha_ptr != nullptr) : ((FEAT & EF_ALPHAPTR) != 0);
     const bool osum = GENERIC ? (p.osum != nullptr) : ((FEAT & EF_OSUM) != 0);
     const float alpha = has_aptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
@@ -496,9 +499,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
           }
           if (!ok) continue;
+          float4 pv = v;  // what out_pre16 receives: the pre-activation value, or gelu'(v) with pre_is_grad
+          if (act == FVIT_ACT_RELU) {
+            v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+          } else if (act == FVIT_ACT_GELU) {
+            if (has_pre && pregrad) {
+              v.x = fvit_gelu_both(v.x, pv.x), v.y = fvit_gelu_both(v.y, pv.y), v.z = fvit_gelu_both(v.z, pv.z),
+              v.w = fvit_gelu_both(v.w, pv.w);
+            } else {
+              v.x = gelu_erf(v.x), v.y = gelu_erf(v.y), v.z = gelu_erf(v.z), v.w = gelu_erf(v.w);
+            }
+          }
           if (has_pre) {
             uint16_t* o = reinterpret_cast<uint16_t*>(p.out_pre16) + (long long)(row_base + rl) * p.ld_pre16 + col;
-            const uint32_t lo = pack2_16(v.x, v.y, p.bf16), hi = pack2_16(v.z, v.w, p.bf16);
+            const uint32_t lo = pack2_16(pv.x, pv.y, p.bf16), hi = pack2_16(pv.z, pv.w, p.bf16);
             if (cfull && p.vec_ok) {
               *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
             } else {
@@ -508,10 +522,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if (col + 3 < n_end) o[3] = (uint16_t)(hi >> 16);
             }
           }
-          if (act == FVIT_ACT_RELU) {
-            v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
-          } else if (act == FVIT_ACT_GELU) {
-            v.x = gelu_erf(v.x), v.y = gelu_erf(v.y), v.z = gelu_erf(v.z), v.w = gelu_erf(v.w);
+          if (act == FVIT_ACT_MUL_AUX) {
+            float a[4];
+            unpack4_16(av[k], p.bf16, a);
+            v.x *= a[0], v.y *= a[1], v.z *= a[2], v.w *= a[3];
           } else if (use_aux) {
             float a[4];
             unpack4_16(av[k], p.bf16, a);
@@ -720,8 +734,9 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   const int split_k = a->split_k > 1 ? a->split_k : 1;
   if (split_k > 1)
     FVIT_CHECK(a->out_f32 && !a->out_f16 && !a->col_sum, "fvit_gemm: split_k needs out_f32 only");
-  if (a->act == FVIT_ACT_GELU_BWD || a->act == FVIT_ACT_RELU_BWD)
+  if (a->act == FVIT_ACT_GELU_BWD || a->act == FVIT_ACT_RELU_BWD || a->act == FVIT_ACT_MUL_AUX)
     FVIT_CHECK(a->aux != nullptr, "fvit_gemm: backward activation needs aux");
+  FVIT_CHECK(a->act >= FVIT_ACT_NONE && a->act <= FVIT_ACT_MUL_AUX, "fvit_gemm: unknown activation code %d", a->act);
   FVIT_CHECK((a->col_sum == nullptr) == (a->col_sumsq == nullptr),
              "fvit_gemm: col_sum and col_sumsq go together");
   FVIT_CHECK(!a->col_sum || a->n <= STATS_MAX_N, "fvit_gemm: statistics support n <= %d", STATS_MAX_N);
@@ -792,6 +807,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.aux_shift = a->aux_shift;
   p.osum = a->out_colsum;
   p.osum_alpha = a->out_colsum_alpha;
+  p.pre_is_grad = (a->pre_is_grad && a->out_pre16 && a->act == FVIT_ACT_GELU) ? 1 : 0;
   // vector path: every touched row segment must be 16-byte aligned
   bool vec = true;
   if (a->out_f32)
@@ -842,6 +858,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (a->col_scale2) feat |= EF_CS2;
   if (a->row_scale) feat |= EF_RS;
   if (a->out_colsum) feat |= EF_OSUM;
+  if (p.pre_is_grad) feat |= EF_PREGRAD;
   const bool needs_generic = false;
 #define FVIT_GEMM_LAUNCH(F)                                                                            \
   do {                                                                                                 \
@@ -869,6 +886,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
       // ---- training forward
       case FVIT_ACTF(0) | EF_O16 | EF_STATS: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_O16 | EF_STATS);         // raw conv + BN statistics
       case FVIT_ACTF(2) | EF_O16 | EF_PRE: FVIT_GEMM_LAUNCH(FVIT_ACTF(2) | EF_O16 | EF_PRE);             // fc1 saving the pre-GELU value
+      case FVIT_ACTF(2) | EF_O16 | EF_PRE | EF_PREGRAD:
+        FVIT_GEMM_LAUNCH(FVIT_ACTF(2) | EF_O16 | EF_PRE | EF_PREGRAD);                                    // fc1 saving gelu'
       case FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_RS: FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_RS);  // branch + stochastic depth
       case FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_CS2 | EF_PRE:
         FVIT_GEMM_LAUNCH(FVIT_ACTF(0) | EF_RESID | EF_O32 | EF_CS2 | EF_PRE);                             // branch with layer scale
@@ -882,6 +901,9 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
       case FVIT_ACTF(3) | EF_O16: FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16);                               // conv dgrad * gelu'
       case FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR | EF_OSUM:
         FVIT_GEMM_LAUNCH(FVIT_ACTF(3) | EF_O16 | EF_ALPHAPTR | EF_OSUM);                                  // fc2 dgrad * gelu' + fc1 bias gradient
+      case FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR);   // fc2 dgrad * saved gelu'
+      case FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR | EF_OSUM:
+        FVIT_GEMM_LAUNCH(FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR | EF_OSUM);                                  // ... + fc1 bias gradient
       default: break;
     }
   }

@@ -738,80 +738,6 @@ cpb_mlp_bwd_kernel(const float* __restrict__ coords, int P, const float* __restr
   atomicAdd(db0 + j, dh);
 }
 
-// Blocked variants of the two kernels above: the token-embedding MLPs have few points (P = 16 .. 169) and many
-// channels (D = C up to 1568), so the versions above re-read `hidden` once per channel and `w1` once per point
-// through L2 (80-160 MB per call). Here a CTA covers 8 channels (dW1) resp. all points (d hidden), and each
-// operand is read once.
-//   dw1[d][j] += sc * sum_p dout[p][d] * hid[p][j] for the 8 channels d0 .. d0+7 of the CTA; thread = hidden unit j
-__global__ void __launch_bounds__(512)
-cpb_mlp_bwd_w1x8_kernel(int P, const float* __restrict__ hidden, const float* __restrict__ dout, int D,
-                        const float* __restrict__ scalar, float* __restrict__ dw1) {
-  extern __shared__ float sdo8[];  // [8][P] dout columns of this CTA (scaled)
-  const int d0 = blockIdx.x * 8;
-  const float sc = scalar ? __ldg(scalar) : 1.f;
-  for (int i = threadIdx.x; i < 8 * P; i += blockDim.x) {
-    const int dd = i / P, pp = i - dd * P;
-    sdo8[i] = d0 + dd < D ? dout[(long long)pp * D + d0 + dd] * sc : 0.f;
-  }
-  __syncthreads();
-  const int j = threadIdx.x;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int pp = 0; pp < P; ++pp) {
-    const float hv = hidden[(long long)pp * 512 + j];
-#pragma unroll
-    for (int dd = 0; dd < 8; ++dd) acc[dd] = fmaf(sdo8[dd * P + pp], hv, acc[dd]);
-  }
-#pragma unroll
-  for (int dd = 0; dd < 8; ++dd)
-    if (d0 + dd < D) dw1[(long long)(d0 + dd) * 512 + j] += acc[dd];
-}
-//   dhid[p][j] = relu'(hid[p][j]) * sc * sum_d dout[p][d] w1[d][j] -> dw0[j][:] += dhid * coords[p][:], db0[j] += dhid.
-//   grid (4 chunks of 128 hidden units, splits of the channel range); a thread keeps the partial sums of up to 64
-//   points in registers while it streams its w1 column once; three atomics per thread at the end.
-constexpr int CPB_PB = 64, CPB_DC = 32;
-__global__ void __launch_bounds__(128)
-cpb_mlp_bwd_hid_kernel(const float* __restrict__ coords, int P, const float* __restrict__ w1,
-                       const float* __restrict__ hidden, const float* __restrict__ dout, int D,
-                       const float* __restrict__ scalar, float* __restrict__ dw0, float* __restrict__ db0) {
-  __shared__ float sd[CPB_PB * CPB_DC];  // [point][channel of the current chunk]
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  const int d0 = (int)((long long)D * blockIdx.y / gridDim.y), d1 = (int)((long long)D * (blockIdx.y + 1) / gridDim.y);
-  const float sc = scalar ? __ldg(scalar) : 1.f;
-  float s0 = 0.f, s1 = 0.f, sb = 0.f;
-  for (int pb = 0; pb < P; pb += CPB_PB) {
-    const int np = min(CPB_PB, P - pb);
-    float acc[CPB_PB];
-#pragma unroll
-    for (int i = 0; i < CPB_PB; ++i) acc[i] = 0.f;
-    for (int dc = d0; dc < d1; dc += CPB_DC) {
-      const int nd = min(CPB_DC, d1 - dc);
-      __syncthreads();
-      for (int i = threadIdx.x; i < CPB_PB * CPB_DC; i += blockDim.x) {
-        const int pp = i / CPB_DC, dd = i - pp * CPB_DC;
-        sd[i] = (pp < np && dd < nd) ? dout[(long long)(pb + pp) * D + dc + dd] * sc : 0.f;
-      }
-      __syncthreads();
-      for (int dd = 0; dd < nd; ++dd) {
-        const float wv = w1[(long long)(dc + dd) * 512 + j];
-#pragma unroll
-        for (int pp = 0; pp < CPB_PB; ++pp) acc[pp] = fmaf(sd[pp * CPB_DC + dd], wv, acc[pp]);
-      }
-    }
-#pragma unroll
-    for (int pp = 0; pp < CPB_PB; ++pp) {
-      if (pp < np && hidden[(long long)(pb + pp) * 512 + j] > 0.f) {
-        const float dh = acc[pp];
-        s0 = fmaf(dh, coords[2 * (pb + pp)], s0);
-        s1 = fmaf(dh, coords[2 * (pb + pp) + 1], s1);
-        sb += dh;
-      }
-    }
-  }
-  atomicAdd(dw0 + 2 * j, s0);
-  atomicAdd(dw0 + 2 * j + 1, s1);
-  atomicAdd(db0 + j, sb);
-}
-
 // Backward of the head: y[b,t,c] = xhat*w + beta with batch statistics, pooled[b,c] = mean_t y.
 // reduce: s1[c] = sum_b dp[b,c] ; s2[c] = sum_b dp[b,c]/T * sum_t xhat[b,t,c]   (dp = d pooled, scaled)
 __global__ void pool_bn_bwd_reduce_kernel(const float* __restrict__ xs, long long ldx, const int* __restrict__ rows,
@@ -1522,17 +1448,6 @@ int fvit_attn_bias_bwd(const float* dbias, const float* bias, const int64_t* ind
 int fvit_cpb_mlp_bwd(const float* coords, int32_t P, const float* w1, const float* hidden, const float* dout,
                      int32_t D, const float* scalar, float* dw0, float* db0, float* dw1, void* stream) {
   FVIT_CHECK(coords && w1 && hidden && dout && dw0 && db0 && dw1 && P > 0 && D > 0, "fvit_cpb_mlp_bwd: bad arguments");
-  if (D >= 64 && (size_t)8 * P * sizeof(float) <= 48 * 1024) {  // token embeddings: every operand read once
-    cpb_mlp_bwd_w1x8_kernel<<<(D + 7) / 8, 512, (size_t)8 * P * sizeof(float), (cudaStream_t)stream>>>(P, hidden, dout, D,
-                                                                                                       scalar, dw1);
-    int rc8 = post_launch("cpb_mlp_bwd_w1x8_kernel");
-    if (rc8) return rc8;
-    int sp = D / 32;   // channel splits: enough CTAs to cover the SMs, at least one 32-channel chunk each
-    sp = sp < 1 ? 1 : (sp > 40 ? 40 : sp);
-    cpb_mlp_bwd_hid_kernel<<<dim3(4, (unsigned)sp), 128, 0, (cudaStream_t)stream>>>(coords, P, w1, hidden, dout, D, scalar,
-                                                                                    dw0, db0);
-    return post_launch("cpb_mlp_bwd_hid_kernel");
-  }
   cpb_mlp_bwd_w1_kernel<<<D, 512, P * sizeof(float), (cudaStream_t)stream>>>(P, hidden, dout, D, scalar, dw1);
   int rc = post_launch("cpb_mlp_bwd_w1_kernel");
   if (rc) return rc;

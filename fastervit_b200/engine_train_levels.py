@@ -269,7 +269,8 @@ def _emit_token_level_train(self, i: int, level, tl: dict) -> None:
 def _mlp_fwd_train(self, nm: str, mlp, gamma, rows: int, y16, p16, h16, stream_buf, u16, rs=None) -> dict:
     n1, k1 = mlp.fc1.weight.shape
     w1, ld1 = self._pack_linear(nm + ".fc1", mlp.fc1)
-    # fc1: pre-GELU saved through out_pre16, GELU output is the fc2 operand
+    # fc1: gelu'(pre-activation) saved through out_pre16 (one erf evaluation yields GELU and its derivative, so the
+    # fc2 data-gradient epilogue is a plain multiply: FVIT_ACT_MUL_AUX), GELU output is the fc2 operand
     g = L.GemmArgs()
     g.a, g.a_rows, g.lda, g.a_planes = y16.data_ptr(), rows, k1, 1
     g.b, g.b_rows, g.ldb = w1.data_ptr(), n1, ld1
@@ -277,6 +278,7 @@ def _mlp_fwd_train(self, nm: str, mlp, gamma, rows: int, y16, p16, h16, stream_b
     g.col_shift, g.act = mlp.fc1.bias.data_ptr(), L.ACT_GELU
     g.out_f16, g.ld_out_f16 = h16.data_ptr(), n1
     g.out_pre16, g.ld_out_pre16 = p16.data_ptr(), n1
+    g.pre_is_grad = 1
     self._gemm_keep.append(g)
     import ctypes as C
     self.ops.append((self.lib.fvit_gemm, (C.byref(g),), "fvit_gemm"))
@@ -420,10 +422,10 @@ def _mlp_bwd(self, tl: dict, ms: dict, gamma, g_ptr: int, rows: int, ln: nn.Laye
         if br["gamma"] is not None:
             self._op(ops, "fvit_colsum", g_ptr, 0, Cc, None, ms["u16"].data_ptr(), Cc, rows, Cc, None, ("scal", 1),
                      self.G(gamma), ms["rs"])
-    # fc2: dW2, db2, dp = (dz W2) o gelu'(p)
+    # fc2: dW2, db2, dp = (dz W2) o gelu'(p)   (p16 holds gelu'(p), saved by the forward epilogue)
     self._linear_bwd(lin=mlp.fc2, w16=ms["w2"].data_ptr(), ldw=ms["ld2"], x16=ms["h16"].data_ptr(), ldx=hid,
                      dz16=dz.data_ptr(), lddz=Cc, rows=rows, n_out=Cc, k_in=hid, br=br, dx16=dp.data_ptr(), lddx=hid,
-                     dx_act=L.ACT_GELU_BWD, dx_aux=ms["p16"].data_ptr(), ld_aux=hid, bias_done=fused,
+                     dx_act=L.ACT_MUL_AUX, dx_aux=ms["p16"].data_ptr(), ld_aux=hid, bias_done=fused,
                      dx_colsum=(self.G(mlp.fc1.bias), ("scal", 1)) if mlp.fc1.bias is not None else None)
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
     # (fc1's bias gradient = column sums of dp, taken in the epilogue of the GEMM that produced dp)

@@ -35,7 +35,8 @@ enum {
   FVIT_ACT_RELU = 1,
   FVIT_ACT_GELU = 2,     /* exact erf GELU (nn.GELU default; fv.py:379,491) */
   FVIT_ACT_GELU_BWD = 3, /* v *= gelu'(aux[row,col])  (backward of the above) */
-  FVIT_ACT_RELU_BWD = 4  /* v *= (aux[row,col] > 0) */
+  FVIT_ACT_RELU_BWD = 4, /* v *= (aux[row,col] > 0) */
+  FVIT_ACT_MUL_AUX = 5   /* v *= aux[row,col]  (aux = gelu' saved by the forward GEMM, see pre_is_grad) */
 };
 
 /* ---- tensor-core GEMM with shifted-row taps and fused epilogue --------------------------------
@@ -115,6 +116,8 @@ typedef struct fvit_gemm_args {
   const float* out_colsum_alpha; /* device scalar, NULL = 1 */
   const float* aux_scale; /* optional fp32 [n] pair: the *_BWD activations see aux * aux_scale + aux_shift (aux = saved raw */
   const float* aux_shift; /* convolution output, scale/shift = that BatchNorm's batch-statistics affine) */
+  int32_t pre_is_grad;    /* with act == FVIT_ACT_GELU and out_pre16: store gelu'(v) there instead of v, so the
+                             backward GEMM's epilogue is a plain multiply (FVIT_ACT_MUL_AUX) */
 } fvit_gemm_args;
 
 int fvit_gemm(const fvit_gemm_args* args, void* stream);

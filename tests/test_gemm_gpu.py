@@ -257,6 +257,41 @@ def test_gemm_gelu_bwd_epilogue():
     assert _rel(o16, ref) < 1e-3
 
 
+@pytest.mark.parametrize("m,n,k", [(512, 256, 128), (1000, 3136, 200), (130, 200, 72)])
+def test_gemm_gelu_saves_derivative_and_mul_aux_consumes_it(m, n, k):
+    """Training forward of fc1 (fv.py:401-404): one epilogue emits GELU(z) and gelu'(z) (pre_is_grad); the fc2
+    data-gradient GEMM multiplies by the saved derivative (FVIT_ACT_MUL_AUX) and sums the rounded output per
+    column (fc1 bias gradient). The GELU output must be bit-identical to the plain GELU epilogue."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.1).half()
+    bias = torch.randn(n, device="cuda", generator=g)
+    h16 = torch.zeros(m, n, device="cuda").half()
+    g16 = torch.zeros(m, n, device="cuda").half()
+    lib.gemm(a, b, act=lib.ACT_GELU, col_shift=bias, out_f16=h16, out_pre16=g16, pre_is_grad=True)
+    plain = torch.zeros(m, n, device="cuda").half()
+    pre16 = torch.zeros(m, n, device="cuda").half()
+    lib.gemm(a, b, act=lib.ACT_GELU, col_shift=bias, out_f16=plain, out_pre16=pre16)
+    assert torch.equal(h16, plain)
+    z = (a.double() @ b.double().t() + bias.double()).requires_grad_(True)
+    torch.nn.functional.gelu(z).sum().backward()
+    assert _rel(pre16, z.detach()) < 1e-3          # without the flag out_pre16 still holds the pre-activation
+    assert (g16.double() - z.grad).abs().max().item() < 1.5e-3   # |gelu'| <= 1.13, fp16 rounding + A-S erf
+    # backward: dH = (dY @ W2) * saved derivative, plus the column sums of the rounded result
+    dy = torch.randn(m, 64, device="cuda", generator=g).half()
+    w2 = (torch.randn(64, n, device="cuda", generator=g) * 0.1).half()      # [K = 64, n]: MN-major B operand
+    dh = torch.zeros(m, n, device="cuda").half()
+    one = torch.ones(1, device="cuda")
+    colsum = torch.zeros(n, device="cuda")
+    lib.gemm(dy, w2, b_mn=True, act=lib.ACT_MUL_AUX, aux=g16, alpha_ptr=one, out_f16=dh, out_colsum=colsum,
+             out_colsum_alpha=one)
+    ref = (dy.double() @ w2.double()) * g16.double()
+    assert _rel(dh, ref) < 1e-3
+    want = dh.double().sum(0)
+    assert (colsum.double() - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("m,n", [(512, 256), (1000, 3136), (130, 200)])
 def test_gemm_output_column_sums(m, n):
     """out_colsum: per-column sum of the rounded fp16 output, scaled by a device scalar (bias gradient of the
