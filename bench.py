@@ -54,13 +54,17 @@ def peaks() -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi sampler running during the timed region (B200_PROFILING.md 'clocks line')."""
+    """nvidia-smi sampler (B200_PROFILING.md 'clocks line'). It is started before the warm-up steps (nvidia-smi needs
+    ~1 s before its first sample) and every line is time-stamped on arrival; `stop()` reports the samples that fall
+    inside the timed region [mark_begin, mark_end]. If the timed region is too short to hold two samples, the
+    samples of the warm-up + timed period (the GPU is under the same load) are used and `window` says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -74,7 +78,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -84,9 +94,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else time.time()
+        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.15]
+        window = "timed region"
+        if len(inside) < 2:   # short run: fall back to everything sampled while the same steps were running
+            inside = [ln for ts, ln in self.lines if ts <= t1 + 0.15]
+            window = "warm-up + timed region (timed region shorter than two sampling periods)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -99,7 +116,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float = 20.0) -> dict:
@@ -286,12 +303,13 @@ def main() -> None:
             return loss
         return model(xb)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()   # before the warm-up: nvidia-smi takes about a second to deliver its first sample
     with torch.set_grad_enabled(mode == "train"):
         for i in range(args.warmup):
             step(xs[i % nbuf])
         sync_all()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.mark_begin()
         L.reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -299,6 +317,7 @@ def main() -> None:
             out = step(xs[i % nbuf])
         e1.record()
         sync_all()
+        sampler.mark_end()
         launches = L.launch_count()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
@@ -388,10 +407,15 @@ def main() -> None:
         gm = by.get("fvit_gemm")
         prof_table = {k: dict(ms=round(v["ms"], 4), launches=v["n"], share=round(v["ms"] / tot, 4),
                               gflop=round(v["flops"] / 1e9, 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
-        traffic = None   # DRAM bytes per GEMM launch from the committed ncu launch list of this workload
-        tf = ROOT / "profiles" / "r01b_traffic.json"
-        if tf.exists():
-            traffic = json.loads(tf.read_text()).get(args.workload, {}).get("gemm_dram_bytes_per_launch")
+        traffic, traffic_src = None, None   # DRAM bytes per GEMM launch from the newest committed ncu launch list
+        for tf in sorted((ROOT / "profiles").glob("r*_traffic.json"), reverse=True):
+            try:
+                traffic = json.loads(tf.read_text()).get(args.workload, {}).get("gemm_dram_bytes_per_launch")
+            except (OSError, ValueError):
+                traffic = None
+            if traffic is not None:
+                traffic_src = f"profiles/{tf.name}"
+                break
         if gm:
             ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
             roofline = {"kernel": "gemm_tcgen05_kernel (fvit_gemm: conv taps + linear layers; fwd, dgrad and wgrad launches)",
@@ -399,7 +423,7 @@ def main() -> None:
                         "achieved": round(ach, 2), "peak": pk["tensor"], "unit": "TFLOP/s",
                         "frac": round(ach / pk["tensor"], 4),
                         "traffic": None if traffic is None else round(traffic),
-                        "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r01b_traffic.json)",
+                        "traffic_unit": f"DRAM bytes per launch (ncu dram__bytes_read+write, {traffic_src})",
                         "peak_source": f"{pk['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
                         "launches_per_step": gm["n"], "avg_launch_ms": round(gm["ms"] / gm["n"], 5),
                         "alg_gflop_per_launch": round(gm["flops"] / gm["n"] / 1e9, 3),
