@@ -443,7 +443,9 @@ def main() -> None:
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1)
     cpu = None
     if rank == 0 and world == 1:
-        cpu = cpu_reference_rate(args.workload, steps=1000, warmup=1, budget_s=15.0)
+        # bounded sample of the reference path on the host cores (FVIT_BENCH_CPU_BUDGET_S: seconds, default 15)
+        cpu = cpu_reference_rate(args.workload, steps=1000, warmup=1,
+                                 budget_s=float(os.environ.get("FVIT_BENCH_CPU_BUDGET_S", "15")))
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
