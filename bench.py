@@ -423,7 +423,8 @@ def main() -> None:
                         "achieved": round(ach, 2), "peak": pk["tensor"], "unit": "TFLOP/s",
                         "frac": round(ach / pk["tensor"], 4),
                         "traffic": None if traffic is None else round(traffic),
-                        "traffic_unit": f"DRAM bytes per launch (ncu dram__bytes_read+write, {traffic_src})",
+                        "traffic_unit": (f"DRAM bytes per launch (ncu dram__bytes_read+write, {traffic_src})" if traffic_src
+                                         else "no ncu launch list with DRAM bytes committed for this workload"),
                         "peak_source": f"{pk['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
                         "launches_per_step": gm["n"], "avg_launch_ms": round(gm["ms"] / gm["n"], 5),
                         "alg_gflop_per_launch": round(gm["flops"] / gm["n"] / 1e9, 3),
