@@ -84,3 +84,40 @@ def test_bench_reference_arm_only_rank0_prints():
     assert outs[0] == ""                       # rank 1: exits 0 without work
     line = json.loads(outs[1].splitlines()[-1])  # rank 0: one JSON line
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_clock_sampler_windows_samples_to_the_timed_region(tmp_path, monkeypatch):
+    """bench.py's nvidia-smi sampler: lines are time-stamped on arrival, only those inside [mark_begin, mark_end] count,
+    throttle reasons are collected, and a timed region too short for two samples falls back to warm-up + timed."""
+    import importlib.util
+    import os
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.3\ni=0\nwhile true; do\n"
+                    "if [ $((i % 2)) -eq 0 ]; then echo '1935, 1965, 998.1, Not Active, Not Active, Not Active, Active'; "
+                    "else echo '1965, 1965, 800.0, Not Active, Not Active, Not Active, Not Active'; fi\n"
+                    "i=$((i+1)); sleep 0.05\ndone\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}{os.pathsep}{os.environ['PATH']}")
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.8)            # "warm-up": samples arrive but must not be counted
+    s.mark_begin()
+    time.sleep(0.5)
+    s.mark_end()
+    time.sleep(0.2)            # samples after the region must not be counted either
+    out = s.stop()
+    assert out["window"] == "timed region" and 5 <= out["samples"] <= 14
+    assert out["sm_max_mhz"] == 1965.0 and out["sm_mhz"] in (1935.0, 1965.0) and out["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.7)
+    s.mark_begin()
+    time.sleep(0.01)
+    s.mark_end()
+    out = s.stop()
+    assert out["window"].startswith("warm-up") and out["samples"] >= 2
