@@ -18,8 +18,6 @@ Tensor-core operands are fp16, accumulation fp32, residual stream / LayerNorm / 
 from __future__ import annotations
 
 import ctypes as C
-import math
-from typing import Callable
 
 import torch
 import torch.nn as nn

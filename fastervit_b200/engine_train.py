@@ -17,7 +17,6 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
-import torch.nn as nn
 
 from . import lib as L
 from .engine import Plan, _ru

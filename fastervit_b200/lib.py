@@ -6,7 +6,6 @@ device, this module raises. PyTorch is used only for device memory and streams.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 
 import torch

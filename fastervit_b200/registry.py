@@ -6,7 +6,6 @@ importable, so `timm.create_model('faster_vit_0_224')` (validate.py:195, train.p
 from __future__ import annotations
 
 import fnmatch
-import functools
 import re
 from collections import OrderedDict
 
