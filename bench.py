@@ -45,6 +45,11 @@ ALG_GFLOP_FWD = {"fv0_fwd": 6.7237, "fv4_fwd": 85.3574, "ar0_fwd": 73.0828,
                  "fv0_train": 20.3580, "fv4_train": 258.1946}  # train entries: fwd+bwd
 
 
+# published numbers for the same metric (the reference README's inference-throughput column, hardware
+# "not stated in repo", paper: A100 / TensorRT); nothing is published for forward+backward or for any-res
+PUBLISHED_IMG_S = {"fv0_fwd": 5802.0, "fv4_fwd": 849.0}
+
+
 def peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -453,7 +458,9 @@ def main() -> None:
         alg = ALG_GFLOP_FWD[args.workload] * 1e9
         line = {"metric": "images/sec", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": (round(value / world / PUBLISHED_IMG_S[args.workload], 3)
+                                if args.workload in PUBLISHED_IMG_S else None),
                 "dtype": "fp16 operands, fp32 accumulate / residual / statistics", "data": "synthetic",
                 "config": config, "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "clocks": clocks, "roofline": roofline,
