@@ -317,9 +317,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   }
 }
 
-static std::mutex g_at_mu;
-static std::unordered_map<uint64_t, CUtensorMap> g_at_cache;
-
 template <int HDP>
 static int launch_attn(const CUtensorMap& tm, const AttnParams& p, size_t smem, cudaStream_t st) {
   static bool configured = false;
@@ -328,8 +325,10 @@ static int launch_attn(const CUtensorMap& tm, const AttnParams& p, size_t smem, 
     configured = true;
   }
   const int items = p.tiles * p.heads;
-  const int sms = num_sms();
-  attn_tc_kernel<HDP><<<items < sms ? items : sms, AT_THREADS, smem, st>>>(tm, p);
+  // the kernel is built for two resident CTAs per SM (__launch_bounds__(192, 2), <= 113 KB of shared memory each):
+  // one CTA's softmax / epilogue phase overlaps the other's TMA + MMA phase
+  const int slots = (smem <= 113 * 1024 ? 2 : 1) * num_sms();
+  attn_tc_kernel<HDP><<<items < slots ? items : slots, AT_THREADS, smem, st>>>(tm, p);
   return post_launch("attn_tc_kernel");
 }
 
@@ -360,22 +359,12 @@ extern "C" int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, in
   p.ldo = ldo;
   CUtensorMap tm;
   {
-    const uint64_t key = reinterpret_cast<uint64_t>(qkv) ^ ((uint64_t)ldq << 40) ^ ((uint64_t)p.rows_total << 8) ^
-                         (uint64_t)hdp ^ ((uint64_t)heads << 52) ^ ((uint64_t)p.slot << 30);
-    std::lock_guard<std::mutex> g(g_at_mu);
-    auto it = g_at_cache.find(key);
-    if (it != g_at_cache.end()) {
-      tm = it->second;
-    } else {
-      uint64_t dims[2] = {(uint64_t)(3 * heads * hdp), (uint64_t)p.rows_total};
-      uint64_t strides[1] = {(uint64_t)ldq * 2};
-      uint32_t box[2] = {(uint32_t)hdp, (uint32_t)p.slot};
-      int rc = encode_tmap_16bit(&tm, qkv, 2, dims, strides, box,
-                                 hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
-      if (g_at_cache.size() > 4096) g_at_cache.clear();
-      g_at_cache.emplace(key, tm);
-    }
+    uint64_t dims[2] = {(uint64_t)(3 * heads * hdp), (uint64_t)p.rows_total};
+    uint64_t strides[1] = {(uint64_t)ldq * 2};
+    uint32_t box[2] = {(uint32_t)hdp, (uint32_t)p.slot};
+    int rc = cached_tmap_16bit(&tm, qkv, 2, dims, strides, box,
+                               hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
   }
   const size_t smem = 1024 + (hdp == 64 ? AttnSmem<64>::BIAS_OFF : AttnSmem<32>::BIAS_OFF) +
                       ((size_t)S * S * 4 + 15) / 16 * 16 + 128;
@@ -759,12 +748,12 @@ extern "C" int fvit_attn_tc_bwd(const void* qkv, int64_t ldq, const void* dout, 
     uint64_t dims[2] = {(uint64_t)(3 * heads * hdp), (uint64_t)rows_total};
     uint64_t strides[1] = {(uint64_t)ldq * 2};
     uint32_t box[2] = {(uint32_t)hdp, (uint32_t)p.slot};
-    int rc = encode_tmap_16bit(&tq, qkv, 2, dims, strides, box,
+    int rc = cached_tmap_16bit(&tq, qkv, 2, dims, strides, box,
                                hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     uint64_t dims2[2] = {(uint64_t)(heads * hdp), (uint64_t)rows_total};
     uint64_t strides2[1] = {(uint64_t)lddo * 2};
-    rc = encode_tmap_16bit(&td, dout, 2, dims2, strides2, box,
+    rc = cached_tmap_16bit(&td, dout, 2, dims2, strides2, box,
                            hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }

@@ -3,6 +3,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/fvit.h"
 
@@ -83,6 +84,53 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
     return set_error("cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu box %u,%u)",
                      (int)r, rank, (unsigned long long)dims[0],
                      (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+  return 0;
+}
+
+namespace {
+struct TmapKey {
+  const void* base;
+  uint64_t d[3], s[2];
+  uint32_t b[3];
+  int rank, swz;
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    for (int i = 0; i < 3; ++i) mix(k.d[i]), mix(k.b[i]);
+    mix(k.s[0]), mix(k.s[1]), mix((uint64_t)k.rank), mix((uint64_t)k.swz);
+    return h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+}  // namespace
+
+int cached_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  TmapKey key;
+  std::memset(&key, 0, sizeof(key));  // padding bytes take part in the memcmp
+  key.base = base, key.rank = rank, key.swz = (int)swz;
+  for (int i = 0; i < rank && i < 3; ++i) {
+    key.d[i] = dims[i];
+    key.b[i] = box[i];
+    if (i > 0) key.s[i - 1] = strides_bytes[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  int rc = encode_tmap_16bit(out, base, rank, dims, strides_bytes, box, swz);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(g_tmap_mu);
+  if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
   return 0;
 }
 

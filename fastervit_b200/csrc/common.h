@@ -42,6 +42,11 @@ int num_sms();
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
+// Same, memoised on the complete geometry (base, rank, dims, strides, box, swizzle): the launch lists replay the
+// same few hundred descriptors every step and cuTensorMapEncodeTiled costs microseconds of host time.
+int cached_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -672,47 +672,13 @@ static int pick_tile_n(int m, int n, int split_k, int b_mn, int sms) {
   return best;
 }
 
-struct TmapKey {
-  const void* base;
-  uint64_t d0, d1, d2, s1, s2;
-  uint32_t b0, b1;
-  bool operator==(const TmapKey& o) const {
-    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 &&
-           b0 == o.b0 && b1 == o.b1;
-  }
-};
-struct TmapKeyHash {
-  size_t operator()(const TmapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.base);
-    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-    mix(k.d0), mix(k.d1), mix(k.d2), mix(k.s1), mix(k.s2), mix(k.b0), mix(k.b1);
-    return h;
-  }
-};
-static std::mutex g_tmap_mu;
-static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
-
 // 3-D (or degenerate) 16-bit tensor map with a {b0, b1, 1} box, cached by geometry.
 static int get_tmap(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                     uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, int rank) {
-  TmapKey key{base, d0, d1, d2, s1_bytes, s2_bytes, b0, b1};
-  {
-    std::lock_guard<std::mutex> g(g_tmap_mu);
-    auto it = g_tmap_cache.find(key);
-    if (it != g_tmap_cache.end()) {
-      *out = it->second;
-      return 0;
-    }
-  }
   uint64_t dims[3] = {d0, d1, d2};
   uint64_t strides[2] = {s1_bytes, s2_bytes};
   uint32_t box[3] = {b0, b1, 1};
-  int rc = encode_tmap_16bit(out, base, rank, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  std::lock_guard<std::mutex> g(g_tmap_mu);
-  if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
-  g_tmap_cache.emplace(key, *out);
-  return 0;
+  return cached_tmap_16bit(out, base, rank, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace fvit

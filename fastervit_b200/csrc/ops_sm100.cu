@@ -780,6 +780,44 @@ __global__ void pool_affine_kernel(const float* __restrict__ xs, long long ldx,
   }
 }
 
+// forward_features (fv.py:949-953): the BatchNorm-ed last-level map in the reference's NCHW layout,
+// out[b][c][t] = xs[row_map[b*T + t]][c] * scale[c] + shift[c]; 32 x 32 tiles transposed through shared memory so
+// both the token-major reads and the NCHW writes are coalesced.
+__global__ void feature_map_kernel(const float* __restrict__ xs, long long ldx, const int* __restrict__ row_map,
+                                   int T, int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                                   float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (t < T && c < C) {
+      const long long row = row_map ? row_map[(long long)b * T + t] : (long long)b * T + t;
+      v = fmaf(xs[row * ldx + c], scale[c], shift[c]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < T && c < C) out[((long long)b * C + c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
+// forward_head (fv.py:955-958): AdaptiveAvgPool2d(1) + flatten of an NCHW fp32 map -> fp16 classifier operand;
+// one warp per (image, channel).
+__global__ void nchw_pool_kernel(const float* __restrict__ x, int BC, int T, int C, __half* __restrict__ out,
+                                 long long ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= BC) return;
+  const float* src = x + (long long)warp * T;
+  float a = 0.f;
+  for (int t = lane; t < T; t += 32) a += src[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[(long long)(warp / C) * ldo + warp % C] = __float2half_rn(a / T);
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -1029,6 +1067,23 @@ int fvit_pool_affine_fwd(const float* xs, int64_t ldx, const int32_t* row_map, i
   pool_affine_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(
       xs, ldx, row_map, B, T, C, scale, shift, (__half*)out, ldo);
   return post_launch("pool_affine_kernel");
+}
+
+int fvit_feature_map_fwd(const float* xs, int64_t ldx, const int32_t* row_map, int32_t B, int32_t T, int32_t C,
+                         const float* scale, const float* shift, float* out_nchw, void* stream) {
+  FVIT_CHECK(xs && scale && shift && out_nchw && B > 0 && T > 0 && C > 0 && B <= 65535,
+             "fvit_feature_map_fwd: bad arguments");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  feature_map_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(xs, ldx, row_map, T, C, scale, shift, out_nchw);
+  return post_launch("feature_map_kernel");
+}
+
+int fvit_nchw_pool_f16(const float* x, int32_t B, int32_t C, int32_t T, void* out16, int64_t ldo, void* stream) {
+  FVIT_CHECK(x && out16 && B > 0 && C > 0 && T > 0 && ldo >= C, "fvit_nchw_pool_f16: bad arguments");
+  const long long warps = (long long)B * C;
+  nchw_pool_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (int)warps, T, C,
+                                                                                           (__half*)out16, ldo);
+  return post_launch("nchw_pool_kernel");
 }
 
 }  // extern "C"

@@ -52,9 +52,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (error surfaces on the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // (try_wait suspends in hardware for a bounded time per poll; after 2^16 polls the loop backs off so that a long
+  // but legitimate wait -- profiler replay, SM time-slicing next to a collective -- cannot reach the bound: 2^24
+  // polls with back-off are many seconds)
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 21)) __trap();
+    if (++spins > (1u << 16)) {
+      __nanosleep(200);
+      if (spins > (1u << 24)) __trap();
+    }
   }
 }
 

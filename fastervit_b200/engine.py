@@ -79,7 +79,39 @@ class Plan:
         self._gemm_keep: list = []        # keeps ctypes structs alive
         self._x_args: list = []           # stem-conv calls that take the input pointer at run time
         self.op_flops: dict[int, float] = {}  # op index -> algorithmic FLOPs (GEMM launches)
+        self.marks: list[tuple[int, str, dict]] = []   # (ops issued so far, reference module name, where its output lives)
         self._build()
+
+    # ---- per-module activation taps (parity tests against the reference's forward hooks) ---------
+    def _mark(self, name: str, **where) -> None:
+        self.marks.append((len(self.ops), name, where))
+
+    def _extract(self, where: dict) -> torch.Tensor:
+        """The activation a mark points at, in the reference's layout (NCHW maps / [nW, ws*ws, C] windows)."""
+        B = self.B
+        if where["kind"] == "conv":      # zero-bordered NHWC fp32 map
+            lv = where["lv"]
+            t = lv["x32"].view(B, lv["H"] + 2, lv["W"] + 2, lv["C"])[:, 1:-1, 1:-1]
+            return t.permute(0, 3, 1, 2).contiguous()
+        tl = where["tl"]
+        if where["kind"] == "tok_map":   # window-major token buffer read through the (cropped) pixel map
+            t = tl["xs"][tl["crop_map"].long()].view(B, tl["H"], tl["W"], tl["C"])
+            return t.permute(0, 3, 1, 2).contiguous()
+        nW, S, ncw = tl["nW"], tl["S"], tl["ncw"]   # "windows": HAT block output x (fv.py:701)
+        return tl["xs"][:nW * S].view(nW, S, tl["C"])[:, ncw:].contiguous()
+
+    def debug_activations(self, x: torch.Tensor, prep: bool = True) -> dict[str, torch.Tensor]:
+        """Run the forward launch list piecewise and return {reference module name: activation} at every mark —
+        the per-module outputs the golden fixtures sample with forward hooks (oracle/make_golden.py)."""
+        if prep:
+            self.run_ops(self.prep_ops, None)
+        out, done = {}, 0
+        for upto, name, where in self.marks:
+            self.run_ops(self.ops[done:upto], x)
+            done = upto
+            out[name] = self._extract(where)
+        self.run_ops(self.ops[done:], x)
+        return out
 
     # ---- op emitters --------------------------------------------------------------------------
     def _op(self, target: list, name: str, *args) -> None:
@@ -182,6 +214,7 @@ class Plan:
                    out_f32=lvl["x32"].data_ptr(), ld_o32=lvl["C"], out_f16=lvl["x16"].data_ptr(),
                    ld_o16=lvl["ld"])
 
+        self._mark("patch_embed", kind="conv", lv=lvl)
         # ---------------- levels
         Hc, Wc, Cc = H0, W0, dim
         for i, level in enumerate(m.levels):
@@ -189,6 +222,7 @@ class Plan:
                 if i > 0:
                     lvl = self._conv_level_buffers(i, Cc, Hc, Wc)
                     self._emit_downsample_conv(i - 1, prev, lvl, to_conv=True)
+                    self._mark(f"levels.{i - 1}", kind="conv", lv=lvl)
                 self._emit_conv_blocks(i, level, lvl)
                 prev = dict(kind="conv", **lvl)
             else:
@@ -199,8 +233,11 @@ class Plan:
                     # rows are fully overwritten by the downsample GEMM / tokenizer
                     self.ops.append(("zero", tl["xs"], "memset"))
                 self._emit_downsample_conv(i - 1, prev, tl, to_conv=False)
+                self._mark(f"levels.{i - 1}", kind="tok_map", tl=tl)
                 self._emit_token_level(i, level, tl)
                 prev = dict(kind="tok", **tl)
+                if level.downsample is None:
+                    self._mark(f"levels.{i}", kind="tok_map", tl=tl)
             if level.downsample is not None:
                 Hc, Wc, Cc = (Hc + 1) // 2, (Wc + 1) // 2, Cc * 2
         # ---------------- head: BN folded into the average pool, then the classifier GEMM
@@ -210,6 +247,7 @@ class Plan:
         T = prev["H"] * prev["W"]
         pooled = nb.new("head.pooled", (B, _ru(nf, 8)), torch.float16)
         self.pooled = pooled
+        self.norm_fold = (sN, tN)
         self._op(self.ops, "fvit_pool_affine_fwd", prev["xs"].data_ptr(), nf, prev["crop_map"].data_ptr(), B, T,
                  nf, sN.data_ptr(), tN.data_ptr(), pooled.data_ptr(), pooled.stride(0))
         if isinstance(m.head, nn.Linear):
@@ -274,6 +312,7 @@ class Plan:
                        m=lv["rows"], n=Cc, kc=Cc, taps=taps, col_scale=s2.data_ptr(), col_shift=t2.data_ptr(),
                        m_alg=self.B * lv["H"] * lv["W"], resid=lv["x32"].data_ptr(), ld_resid=Cc, row_map=lv["interior"].data_ptr(),
                        out_f32=lv["x32"].data_ptr(), ld_o32=Cc, out_f16=lv["x16"].data_ptr(), ld_o16=lv["ld"])
+            self._mark(f"levels.{i}.blocks.{j}", kind="conv", lv=lv)
 
     def _emit_downsample_conv(self, i: int, src: dict, dst: dict, to_conv: bool) -> None:
         """Downsample of level i (fv.py:437-440): channel LayerNorm (eps 1e-6) scattered into parity
@@ -533,15 +572,19 @@ class Plan:
             if has_ct and blk.last and blk.do_propagation:
                 g1 = blk.gamma1.data_ptr() if isinstance(blk.gamma1, torch.Tensor) else None
                 self._op(self.ops, "fvit_propagate_fwd", xs_ptr, Cc, tl["prop_src"].data_ptr(), rows, Cc, g1)
+            self._mark(f"levels.{i}.blocks.{j}", kind="windows", tl=tl)
 
     # ---- execution --------------------------------------------------------------------------------
     def weights_key(self) -> tuple:
+        """What the packed fp16 operands of an eval plan were derived from: autograd versions (in-place torch
+        writes) plus the library-wide raw-write epoch, which the fused optimizer / EMA kernels and the train-mode
+        BatchNorm kernels bump because they update parameters through raw pointers without touching versions."""
         k = 0
         for p in self.model.parameters():
             k += p._version
         for b_ in self.model.buffers():
             k += b_._version
-        return (k,)
+        return (k, L.weights_epoch())
 
     def run_ops(self, ops: list, x: torch.Tensor | None) -> None:
         st = L.stream_ptr()
@@ -599,6 +642,24 @@ class Engine:
         self.model = model
         self.plans: dict = {}
         self._prepped: dict = {}
+        self._ptr_sig: tuple | None = None
+
+    def _check_weights(self) -> tuple:
+        """The kernels read parameters / buffers through raw pointers as dense row-major fp32 (int64 for the
+        position index): anything else (`model.half()`, `.to(memory_format=torch.channels_last)`, which re-strides
+        every 4-D conv weight and the relative-coordinate tables) would be silently mis-read. Half / bf16
+        parameters raise; non-contiguous tensors are re-laid out in place (values unchanged — memory format of the
+        weights is irrelevant to these kernels; channels_last *inputs* are consumed through their strides).
+        Returns the pointer signature the cached plans were built against."""
+        ptrs = []
+        for name, t in list(self.model.named_parameters()) + list(self.model.named_buffers()):
+            if t.is_floating_point() and t.dtype != torch.float32:
+                raise L.FvitError(f"{name} is {t.dtype}: fastervit_b200 keeps parameters and buffers in float32 (the "
+                                  "kernels form their own fp16 tensor-core operands); drop .half() / .bfloat16()")
+            if not t.is_contiguous():
+                t.data = t.data.contiguous()
+            ptrs.append(t.data_ptr())
+        return tuple(ptrs)
 
     def _plan(self, x: torch.Tensor) -> Plan:
         if not x.is_cuda:
@@ -610,6 +671,13 @@ class Engine:
         if p0.device != x.device:
             raise L.FvitError(f"model is on {p0.device} but the input is on {x.device}")
         training = self.model.training
+        sig = self._check_weights()
+        if sig != self._ptr_sig:
+            # parameters were re-allocated (.to(), .data = ..., load_state_dict(assign=True)): every cached plan
+            # holds dangling pointers
+            self.plans.clear()
+            self._prepped.clear()
+            self._ptr_sig = sig
         key = (tuple(x.shape), training, x.device.index)
         plan = self.plans.get(key)
         if plan is None:
@@ -639,28 +707,42 @@ class Engine:
                 plan.run_ops(plan.prep_ops, None)
                 self._prepped[id(plan)] = wk
             plan.run_ops(plan.ops, x)
-        if features_only or plan.logits is None:
-            # pooled features (fv.py:949-958); held as the fp16 operand of the classifier GEMM
+            if features_only:
+                # forward_features (fv.py:949-953): the BatchNorm-ed last-level map, NCHW fp32 like the reference
+                f = plan.feat
+                nf = self.model.num_features
+                out = torch.empty(plan.B, nf, f["H"], f["W"], dtype=torch.float32, device=x.device)
+                L.call("fvit_feature_map_fwd", f["xs"].data_ptr(), nf, f["crop_map"].data_ptr(), plan.B,
+                       f["H"] * f["W"], nf, plan.norm_fold[0].data_ptr(), plan.norm_fold[1].data_ptr(), out.data_ptr())
+                return out
+        if plan.logits is None:
+            # num_classes = 0: head is nn.Identity, forward returns the pooled features (fv.py:955-958)
             return plan.pooled[:, :self.model.num_features].float()
         return plan.logits.clone()
 
     def forward_head(self, feats: torch.Tensor) -> torch.Tensor:
-        """`self.head(feats)` (fv.py:960) on caller-provided pooled features, eval mode: one fvit_gemm."""
+        """avgpool + flatten + head (fv.py:955-958) on the [B, C, H, W] map `forward_features` returns (an already
+        pooled [B, C] tensor is accepted too), eval mode: pooling kernel + one fvit_gemm."""
         m = self.model
-        if not isinstance(m.head, torch.nn.Linear):
-            return feats
         if m.training and torch.is_grad_enabled():
             raise L.FvitError("forward_head is an inference helper; the autograd training path is forward()")
-        if not feats.is_cuda or feats.dim() != 2 or feats.shape[1] != m.num_features:
-            raise L.FvitError(f"forward_head expects a CUDA [B, {m.num_features}] tensor, got {tuple(feats.shape)} on "
-                              f"{feats.device}")
+        if (not feats.is_cuda or feats.dim() not in (2, 4) or feats.shape[1] != m.num_features
+                or feats.dtype != torch.float32):
+            raise L.FvitError(f"forward_head expects a CUDA float32 [B, {m.num_features}, H, W] (or pooled [B, "
+                              f"{m.num_features}]) tensor, got {tuple(feats.shape)} {feats.dtype} on {feats.device}")
+        self._check_weights()
         with torch.cuda.device(feats.device):
             nf, Bf = m.num_features, feats.shape[0]
             ld = _ru(nf, 8)
-            f32 = feats.float().contiguous()
+            f32 = feats.contiguous()
             a16 = torch.zeros(Bf, ld, dtype=torch.float16, device=feats.device)
+            if feats.dim() == 4:
+                L.call("fvit_nchw_pool_f16", f32.data_ptr(), Bf, nf, f32.shape[2] * f32.shape[3], a16.data_ptr(), ld)
+            else:
+                L.call("fvit_cast_pad_f16", f32.data_ptr(), nf, a16.data_ptr(), ld, Bf, nf, ld)
+            if not isinstance(m.head, torch.nn.Linear):
+                return a16[:, :nf].float()
             w16 = torch.zeros(m.num_classes, ld, dtype=torch.float16, device=feats.device)
-            L.call("fvit_cast_pad_f16", f32.data_ptr(), nf, a16.data_ptr(), ld, Bf, nf, ld)
             L.call("fvit_cast_pad_f16", m.head.weight.data_ptr(), nf, w16.data_ptr(), ld, m.num_classes, nf, ld)
             out = torch.empty(Bf, m.num_classes, dtype=torch.float32, device=feats.device)
             L.gemm(a16, w16, kc=nf, col_shift=m.head.bias, out_f32=out)

@@ -187,6 +187,10 @@ class TrainPlan(Plan):
 
     # ------------------------------------------------------------------------------ execution
     def run_forward(self, x: torch.Tensor) -> torch.Tensor:
+        # saved activations / batch statistics / drop masks live in this plan's persistent buffers: a new forward
+        # invalidates the state an earlier, not yet differentiated forward left behind (checked in backward)
+        self.fwd_generation = getattr(self, "fwd_generation", 0) + 1
+        L.bump_weights_epoch()   # BatchNorm running statistics are updated through raw pointers
         for t in self.fwd_zero:
             t.zero_()
         if self.drop_specs:
@@ -315,13 +319,22 @@ class _FasterViTFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan: TrainPlan, x: torch.Tensor, *params):
+        if x.requires_grad:
+            raise L.FvitError("the input requires grad, but the backward plan stops at the first convolution (no "
+                              "gradient w.r.t. the image is computed); detach the input")
         ctx.plan = plan
         logits = plan.run_forward(x)
+        ctx.generation = plan.fwd_generation
         return logits.clone()
 
     @staticmethod
     def backward(ctx, dlogits):
         plan: TrainPlan = ctx.plan
+        if ctx.generation != plan.fwd_generation:
+            raise L.FvitError(
+                "backward of a stale forward: another train-mode forward of the same input shape ran in between and "
+                "overwrote the saved activations of this one (one autograd node per step: call backward before the "
+                "next forward, or use different plans / model copies for multi-view losses)")
         plan.run_backward(dlogits.contiguous().float())
         return (None, None, *plan.grad_views())
 

@@ -122,6 +122,8 @@ _OP_SIGS: dict[str, list] = {
     "fvit_token_init_fwd": [_P, _L, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
     "fvit_propagate_fwd": [_P, _L, _P, _I, _I, _P, _P],
     "fvit_pool_affine_fwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _L, _P],
+    "fvit_feature_map_fwd": [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P],
+    "fvit_nchw_pool_f16": [_P, _I, _I, _I, _P, _L, _P],
     # optimizer step (include/fvit.h "optimizer step on the flat gradient buffer")
     "fvit_optim_gather_f32": [_P, _I, _P, _P, _P, _P],
     "fvit_optim_sqnorm": [_P, _I, _P, _P, _P, _P],
@@ -131,6 +133,20 @@ _OP_SIGS: dict[str, list] = {
     "fvit_optim_lamb_stage2": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _P],
     "fvit_optim_ema": [_P, _I, _P, _P, _F, _P],
 }
+
+
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    return _weights_epoch
+
+
+def bump_weights_epoch() -> None:
+    """Called by everything that writes parameters / buffers through raw pointers (fused optimizer and EMA steps,
+    train-mode BatchNorm running statistics): eval plans re-pack their fp16 operands when the epoch moved."""
+    global _weights_epoch
+    _weights_epoch += 1
 
 
 def check(rc: int) -> None:

@@ -287,8 +287,12 @@ class FasterViT(nn.Module):
         return self._get_engine().forward(x)
 
     def _load_state_dict(self, pretrained, strict: bool = False):
-        from .registry import load_checkpoint
-        load_checkpoint(self, pretrained, strict=strict)
+        """The reference model's own loader (fv.py:967-972 -> _load_checkpoint / _load_state_dict, fv.py:112-209):
+        tolerant by default — tensors whose shape differs from the model's (a head built for another
+        `num_classes`, positional buffers of another resolution / window) are reported and skipped, missing
+        `num_batches_tracked` counters are ignored, and only `strict=True` raises."""
+        from .registry import load_state_dict_tolerant, read_checkpoint_state
+        load_state_dict_tolerant(self, read_checkpoint_state(pretrained), strict=strict)
 
 
 def build_model(name: str, pretrained: bool = False, **kwargs) -> FasterViT:

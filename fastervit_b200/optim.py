@@ -294,6 +294,7 @@ class _FlatOptimizer(torch.optim.Optimizer):
         active = [g is not None for g in grads]
         if not any(active):
             return loss
+        L.bump_weights_epoch()   # parameters are about to change through raw pointers (no autograd version bump)
         with _device_guard(lay["dev"]):
             p_key = tuple(p.data_ptr() for p in ps)
             if p_key != lay["p_key"]:   # parameters were re-allocated (.to(), load with assign=True, ...)
@@ -463,6 +464,7 @@ class FlatEma(nn.Module):
             if len(c["plans"]) >= 4:
                 c["plans"].clear()
             plan = c["plans"][key] = self._plan(c, ev, mv, skip_params)
+        L.bump_weights_epoch()   # the EMA copy is written through raw pointers
         for t in plan["launches"]:
             with _device_guard(t["dev"]):
                 L.call("fvit_optim_ema", t["tb"].chunks.data_ptr(), t["tb"].nchunks, t["seg_e"].data_ptr(),

@@ -89,6 +89,55 @@ def load_state_dict(checkpoint_path: str, use_ema: bool = False):
     return out
 
 
+def read_checkpoint_state(filename: str):
+    """fv.py:172-209 (`_load_checkpoint`): `state_dict` / `model` / bare dict, `module.` prefix removed when the
+    first key has it, `encoder.` sub-tree selected when the sorted-first key starts with `encoder`."""
+    ckpt = torch.load(filename, map_location='cpu')
+    if not isinstance(ckpt, dict):
+        raise RuntimeError(f'No state_dict found in checkpoint file {filename}')
+    sd = ckpt['state_dict'] if 'state_dict' in ckpt else (ckpt['model'] if 'model' in ckpt else ckpt)
+    if list(sd.keys())[0].startswith('module.'):
+        sd = {k[7:]: v for k, v in sd.items()}
+    if sorted(sd.keys())[0].startswith('encoder'):
+        sd = {k.replace('encoder.', ''): v for k, v in sd.items() if k.startswith('encoder.')}
+    return sd
+
+
+def load_state_dict_tolerant(module, state_dict, strict: bool = False, logger=None):
+    """fv.py:112-168 (`_load_state_dict`): walk the module tree with `_load_from_state_dict` so that size
+    mismatches are collected as messages (and those tensors left untouched) instead of raised; the summary is
+    printed (or logged) unless `strict`, in which case it raises RuntimeError like the reference."""
+    unexpected, all_missing, err_msg = [], [], []
+    metadata = getattr(state_dict, '_metadata', None)
+    state_dict = dict(state_dict) if not isinstance(state_dict, OrderedDict) else state_dict.copy()
+    if metadata is not None:
+        state_dict._metadata = metadata
+
+    def load(mod, prefix=''):
+        local = {} if metadata is None else metadata.get(prefix[:-1], {})
+        mod._load_from_state_dict(state_dict, prefix, local, True, all_missing, unexpected, err_msg)
+        for name, child in mod._modules.items():
+            if child is not None:
+                load(child, prefix + name + '.')
+
+    load(module)
+    missing = [k for k in all_missing if 'num_batches_tracked' not in k]
+    if unexpected:
+        err_msg.append('unexpected key in source ' f'state_dict: {", ".join(unexpected)}\n')
+    if missing:
+        err_msg.append(f'missing keys in source state_dict: {", ".join(missing)}\n')
+    if err_msg:
+        err_msg.insert(0, 'The model and loaded state dict do not match exactly\n')
+        msg = '\n'.join(err_msg)
+        if strict:
+            raise RuntimeError(msg)
+        if logger is not None:
+            logger.warning(msg)
+        else:
+            print(msg)
+    return missing, unexpected
+
+
 def load_checkpoint(model, checkpoint_path: str, use_ema: bool = False, strict: bool = True):
     sd = load_state_dict(checkpoint_path, use_ema)
     return model.load_state_dict(sd, strict=strict)

@@ -239,6 +239,15 @@ int fvit_pool_affine_fwd(const float* xs, int64_t ldx, const int32_t* row_map, i
                          int32_t C, const float* scale, const float* shift, void* out, int64_t ldo,
                          void* stream);
 
+/* forward_features (faster_vit.py:949-953): the BatchNorm-ed (scale/shift folded) last-level activation in the
+ * reference's NCHW fp32 layout: out[b][c][t] = xs[row_map[b*T+t]][c] * scale[c] + shift[c]. */
+int fvit_feature_map_fwd(const float* xs, int64_t ldx, const int32_t* row_map, int32_t B, int32_t T, int32_t C,
+                         const float* scale, const float* shift, float* out_nchw, void* stream);
+
+/* forward_head (faster_vit.py:955-958): AdaptiveAvgPool2d(1) + flatten of an NCHW fp32 map into the fp16 operand
+ * [B, ldo] of the classifier GEMM. */
+int fvit_nchw_pool_f16(const float* x, int32_t B, int32_t C, int32_t T, void* out16, int64_t ldo, void* stream);
+
 /* ==== backward pass (fv.py has no backward code: the reference relies on autograd, train.py:879-896) ====
  * Activation gradients are fp16 tensors (or the fp32 residual-stream gradient) multiplied by a
  * power-of-two scale S kept in device memory, gs = {S, 1/S}; parameter gradients are fp32, un-scaled by

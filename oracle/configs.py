@@ -33,6 +33,19 @@ CASES = {
         dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 5, 6],
         ct_size=2, mlp_ratio=4, resolution=[240, 336], hat=[False, False, True, False],
         do_propagation=False, any_res=True)),
+    # any-res reduced with the larger window sequences the attention kernels special-case: S = 81 + 4 = 85 (one
+    # 128-row slot, key loop not needed) and S = 144 + 4 = 148 (BASELINE config 4's level-2 geometry: window 12,
+    # ct_size 2, non-square carrier grid) -- forward and backward
+    "tiny_ar85": ("faster_vit_0_any_res", dict(resolution=[144, 288], window_size=[7, 7, 9, 5], ct_size=2, dim=16,
+                                               in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 9, 5],
+        ct_size=2, mlp_ratio=4, resolution=[144, 288], hat=[False, False, True, False],
+        do_propagation=False, any_res=True)),
+    "tiny_ar148": ("faster_vit_0_any_res", dict(resolution=[384, 576], window_size=[7, 7, 12, 6], ct_size=2, dim=16,
+                                                in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 12, 6],
+        ct_size=2, mlp_ratio=4, resolution=[384, 576], hat=[False, False, True, False],
+        do_propagation=False, any_res=True)),
     # 21k fine-tuned family reduced (fv.py:1253-1418): no carrier tokens anywhere (hat all False), layer scale,
     # one 24 x 24 window at level 2 (S = 576: the streaming attention kernel) and 12 x 12 at level 3 (S = 144)
     "tiny_21k": ("faster_vit_4_21k_384", dict(dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(

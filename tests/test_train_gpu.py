@@ -37,7 +37,7 @@ def _sample(t, n=512):
     return f[::stride].float().cpu()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "fv0"])
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar148", "fv0", "fv4"])
 def test_train_step_matches_reference(case):
     g, tr, model, logits, loss = _run(case)
     ref = tr["logits"].to(logits.device)
@@ -50,7 +50,7 @@ def test_train_step_matches_reference(case):
         d = (_sample(sd[k]) - want["sample"]).abs().max().item()
         assert d <= 1e-3 * max(want["amax"], 1e-6) + 1e-6, (k, d)
     gmax = max(w["amax"] for w in tr["grads"].values())
-    bad = []
+    bad, l2s = [], []
     for k, p in model.named_parameters():
         want = tr["grads"][k]
         assert p.grad is not None and tuple(p.grad.shape) == tuple(want["shape"]), k
@@ -58,9 +58,32 @@ def test_train_step_matches_reference(case):
         floor = max(want["amax"], 1e-3 * gmax)
         emax = (smp - want["sample"]).abs().max().item() / floor
         el2 = (smp - want["sample"]).norm().item() / max(want["sample"].norm().item(), 1e-3 * gmax * smp.numel() ** 0.5)
+        l2s.append(el2)
         if emax > 8e-2 or el2 > 4e-2:
             bad.append((k, emax, el2))
     assert not bad, bad[:10]
+    # the ceilings above are set by a handful of ill-conditioned tensors (tiny-batch BatchNorm biases); the bulk of
+    # the gradients must sit at the fp16-operand noise floor: median relative L2 error <= 3e-3
+    med = sorted(l2s)[len(l2s) // 2]
+    print(f"{case}: {len(l2s)} gradients, median rel-L2 {med:.2e}, worst {max(l2s):.2e}")
+    assert med <= 3e-3, med
+
+
+def test_backward_of_a_stale_forward_raises():
+    """Two train-mode forwards of the same shape share the plan's saved-activation buffers: differentiating the
+    first after the second ran must raise instead of returning gradients of mixed state; so must an input that
+    requires grad (no image gradient is produced)."""
+    from fastervit_b200.lib import FvitError
+    g, tr, model, logits, loss = _run("tiny_a")
+    from oracle import fastervit_oracle as O
+    x = O.synth_input(tr["batch"], g["cfg"]["resolution"], 9, torch.float32).cuda()
+    l1 = model(x).sum()
+    l2 = model(x * 0.5).sum()
+    with pytest.raises(FvitError):
+        l1.backward()
+    l2.backward()      # the latest forward is still differentiable
+    with pytest.raises(FvitError):
+        model(x.clone().requires_grad_(True))
 
 
 def test_second_step_and_grad_accumulation_semantics():
