@@ -52,6 +52,7 @@ struct GemmParams {
   int b_ntaps, tiles_per_tap;  // >1: N tiles enumerate (tap, n tile); tap t reads B rows shifted by tap_shift[t]
   int atomic_out;  // split-K style accumulation: atomicAdd(alpha * acc) into out_f32
   int stages;
+  int cg;  // 1: one CTA per 128-row tile; 2: CTA pair (tcgen05 cta_group::2) per 256-row tile, B split over the pair
   int acc_stride, nacc;  // TMEM columns per accumulator stage and number of stages
   uint32_t idesc;
   int tap_shift[16];
@@ -190,8 +191,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // MN-major B is staged as whole 64-column atoms (the MMA reads the first tile_n columns of them)
-  const int b_stage_bytes = (p.b_mn ? ((p.tile_n + 63) & ~63) : p.tile_n) * BK * 2;
+  // CTA pair: this CTA stages its 128 rows of A and its half of the B tile; the leader issues M = 256 MMAs that
+  // read both CTAs' shared memory at the same offsets and write 128 accumulator rows into each CTA's TMEM
+  const int cg = p.cg;
+  const uint32_t cta_rank = cg == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit0 = blockIdx.x / cg, nunits = gridDim.x / cg;  // work units are dealt to CTAs / CTA pairs
+  const int b_cols = p.tile_n / cg;                            // B rows (N columns) staged by this CTA
+  // MN-major B is staged as whole 64-column atoms (the MMA reads the first b_cols columns of them)
+  const int b_stage_bytes = (p.b_mn ? ((b_cols + 63) & ~63) : b_cols) * BK * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint8_t* ctrl = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
@@ -209,13 +217,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int s = 0; s < p.nacc; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);
+      mbar_init(&acc_empty[s], 8 * cg);  // the leader's copy collects the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (cg == 2) tmem_alloc_cg2(tmem_base_slot, TMEM_COLS);
+    else tmem_alloc(tmem_base_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (cg == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -226,10 +238,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      for (int w = unit0; w < work_total; w += nunits) {
         int tm, tn, split;
         decode_work(p, w, tm, tn, split);
-        const int m0 = tm * BM;
+        const int m0 = (tm * cg + (int)cta_rank) * BM;
         int n0 = tn * p.tile_n;
         int b_shift = p.b_row_off;
         if (p.b_ntaps > 1) {
@@ -237,29 +249,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           n0 = (tn - tap * p.tiles_per_tap) * p.tile_n;
           b_shift += p.tap_shift[tap];
         }
+        n0 += (int)cta_rank * b_cols;
         const int kb0 = (int)((long long)p.num_kb * split / p.split_k);
         const int kb1 = (int)((long long)p.num_kb * (split + 1) / p.split_k);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          if (!p.a_mn) {
-            const int tap = kb / p.kb_per_tap;
-            const int kc0 = (kb - tap * p.kb_per_tap) * BK;
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], kc0, m0 + p.tap_shift[tap],
-                        p.tap_plane[tap]);
+          // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the whole pair
+          if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * cg));
+          if (cg == 1) {
+            if (!p.a_mn) {
+              const int tap = kb / p.kb_per_tap;
+              const int kc0 = (kb - tap * p.kb_per_tap) * BK;
+              tma_load_3d(sa, &tmap_a, &full_bar[stage], kc0, m0 + p.tap_shift[tap], p.tap_plane[tap]);
+            } else {
+              // A stored [K rows][M cols]: two 64-wide MN atoms of BK rows each
+              tma_load_3d(sa, &tmap_a, &full_bar[stage], m0, kb * BK + p.a_row_off, 0);
+              tma_load_3d(sa + BK * 128, &tmap_a, &full_bar[stage], m0 + 64, kb * BK + p.a_row_off, 0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
+            } else {
+              for (int j = 0; j < (b_cols + 63) / 64; ++j)
+                tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BK + b_shift);
+            }
           } else {
-            // A stored [K rows][M cols]: two 64-wide MN atoms of BK rows each
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], m0, kb * BK + p.a_row_off, 0);
-            tma_load_3d(sa + BK * 128, &tmap_a, &full_bar[stage], m0 + 64, kb * BK + p.a_row_off,
-                        0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n0);
-          } else {
-            for (int j = 0; j < (p.tile_n + 63) / 64; ++j)
-              tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BK + b_shift);
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (!p.a_mn) {
+              const int tap = kb / p.kb_per_tap;
+              const int kc0 = (kb - tap * p.kb_per_tap) * BK;
+              tma_load_3d_cg2(sa, &tmap_a, fb, kc0, m0 + p.tap_shift[tap], p.tap_plane[tap]);
+            } else {
+              tma_load_3d_cg2(sa, &tmap_a, fb, m0, kb * BK + p.a_row_off, 0);
+              tma_load_3d_cg2(sa + BK * 128, &tmap_a, fb, m0 + 64, kb * BK + p.a_row_off, 0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_cg2(sb, &tmap_b, fb, kb * BK, n0);
+            } else {
+              for (int j = 0; j < (b_cols + 63) / 64; ++j)
+                tma_load_2d_cg2(sb + j * BK * 128, &tmap_b, fb, n0 + j * 64, kb * BK + b_shift);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -281,7 +311,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t b_lbo = p.b_mn ? BK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
       const uint32_t b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
-      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      for (int w = unit0; w < work_total; w += nunits) {
         int tm_, tn_, split;
         decode_work(p, w, tm_, tn_, split);
         const int kb0 = (int)((long long)p.num_kb * split / p.split_k);
@@ -298,15 +328,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
-            umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (cg == 2) umma_f16_ss_cg2(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+          if (cg == 2) umma_commit_cg2(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (cg == 2) umma_commit_cg2(&acc_full[acc]);
+        else umma_commit(&acc_full[acc]);
         if (++acc == p.nacc) {
           acc = 0;
           acc_phase ^= 1;
@@ -359,10 +394,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const float osum_alpha = (osum && p.osum_alpha) ? __ldg(p.osum_alpha) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+    const uint32_t acc_empty_leader = cg == 2 ? mapa_shared(smem_u32(&acc_empty[0]), 0) : 0u;
+    for (int w = unit0; w < work_total; w += nunits) {
       int tm, tn, split_;
       decode_work(p, w, tm, tn, split_);
-      const int row_base = tm * BM + quad * 32;
+      const int row_base = (tm * cg + (int)cta_rank) * BM + quad * 32;
       int n0 = tn * p.tile_n;
       int n_end = min(p.n, n0 + p.tile_n);
       if (p.b_ntaps > 1) {  // output columns [tap * n, (tap + 1) * n)
@@ -625,7 +661,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // hand the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if (cg == 2) mbar_arrive_cluster(acc_empty_leader + 8u * acc);
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
@@ -644,29 +683,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();                     // role loops leave lane 0 behind: reconverge before the aligned barrier
+  if (cg == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory / TMEM until the very end
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (cg == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int pick_tile_n(int m, int n, int split_k, int b_mn, int sms) {
-  const int tiles_m = ceil_div(m, BM);
-  const int step = 16;  // MMA N granularity (MN-major B is staged in 64-column atoms, any multiple of 16 is legal)
-  (void)b_mn;
-  int best = 0;
+// Cost model for (cta_group, tile_n): waves of work units over the CTAs / CTA pairs, each unit costing its MMA time
+// (~ tile_n per K block; a pair retires a 256-row tile in the time one CTA needs for 128 rows, and its operand
+// traffic per flop is 2/3 of the single-CTA tile's) plus a fixed part for the A stream / epilogue setup.
+struct TileChoice {
+  int cg, tile_n;
+};
+static double cg2_gain() {  // relative main-loop time of the pair per 128 rows (FVIT_GEMM_CG2_GAIN to tune)
+  static double g = -1.0;
+  if (g < 0) {
+    const char* e = getenv("FVIT_GEMM_CG2_GAIN");
+    g = e ? atof(e) : 0.8;
+  }
+  return g;
+}
+static int forced_cg() {  // FVIT_GEMM_CG=1|2 forces the mode where legal (A/B experiments)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVIT_GEMM_CG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static TileChoice pick_tile(int m, int n, int split_k, int sms, int want_cg, int want_tile_n) {
+  TileChoice best{1, 16};
   double best_cost = 1e30;
-  for (int bn = step; bn <= 256; bn += step) {
-    const int tiles_n = ceil_div(n, bn);
-    const long long work = (long long)tiles_m * tiles_n * split_k;
-    const long long waves = (work + sms - 1) / sms;
-    // per-tile cost: MMA time ~ bn, plus a fixed part for the A stream / epilogue setup
-    const double cost = (double)waves * (bn + 48.0);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (want_cg && cg != want_cg) continue;
+    if (cg == 2 && m <= BM) continue;  // the second CTA of the pair would only see padding rows
+    const int tiles_m = ceil_div(m, BM * cg);
+    const int step = 16 * cg;  // each CTA of a pair stages tile_n / 2 columns of B: keep that a multiple of 16
+    for (int bn = step; bn <= 256; bn += step) {
+      if (want_tile_n > 0 && bn != want_tile_n) continue;
+      const int tiles_n = ceil_div(n, bn);
+      const long long work = (long long)tiles_m * tiles_n * split_k;
+      const int slots = sms / cg;
+      const long long waves = (work + slots - 1) / slots;
+      const double cost = (double)waves * (bn * (cg == 2 ? cg2_gain() : 1.0) + 48.0);
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best = TileChoice{cg, bn};
+      }
     }
   }
   return best;
@@ -711,10 +779,12 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
              "fvit_gemm: out_colsum needs out_f16, no BN statistics, no split-K");
 
   const int sms = num_sms();
-  int tile_n = a->tile_n;
-  if (tile_n <= 0) tile_n = pick_tile_n(a->m, a->n, split_k * b_ntaps, a->b_mn_major, sms);
-  FVIT_CHECK(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "fvit_gemm: tile_n=%d invalid",
-             tile_n);
+  int want_cg = a->cta_group == 1 || a->cta_group == 2 ? a->cta_group : forced_cg();
+  if (want_cg == 2 && (a->m <= BM || (a->tile_n > 0 && a->tile_n % 32 != 0))) want_cg = 1;
+  const TileChoice tc = pick_tile(a->m, a->n, split_k * b_ntaps, sms, want_cg, a->tile_n > 0 ? a->tile_n : 0);
+  const int tile_n = tc.tile_n, cg = tc.cg;
+  FVIT_CHECK(tile_n >= 16 && tile_n <= 256 && tile_n % (16 * cg) == 0, "fvit_gemm: tile_n=%d invalid (cta_group %d)",
+             tile_n, cg);
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -727,7 +797,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.a_row_off = a->a_row_off;
   p.b_row_off = a->b_row_off;
   p.tile_n = tile_n;
-  p.tiles_m = ceil_div(a->m, BM);
+  p.cg = cg;
+  p.tiles_m = ceil_div(a->m, BM * cg);
   p.tiles_n = ceil_div(a->n, tile_n);
   p.b_ntaps = a->b_ntaps > 1 ? a->b_ntaps : 1;
   p.tiles_per_tap = p.tiles_n;
@@ -735,7 +806,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.split_k = split_k < p.num_kb ? split_k : p.num_kb;
   if (p.split_k < 1) p.split_k = 1;
   p.atomic_out = split_k > 1 ? 1 : 0;
-  const int stage_bytes = A_STAGE_BYTES + (a->b_mn_major ? ((tile_n + 63) & ~63) : tile_n) * BK * 2;
+  const int b_cols = tile_n / cg;  // B columns staged per CTA
+  const int stage_bytes = A_STAGE_BYTES + (a->b_mn_major ? ((b_cols + 63) & ~63) : b_cols) * BK * 2;
   const int stats_bytes = a->col_sum ? SMEM_STATS_BYTES : (a->out_colsum ? 256 * 4 : 0);
   int stages = (SMEM_BUDGET - SMEM_CTRL_BYTES - SMEM_ALIGN_SLACK - SMEM_STG_BYTES - stats_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -743,7 +815,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.stages = stages;
   p.acc_stride = tile_n <= 64 ? 64 : (tile_n <= 128 ? 128 : 256);
   p.nacc = TMEM_COLS / p.acc_stride;
-  p.idesc = make_idesc_f16(BM, tile_n, p.a_mn, p.b_mn, a->bf16 ? 1u : 0u);
+  p.idesc = make_idesc_f16(BM * cg, tile_n, p.a_mn, p.b_mn, a->bf16 ? 1u : 0u);
   for (int i = 0; i < 16; ++i) {
     p.tap_shift[i] = i < (b_ntaps > 1 ? b_ntaps : a->ntaps) ? a->tap_shift[i] : 0;
     p.tap_plane[i] = i < a->ntaps ? a->tap_plane[i] : 0;
@@ -802,7 +874,7 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (!p.b_mn) {
     const uint64_t kdim = a->ntaps == 1 ? (uint64_t)a->kc : (uint64_t)p.num_kb * BK;
     rc = get_tmap(&tmb, a->b, kdim, (uint64_t)a->n, 1, (uint64_t)a->ldb * 2, 0, BK,
-                  (uint32_t)tile_n, 2);
+                  (uint32_t)b_cols, 2);
   } else {
     rc = get_tmap(&tmb, a->b, (uint64_t)a->n, (uint64_t)a->b_rows, 1, (uint64_t)a->ldb * 2, 0, 64,
                   BK, 2);
@@ -811,7 +883,8 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
 
   const int smem_bytes = stages * stage_bytes + SMEM_CTRL_BYTES + SMEM_ALIGN_SLACK + SMEM_STG_BYTES + stats_bytes;
   const long long work = (long long)p.tiles_m * p.tiles_n * p.split_k;
-  const int grid = (int)(work < sms ? work : sms);
+  const int slots = sms / cg;
+  const int grid = (int)(work < slots ? work : slots) * cg;
   // feature mask of this call; launch the matching specialisation if one was instantiated
   uint32_t feat = ((uint32_t)a->act << EF_ACT_SHIFT);
   if (a->resid && !p.atomic_out) feat |= EF_RESID;
@@ -834,7 +907,15 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
       FVIT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));  \
       attr_set = true;                                                                                 \
     }                                                                                                  \
-    kfn<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tma, tmb, p);                        \
+    cudaLaunchConfig_t cfg;                                                                            \
+    memset(&cfg, 0, sizeof(cfg));                                                                      \
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(GEMM_THREADS);                             \
+    cfg.dynamicSmemBytes = (size_t)smem_bytes, cfg.stream = (cudaStream_t)stream;                      \
+    cudaLaunchAttribute attr[1];                                                                       \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                  \
+    attr[0].val.clusterDim.x = (unsigned)cg, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1; \
+    cfg.attrs = attr, cfg.numAttrs = cg == 2 ? 1 : 0;                                                  \
+    FVIT_CUDA(cudaLaunchKernelEx(&cfg, kfn, tma, tmb, p));                                             \
     return post_launch("gemm_tcgen05_kernel");                                                         \
   } while (0)
 #define FVIT_ACTF(x) ((uint32_t)(x) << EF_ACT_SHIFT)

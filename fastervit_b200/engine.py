@@ -92,13 +92,13 @@ class Plan:
         if where["kind"] == "conv":      # zero-bordered NHWC fp32 map
             lv = where["lv"]
             t = lv["x32"].view(B, lv["H"] + 2, lv["W"] + 2, lv["C"])[:, 1:-1, 1:-1]
-            return t.permute(0, 3, 1, 2).contiguous()
+            return t.permute(0, 3, 1, 2).clone()
         tl = where["tl"]
         if where["kind"] == "tok_map":   # window-major token buffer read through the (cropped) pixel map
             t = tl["xs"][tl["crop_map"].long()].view(B, tl["H"], tl["W"], tl["C"])
-            return t.permute(0, 3, 1, 2).contiguous()
+            return t.permute(0, 3, 1, 2).clone()
         nW, S, ncw = tl["nW"], tl["S"], tl["ncw"]   # "windows": HAT block output x (fv.py:701)
-        return tl["xs"][:nW * S].view(nW, S, tl["C"])[:, ncw:].contiguous()
+        return tl["xs"][:nW * S].view(nW, S, tl["C"])[:, ncw:].clone()   # (a copy: xs is rewritten by the next block)
 
     def debug_activations(self, x: torch.Tensor, prep: bool = True) -> dict[str, torch.Tensor]:
         """Run the forward launch list piecewise and return {reference module name: activation} at every mark —

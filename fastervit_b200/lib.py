@@ -42,7 +42,7 @@ class GemmArgs(C.Structure):
         ("out_pre16", C.c_void_p), ("ld_out_pre16", C.c_int64),
         ("out_colsum", C.c_void_p), ("out_colsum_alpha", C.c_void_p),
         ("aux_scale", C.c_void_p), ("aux_shift", C.c_void_p),
-        ("pre_is_grad", C.c_int32),
+        ("pre_is_grad", C.c_int32), ("cta_group", C.c_int32),
     ]
 
 
@@ -179,7 +179,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
          col_scale=None, col_shift=None, col_scale2=None, aux=None, resid=None, row_map=None,
          out_f32=None, out_f16=None, col_sum=None, col_sumsq=None, alpha_ptr=None, row_scale=None,
          out_pre16=None, out_colsum=None, out_colsum_alpha=None, aux_scale=None,
-         aux_shift=None, pre_is_grad: bool = False) -> None:
+         aux_shift=None, pre_is_grad: bool = False, cta_group: int = 0) -> None:
     """Thin functional wrapper over fvit_gemm for 2-D (strided) torch tensors.
 
     K-major operands are [rows, K] tensors, MN-major operands are [K, rows] tensors; only the row
@@ -239,6 +239,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int | None = None, n: int | Non
     g.out_colsum, g.out_colsum_alpha = ptr(out_colsum), ptr(out_colsum_alpha)
     g.aux_scale, g.aux_shift = ptr(aux_scale), ptr(aux_shift)
     g.pre_is_grad = 1 if pre_is_grad else 0
+    g.cta_group = cta_group
     check(lib.fvit_gemm(C.byref(g), stream_ptr()))
 
 

@@ -118,6 +118,8 @@ typedef struct fvit_gemm_args {
   const float* aux_shift; /* convolution output, scale/shift = that BatchNorm's batch-statistics affine) */
   int32_t pre_is_grad;    /* with act == FVIT_ACT_GELU and out_pre16: store gelu'(v) there instead of v, so the
                              backward GEMM's epilogue is a plain multiply (FVIT_ACT_MUL_AUX) */
+  int32_t cta_group;      /* 0 = chosen by the library; 1 = one CTA per 128-row tile; 2 = CTA pair per 256-row tile
+                             (tcgen05 cta_group::2, each CTA stages half of the B tile; needs m > 128) */
 } fvit_gemm_args;
 
 int fvit_gemm(const fvit_gemm_args* args, void* stream);

@@ -313,3 +313,125 @@ def test_gemm_output_column_sums(m, n):
     p = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(p).sum().backward()
     assert _rel(o16, (a.float() @ b.float()) * p.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CTA-pair mode (tcgen05 cta_group::2): 256-row tiles, each CTA of the pair stages half of the B tile. Same
+# contract as the single-CTA kernel, forced with cta_group=2.
+@pytest.mark.parametrize("m,n,k", [(256, 64, 64), (300, 200, 136), (1000, 1000, 520), (129, 784, 200), (4096, 768, 256),
+                                   (53 * 512, 784, 784), (128 * 37 + 5, 3136, 392)])
+def test_gemm_pair_nt_plain(m, n, k):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = torch.randn(n, k, device="cuda", generator=g).half()
+    out = torch.full((m, n), float("nan"), device="cuda")
+    lib.gemm(a, b, out_f32=out, cta_group=2)
+    assert _rel(out, a.float() @ b.float().t()) < 2e-5
+
+
+@pytest.mark.parametrize("tile_n", [32, 96, 160, 224, 256])
+def test_gemm_pair_tile_n(tile_n):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(tile_n)
+    m, n, k = 777, 400, 264
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = torch.randn(n, k, device="cuda", generator=g).half()
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(a, b, out_f32=out, tile_n=tile_n, cta_group=2)
+    assert _rel(out, a.float() @ b.float().t()) < 2e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("m,n,k,tile_n", [(520, 392, 1000, 0), (784, 200, 3000, 0), (300, 392, 1000, 96), (300, 392, 1000, 224)])
+def test_gemm_pair_mn_major(a_mn, b_mn, m, n, k, tile_n):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    A = torch.randn(m, k, device="cuda", generator=g).half()
+    B = torch.randn(n, k, device="cuda", generator=g).half()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = torch.zeros(m, n, device="cuda")
+    lib.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_f32=out, tile_n=tile_n, cta_group=2)
+    assert _rel(out, A.float() @ B.float().t()) < 2e-5
+
+
+def test_gemm_pair_epilogue_stats_and_split_k():
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    m, n, k = 1000, 328, 256
+    a = (torch.randn(m, k, device="cuda", generator=g) * 0.2).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.2).half()
+    cs = torch.rand(n, device="cuda", generator=g) + 0.5
+    sh = torch.randn(n, device="cuda", generator=g)
+    cs2 = torch.rand(n, device="cuda", generator=g) + 0.5
+    perm = torch.randperm(m, device="cuda", generator=g).int()
+    perm[::17] = -1
+    resid = torch.randn(m, n, device="cuda", generator=g)
+    o32 = torch.full((m, n), 7.0, device="cuda")
+    o16 = torch.full((m, n), 7.0, device="cuda").half()
+    lib.gemm(a, b, alpha=0.5, col_scale=cs, col_shift=sh, act=lib.ACT_GELU, col_scale2=cs2, resid=resid, row_map=perm,
+             out_f32=o32, out_f16=o16, cta_group=2)
+    val = torch.nn.functional.gelu((a.float() @ b.float().t()) * 0.5 * cs + sh) * cs2
+    ref = torch.full((m, n), 7.0, device="cuda")
+    keep = perm >= 0
+    idx = perm[keep].long()
+    ref[idx] = val[keep] + resid[idx]
+    assert _rel(o32, ref) < 2e-5 and _rel(o16, ref) < 1e-3
+    # BatchNorm statistics in the epilogue
+    rm = torch.arange(m, device="cuda").int()
+    rm[5::9] = -1
+    s1, s2 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lib.gemm(a, b, col_shift=sh, row_map=rm, out_f16=o16, col_sum=s1, col_sumsq=s2, cta_group=2)
+    v = (a.float() @ b.float().t() + sh)[rm >= 0]
+    assert _rel(s1, v.sum(0)) < 1e-4 and _rel(s2, (v * v).sum(0)) < 1e-4
+    # split-K atomics, MN-major operands, B row offset
+    kk = 5000
+    A = torch.randn(kk, 256, device="cuda", generator=g).half()
+    B = torch.randn(kk, 192, device="cuda", generator=g).half()
+    out = torch.zeros(256, 192, device="cuda")
+    lib.gemm(A, B, a_mn=True, b_mn=True, split_k=16, alpha=0.25, out_f32=out, cta_group=2)
+    assert _rel(out, 0.25 * (A.float().t() @ B.float())) < 1e-4
+
+
+@pytest.mark.parametrize("cout,cin,k,sk", [(392, 392, 3000, 4), (196, 196, 9000, 16), (640, 320, 700, 2)])
+def test_gemm_pair_taps_in_n_weight_gradient(cout, cin, k, sk):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(k, (cin + 7) // 8 * 8, device="cuda", generator=g).half()[:, :cin]
+    dz = torch.randn(k, (cout + 7) // 8 * 8, device="cuda", generator=g).half()[:, :cout]
+    shifts = [-31, -30, -29, -1, 0, 1, 29, 30, 31]
+    out = torch.zeros(cout, 9 * cin, device="cuda")
+    lib.gemm(dz, x, a_mn=True, b_mn=True, b_taps=shifts, split_k=sk, alpha=0.5, out_f32=out, cta_group=2)
+    ref = torch.zeros_like(out)
+    for t, off in enumerate(shifts):
+        xs = torch.zeros_like(x)
+        if off >= 0:
+            xs[: k - off] = x[off:]
+        else:
+            xs[-off:] = x[: k + off]
+        ref[:, t * cin:(t + 1) * cin] = 0.5 * (dz.float().t() @ xs.float())
+    assert _rel(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 14), (196, 208, 9), (128, 256, 28)])
+def test_gemm_pair_conv3x3_taps(cin, cout, hw):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(cin + hw)
+    bsz, H, W = 3, hw, hw + 2
+    Hp, Wp = H + 2, W + 2
+    ld = (cin + 7) // 8 * 8
+    x = torch.randn(bsz, cin, H, W, device="cuda", generator=g).half()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05).half()
+    xp = torch.zeros(bsz, Hp, Wp, ld, device="cuda", dtype=torch.half)
+    xp[:, 1:-1, 1:-1, :cin] = x.permute(0, 2, 3, 1)
+    a = xp.view(-1, ld)[:, :cin]
+    kc_pad = (cin + 63) // 64 * 64
+    wp = torch.zeros(cout, 9, kc_pad, device="cuda", dtype=torch.half)
+    wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    taps = [((dy - 1) * Wp + (dx - 1), 0) for dy in range(3) for dx in range(3)]
+    out = torch.zeros(bsz * Hp * Wp, cout, device="cuda")
+    lib.gemm(a, wp.view(cout, 9 * kc_pad), kc=cin, taps=taps, out_f32=out, cta_group=2)
+    got = out.view(bsz, Hp, Wp, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(x.float().cpu(), w.float().cpu(), padding=1).cuda()
+    assert _rel(got, ref) < 2e-5

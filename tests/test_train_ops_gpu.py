@@ -15,8 +15,20 @@ def _close(got, ref, rel, what=""):
     assert d <= rel * max(ref.abs().max().item(), 1e-6), (what, d, ref.abs().max().item())
 
 
+_KEEP = []   # device copies handed to the C ABI by raw pointer must outlive the launch (and the allocator's reuse)
+
+
 def _scalar(v):
-    return torch.tensor([v], dtype=torch.float32, device="cuda")
+    t = torch.tensor([v], dtype=torch.float32, device="cuda")
+    _KEEP.append(t)
+    return t
+
+
+def _dev(t):
+    """device pointer of a CUDA copy of t that stays alive until the end of the test module"""
+    c = t.cuda().contiguous()
+    _KEEP.append(c)
+    return c.data_ptr()
 
 
 @pytest.mark.parametrize("rows,C", [(212, 256), (53, 784), (1000, 64), (96, 1568), (37, 24)])
@@ -51,8 +63,8 @@ def test_ln_bwd_matches_autograd(rows, C, mapped):
     dgam = torch.zeros(C, device="cuda")
     dbet = torch.zeros(C, device="cuda")
     in_map = dest.to(torch.int32).cuda() if mapped else None
-    L.call("fvit_ln_bwd", dy16.cuda().data_ptr(), C, None, xhat16.cuda().data_ptr(), C, rstd.float().flatten().cuda().data_ptr(),
-           gamma.float().cuda().data_ptr(), rows, C, gbuf.data_ptr(), C, L.ptr(in_map), 1, 1 if mapped else 0,
+    L.call("fvit_ln_bwd", _dev(dy16), C, None, _dev(xhat16), C, _dev(rstd.float().flatten()),
+           _dev(gamma.float()), rows, C, gbuf.data_ptr(), C, L.ptr(in_map), 1, 1 if mapped else 0,
            _scalar(scal).data_ptr(), dgam.data_ptr(), dbet.data_ptr())
     torch.cuda.synchronize()
     _close(gbuf, want, 2e-5, "g")
@@ -100,11 +112,11 @@ def test_bn_bwd_matches_autograd(rows, C, act, g_is_f16):
     out16 = torch.zeros(rows + pad, C, dtype=torch.float16, device="cuda")
     s1, s2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dw, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    L.call("fvit_bn_bwd", gin.cuda().data_ptr(), g_is_f16, C, g_rows.cuda().data_ptr(), raw16.cuda().data_ptr(), C,
-           r_rows.cuda().data_ptr(), rows, C, mean.detach().float().cuda().data_ptr(), rstd.detach().float().cuda().data_ptr(),
-           w.cuda().data_ptr(), b.cuda().data_ptr(), act, colmul.cuda().data_ptr(), s1.data_ptr(), s2.data_ptr(),
-           _scalar(scal).data_ptr(), out16.data_ptr(), C, o_rows.cuda().data_ptr(), dw.data_ptr(), db.data_ptr(),
-           rsc.cuda().data_ptr())
+    L.call("fvit_bn_bwd", _dev(gin), g_is_f16, C, _dev(g_rows), _dev(raw16), C,
+           _dev(r_rows), rows, C, _dev(mean.detach().float()), _dev(rstd.detach().float()),
+           _dev(w), _dev(b), act, _dev(colmul), s1.data_ptr(), s2.data_ptr(),
+           _scalar(scal).data_ptr(), out16.data_ptr(), C, _dev(o_rows), dw.data_ptr(), db.data_ptr(),
+           _dev(rsc))
     torch.cuda.synchronize()
     _close(out16[o_rows.long().cuda()], xr.grad, 2e-3, "dx")
     _close(dw, scal * wd.grad, 2e-4, "dw")
@@ -130,9 +142,9 @@ def test_affine_rows_matches_torch(rows, C, act):
     ref = v * rsc.double().view(-1, 1) + resid.double()
     o32 = torch.zeros(total, C, device="cuda")
     o16 = torch.zeros(total, C, dtype=torch.float16, device="cuda")
-    L.call("fvit_affine_rows", x16.cuda().data_ptr(), C, rowsel.cuda().data_ptr(), rows, C, scale.cuda().data_ptr(),
-           shift.cuda().data_ptr(), act, resid.cuda().data_ptr(), C, o32.data_ptr(), C, o16.data_ptr(), C,
-           rsc.cuda().data_ptr())
+    L.call("fvit_affine_rows", _dev(x16), C, _dev(rowsel), rows, C, _dev(scale),
+           _dev(shift), act, _dev(resid), C, o32.data_ptr(), C, o16.data_ptr(), C,
+           _dev(rsc))
     torch.cuda.synchronize()
     sel = rowsel.long()
     _close(o32[sel.cuda()], ref[sel], 2e-6 if act != 2 else 2e-6 + 3e-7, "out32")   # A-S erf: |error| < 1.5e-7 absolute
@@ -154,8 +166,8 @@ def test_colsum_matches_torch(a_is_f16):
     colmul = torch.rand(C, generator=g) + 0.5
     rsc = torch.rand(rows, generator=g)
     out = torch.full((C,), 2.0, device="cuda")
-    L.call("fvit_colsum", a.cuda().data_ptr(), a_is_f16, C, a_rows.cuda().data_ptr(), b16.cuda().data_ptr(), C, rows, C,
-           colmul.cuda().data_ptr(), _scalar(0.5).data_ptr(), out.data_ptr(), rsc.cuda().data_ptr())
+    L.call("fvit_colsum", _dev(a), a_is_f16, C, _dev(a_rows), _dev(b16), C, rows, C,
+           _dev(colmul), _scalar(0.5).data_ptr(), out.data_ptr(), _dev(rsc))
     torch.cuda.synchronize()
     ref = 2.0 + 0.5 * colmul.double() * (a[a_rows.long()].double() * b16.double() * rsc.double().view(-1, 1)).sum(0)
     _close(out, ref, 1e-4, "colsum")
@@ -181,8 +193,8 @@ def test_propagate_bwd_matches_autograd():
     y.backward(gbuf.double())
     gb = gbuf.clone().cuda()
     dgam = torch.zeros(C, device="cuda")
-    L.call("fvit_propagate_bwd", gb.data_ptr(), C, xs.cuda().data_ptr(), C, src.cuda().data_ptr(), rows, C,
-           gamma.cuda().data_ptr(), _scalar(2.0).data_ptr(), dgam.data_ptr())
+    L.call("fvit_propagate_bwd", gb.data_ptr(), C, _dev(xs), C, _dev(src), rows, C,
+           _dev(gamma), _scalar(2.0).data_ptr(), dgam.data_ptr())
     torch.cuda.synchronize()
     _close(gb, xd.grad, 1e-5, "g")
     _close(dgam, 2.0 * gm.grad, 1e-4, "dgamma")
@@ -215,8 +227,8 @@ def test_token_init_bwd_matches_autograd():
     ct_rows = (npix + torch.arange(B * oh * ow)).to(torch.int32).cuda()
     dw = torch.zeros(C, 9, device="cuda")
     db = torch.zeros(C, device="cuda")
-    L.call("fvit_token_init_bwd", gbuf.data_ptr(), C, x16.cuda().data_ptr(), C, pix_map.data_ptr(), ct_rows.data_ptr(), B, Hp, Wp,
-           C, w.cuda().data_ptr(), kh, kw, sh, sw, oh, ow, _scalar(0.5).data_ptr(), gbuf.data_ptr(), C, dw.data_ptr(),
+    L.call("fvit_token_init_bwd", gbuf.data_ptr(), C, _dev(x16), C, pix_map.data_ptr(), ct_rows.data_ptr(), B, Hp, Wp,
+           C, _dev(w), kh, kw, sh, sw, oh, ow, _scalar(0.5).data_ptr(), gbuf.data_ptr(), C, dw.data_ptr(),
            db.data_ptr())
     torch.cuda.synchronize()
     want_pix = gpix0.double() + xd.grad.permute(0, 2, 3, 1).reshape(npix, C)
