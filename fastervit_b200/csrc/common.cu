@@ -55,8 +55,19 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int encode_tmap_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                             CUtensorMapDataType dtype);
+
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  // FLOAT16 covers fp16 and bf16 alike for a tiled copy (no arithmetic on the elements).
+  return encode_tmap_typed(out, base, rank, dims, strides_bytes, box, swz, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+}
+
+static int encode_tmap_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                             CUtensorMapDataType dtype) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -76,8 +87,7 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
                          (unsigned long long)gstr[i - 1], i);
     }
   }
-  // FLOAT16 covers fp16 and bf16 alike for a tiled copy (no arithmetic on the elements).
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base),
                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -92,7 +102,7 @@ struct TmapKey {
   const void* base;
   uint64_t d[3], s[2];
   uint32_t b[3];
-  int rank, swz;
+  int rank, swz, esize;
   bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -108,11 +118,23 @@ std::mutex g_tmap_mu;
 std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 }  // namespace
 
+static int cached_tmap_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz, int esize);
+
 int cached_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  return cached_tmap_typed(out, base, rank, dims, strides_bytes, box, swz, 2);
+}
+int cached_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  return cached_tmap_typed(out, base, rank, dims, strides_bytes, box, swz, 4);
+}
+
+static int cached_tmap_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz, int esize) {
   TmapKey key;
   std::memset(&key, 0, sizeof(key));  // padding bytes take part in the memcmp
-  key.base = base, key.rank = rank, key.swz = (int)swz;
+  key.base = base, key.rank = rank, key.swz = (int)swz, key.esize = esize;
   for (int i = 0; i < rank && i < 3; ++i) {
     key.d[i] = dims[i];
     key.b[i] = box[i];
@@ -126,7 +148,8 @@ int cached_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
       return 0;
     }
   }
-  int rc = encode_tmap_16bit(out, base, rank, dims, strides_bytes, box, swz);
+  int rc = encode_tmap_typed(out, base, rank, dims, strides_bytes, box, swz,
+                             esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   if (rc) return rc;
   std::lock_guard<std::mutex> g(g_tmap_mu);
   if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();

@@ -47,6 +47,10 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
 int cached_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
+// fp32 elements (relative-position bias tiles of the key-loop attention kernel)
+int cached_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

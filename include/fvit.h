@@ -197,6 +197,15 @@ int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, 
 int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
                      const float* bias, float scale, void* out, int64_t ldo, void* stream);
 
+/* Key-loop tensor-core attention core for window sequences longer than one 128-row tile (any-res level 2:
+ * S = 12*12 + 4 = 148, faster_vit_any_res.py:805-817; 21k windows S = 196 .. 2304, faster_vit.py:1253-1418):
+ * work item = (window, head, 128 query rows); key tiles of 128 are visited twice (row maxima, then probabilities and
+ * O += P V in TMEM). Same qkv / out layout as fvit_attn_tc_fwd; bias [heads, S, S] fp32 is staged by TMA, so
+ * S % 4 == 0 is required when a bias is given. lse (optional, [groups*S, heads] fp32) receives the log2-domain
+ * log-sum-exp of the scaled, biased scores (saved for the backward pass). */
+int fvit_attn_loop_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
+                       const float* bias, float scale, void* out, int64_t ldo, float* lse, void* stream);
+
 /* ---- training-mode BatchNorm2d (batch statistics; fv.py:459-462, 490-493, 925 under module.train()) ----
  * fvit_colstats_f32: sum[c] += sum_r x[rows[r]][c]; sumsq likewise (fp32 input, optional row list).
  * fvit_bn_finalize : from (sum, sumsq, count) -> biased var for normalisation, running statistics

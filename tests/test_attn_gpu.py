@@ -42,6 +42,37 @@ def test_attn_tc_matches_torch(S, heads, hd, groups, with_bias):
     assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("S,heads,hd,groups", [(148, 8, 32, 30), (148, 8, 32, 480), (196, 16, 49, 8), (144, 4, 24, 5),
+                                               (256, 2, 64, 3), (576, 4, 49, 2), (1024, 2, 49, 1), (2304, 1, 49, 1),
+                                               (132, 3, 32, 7)])
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_attn_loop_matches_torch(S, heads, hd, groups, with_bias):
+    """Key-loop tensor-core attention (S > 128): the any-res level-2 geometry (S = 148, BASELINE config 4) and the
+    21k windows, against fp32 torch on the same fp16 operands; also the saved log-sum-exp vector."""
+    from fastervit_b200 import lib
+    lib.load()
+    hdp = 32 if hd <= 32 else 64
+    g = torch.Generator(device="cuda").manual_seed(S * 131 + heads)
+    qkv = torch.zeros(groups * S, 3, heads, hdp, device="cuda")
+    qkv[..., :hd] = torch.randn(groups * S, 3, heads, hd, device="cuda", generator=g)
+    qkv = qkv.reshape(groups * S, 3 * heads * hdp).half()
+    bias = (torch.randn(heads, S, S, device="cuda", generator=g) * 2 + 4) if with_bias else None
+    out = torch.full((groups * S, heads * hdp), float("nan"), device="cuda", dtype=torch.half)
+    lse = torch.full((groups * S, heads), float("nan"), device="cuda")
+    scale = hd ** -0.5
+    lib.call("fvit_attn_loop_fwd", qkv.data_ptr(), qkv.stride(0), groups, S, heads, hdp,
+             bias.data_ptr() if with_bias else None, scale, out.data_ptr(), out.stride(0), lse.data_ptr())
+    torch.cuda.synchronize()
+    ref = _ref(qkv, groups, S, heads, hd, hdp, bias, scale)
+    assert torch.isfinite(out.float()).all()
+    err = ((out.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 2e-3, err
+    q, k, _ = qkv.float().view(groups, S, 3, heads, hdp)[..., :hd].permute(2, 0, 3, 1, 4)
+    attn = (q @ k.transpose(-2, -1)) * scale + (bias[None] if with_bias else 0.0)
+    want = torch.logsumexp(attn, -1).permute(0, 2, 1).reshape(groups * S, heads) * 1.4426950408889634
+    assert (lse - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
+
+
 # the last four exceed one CTA's shared memory as a full S x S score matrix and take the streaming (key-tiled,
 # running max / sum) kernel: the windows of the 21k fine-tuned models (fv.py:1253-1418) and ragged tails
 @pytest.mark.parametrize("S,heads,hd,groups", [(53, 8, 32, 7), (148, 8, 32, 3), (53, 4, 49, 5), (196, 16, 49, 2),
