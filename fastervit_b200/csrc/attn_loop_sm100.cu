@@ -398,3 +398,383 @@ extern "C" int fvit_attn_loop_fwd(const void* qkv, int64_t ldq, int32_t groups, 
   if (hdp == 64) return launch_attn_loop<64>(tq, tb, p, (cudaStream_t)stream);
   return launch_attn_loop<32>(tq, tb, p, (cudaStream_t)stream);
 }
+
+// =====================================================================================================
+// fvit_attn_loop_bwd: tensor-core backward of the attention core for 128 < S <= 256 (two query / key tiles).
+// Work item = (window, head). With lse (forward) and delta = rowsum(dO * O) per query row:
+//   for key tile j:  for query tile i:
+//       S = Q_i K_j^T, dP = dO_i V_j^T                        (tcgen05, TMEM columns [0,128) / [128,256))
+//       P = exp2(S*scale*log2e + bias*log2e - lse), dS = P*(dP - delta)   (one thread per query row; fp16 tiles in
+//           shared memory; dS accumulated into dbias with 16-byte reductions)
+//       dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j    (TMEM accumulators: dV, dK per key tile, dQ_0 / dQ_1
+//           across the key loop — all 512 columns are in use)
+//   dV_j, dK_j are written after the query loop, dQ_i after the key loop. Nothing but q, k, v, dO, O, lse is read
+// from HBM and nothing but dq, dk, dv (+ the dbias reductions) is written.
+namespace fvit {
+
+struct AttnLoopBwdParams {
+  int groups, S, heads, nt;
+  float scale, scale_log2e;
+  const float* bias;
+  float* dbias;
+  const float* lse;
+  const __half* dout;
+  long long lddo;
+  const __half* out;
+  long long ldo;
+  __half* dqkv;
+  long long lddq;
+};
+
+template <int HDP>
+__global__ void __launch_bounds__(AL_THREADS, 1)
+    attn_loop_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                         const __grid_constant__ AttnLoopBwdParams p) {
+  constexpr uint32_t SWZ = HDP == 64 ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t ROW_BYTES = HDP * 2;
+  constexpr uint32_t SBO_QKV = 8 * ROW_BYTES;
+  constexpr int TILE_BYTES = AL_ROWS * HDP * 2;
+  constexpr int QDO_OFF = 0;                      // Q_0, dO_0, Q_1, dO_1
+  constexpr int KV_OFF = 4 * TILE_BYTES;          // 2 stages of (K_j, V_j)
+  constexpr int P_OFF = KV_OFF + 4 * TILE_BYTES;
+  constexpr int DS_OFF = P_OFF + AL_ROWS * 128 * 2;
+  constexpr int CTRL_OFF = DS_OFF + AL_ROWS * 128 * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, nt = p.nt;
+  uint64_t* qdo_full = reinterpret_cast<uint64_t*>(smem + CTRL_OFF);
+  uint64_t* qdo_empty = qdo_full + 1;
+  uint64_t* kv_full = qdo_empty + 1;   // [2]
+  uint64_t* kv_empty = kv_full + 2;    // [2]
+  uint64_t* sdp_full = kv_empty + 2;
+  uint64_t* sdp_empty = sdp_full + 1;
+  uint64_t* pds_full = sdp_empty + 1;
+  uint64_t* pds_empty = pds_full + 1;
+  uint64_t* dkv_full = pds_empty + 1;
+  uint64_t* dkv_empty = dkv_full + 1;
+  uint64_t* dq_full = dkv_empty + 1;
+  uint64_t* dq_empty = dq_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(qdo_full, 1), mbar_init(qdo_empty, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4);
+    mbar_init(pds_full, 4), mbar_init(pds_empty, 1);
+    mbar_init(dkv_full, 1), mbar_init(dkv_empty, 4);
+    mbar_init(dq_full, 1), mbar_init(dq_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320;
+  const uint32_t tDQ[2] = {tmem_base + 384, tmem_base + 448};
+
+  const int items = p.groups * p.heads;
+  // head-major item order: the CTAs running side by side reduce into the same dbias[head] lines of L2
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, kv_cnt = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        const int grp = w % p.groups, head = w / p.groups;
+        const int row0 = grp * S;
+        mbar_wait(qdo_empty, (it & 1) ^ 1);
+        mbar_expect_tx(qdo_full, (uint32_t)(2 * nt * TILE_BYTES));
+        for (int i = 0; i < nt; ++i) {
+          tma_load_2d(smem + QDO_OFF + (2 * i) * TILE_BYTES, &tmap_qkv, qdo_full, head * HDP, row0 + i * 128);
+          tma_load_2d(smem + QDO_OFF + (2 * i + 1) * TILE_BYTES, &tmap_do, qdo_full, head * HDP, row0 + i * 128);
+        }
+        for (int j = 0; j < nt; ++j, ++kv_cnt) {
+          const int st = kv_cnt & 1;
+          mbar_wait(&kv_empty[st], ((kv_cnt >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          tma_load_2d(smem + KV_OFF + (2 * st) * TILE_BYTES, &tmap_qkv, &kv_full[st], (p.heads + head) * HDP, row0 + j * 128);
+          tma_load_2d(smem + KV_OFF + (2 * st + 1) * TILE_BYTES, &tmap_qkv, &kv_full[st], (2 * p.heads + head) * HDP,
+                      row0 + j * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_ss = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t id_tn = make_idesc_f16(128, HDP, 1, 1);  // A = P / dS read MN-major (M = keys), B MN-major
+      const uint32_t id_dq = make_idesc_f16(128, HDP, 0, 1);
+      const uint32_t sP = smem_u32(smem + P_OFF), sDS = smem_u32(smem + DS_OFF);
+      uint32_t it = 0, kv_cnt = 0, pair = 0, jcnt = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        mbar_wait(qdo_full, it & 1);
+        mbar_wait(dq_empty, (it & 1) ^ 1);  // previous item's dQ accumulators have been read out
+        for (int j = 0; j < nt; ++j, ++kv_cnt, ++jcnt) {
+          const int st = kv_cnt & 1;
+          mbar_wait(&kv_full[st], (kv_cnt >> 1) & 1);
+          const uint32_t sK = smem_u32(smem + KV_OFF + (2 * st) * TILE_BYTES), sV = sK + TILE_BYTES;
+          for (int i = 0; i < nt; ++i, ++pair) {
+            const uint32_t sQ = smem_u32(smem + QDO_OFF + (2 * i) * TILE_BYTES), sDO = sQ + TILE_BYTES;
+            mbar_wait(sdp_empty, (pair & 1) ^ 1);  // the softmax warps have read the previous pair's S / dP
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < HDP / 16; ++k)
+              umma_f16_ss(tS, make_smem_desc(sQ + k * 32, 16, SBO_QKV, SWZ), make_smem_desc(sK + k * 32, 16, SBO_QKV, SWZ), id_ss,
+                          k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < HDP / 16; ++k)
+              umma_f16_ss(tDP, make_smem_desc(sDO + k * 32, 16, SBO_QKV, SWZ), make_smem_desc(sV + k * 32, 16, SBO_QKV, SWZ), id_ss,
+                          k > 0 ? 1u : 0u);
+            umma_commit(sdp_full);
+            mbar_wait(pds_full, pair & 1);
+            if (i == 0) mbar_wait(dkv_empty, (jcnt & 1) ^ 1);  // previous key tile's dV / dK have been read out
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows in steps of 16
+              const uint64_t aP = make_smem_desc(sP + ks * 2048, AL_ROWS * 128, 1024, SWZ_128B);
+              const uint64_t aDS = make_smem_desc(sDS + ks * 2048, AL_ROWS * 128, 1024, SWZ_128B);
+              const uint64_t bDO = make_smem_desc(sDO + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
+              const uint64_t bQ = make_smem_desc(sQ + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
+              umma_f16_ss(tDV, aP, bDO, id_tn, (i > 0 || ks > 0) ? 1u : 0u);
+              umma_f16_ss(tDK, aDS, bQ, id_tn, (i > 0 || ks > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // K = 128 keys
+              const uint64_t aDS = make_smem_desc(sDS + (ks >> 2) * (AL_ROWS * 128) + (ks & 3) * 32, 16, 1024, SWZ_128B);
+              const uint64_t bK = make_smem_desc(sK + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
+              umma_f16_ss(tDQ[i], aDS, bK, id_dq, (j > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(pds_empty);
+          }
+          umma_commit(dkv_full);
+          umma_commit(&kv_empty[st]);
+        }
+        umma_commit(dq_full);
+        umma_commit(qdo_empty);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    uint8_t* sP = smem + P_OFF;
+    uint8_t* sDS = smem + DS_OFF;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    uint32_t it = 0, pair = 0, jcnt = 0;
+    const int Cp = p.heads * HDP;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+      const int grp = w % p.groups, head = w / p.groups;
+      const long long row0 = (long long)grp * S;
+      // per query row of both tiles: delta = sum_c dO * O and the forward's log-sum-exp
+      float delta[2] = {0.f, 0.f}, lse[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = i * 128 + r;
+        if (i < nt && q < S) {
+          const uint4* a = reinterpret_cast<const uint4*>(p.dout + (row0 + q) * p.lddo + head * HDP);
+          const uint4* b = reinterpret_cast<const uint4*>(p.out + (row0 + q) * p.ldo + head * HDP);
+          float acc = 0.f;
+#pragma unroll
+          for (int v = 0; v < HDP / 8; ++v) {
+            const uint4 x = __ldg(a + v), y = __ldg(b + v);
+            const __half2* hx = reinterpret_cast<const __half2*>(&x);
+            const __half2* hy = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fx = __half22float2(hx[e]), fy = __half22float2(hy[e]);
+              acc = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, acc));
+            }
+          }
+          delta[i] = acc;
+          lse[i] = p.lse[(row0 + q) * p.heads + head];
+        }
+      }
+      for (int j = 0; j < nt; ++j, ++jcnt) {
+        const int ncols = min(128, S - j * 128);
+        for (int i = 0; i < nt; ++i, ++pair) {
+          const int q = i * 128 + r;
+          const bool row_ok = q < S;
+          const float my_lse = i == 0 ? lse[0] : lse[1], my_delta = i == 0 ? delta[0] : delta[1];
+          mbar_wait(sdp_full, pair & 1);
+          mbar_wait(pds_empty, (pair & 1) ^ 1);  // the previous pair's gradient MMAs have consumed P / dS
+          tc_fence_after();
+          const float* brow = (p.bias && row_ok) ? p.bias + ((long long)head * S + q) * S + j * 128 : nullptr;
+          float* dbrow = (p.dbias && row_ok) ? p.dbias + ((long long)head * S + q) * S + j * 128 : nullptr;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t pkp[16], pkd[16];
+            if (c0 < ncols) {
+              uint32_t rs[32], rd[32];
+              tmem_ld32(tS + lane_off + c0, rs);
+              tmem_ld32(tDP + lane_off + c0, rd);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const int c = c0 + q4 * 4;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (brow && c < ncols) b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                float pv[4], ds[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const bool in = row_ok && (c + e < ncols);
+                  const float sc = fmaf(__uint_as_float(rs[q4 * 4 + e]), p.scale_log2e, fmaf(bb[e], 1.4426950408889634f, -my_lse));
+                  pv[e] = in ? exp2f(sc) : 0.f;
+                  ds[e] = in ? pv[e] * (__uint_as_float(rd[q4 * 4 + e]) - my_delta) : 0.f;
+                }
+                if (dbrow && c < ncols)  // (S % 4 == 0: a 4-column group is entirely inside or outside the window)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbrow + c), "f"(ds[0]), "f"(ds[1]),
+                               "f"(ds[2]), "f"(ds[3])
+                               : "memory");
+                const __half2 p0 = __floats2half2_rn(pv[0], pv[1]), p1 = __floats2half2_rn(pv[2], pv[3]);
+                const __half2 d0 = __floats2half2_rn(ds[0], ds[1]), d1 = __floats2half2_rn(ds[2], ds[3]);
+                pkp[q4 * 2] = *reinterpret_cast<const uint32_t*>(&p0), pkp[q4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+                pkd[q4 * 2] = *reinterpret_cast<const uint32_t*>(&d0), pkd[q4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&d1);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pkp[e] = 0u, pkd[e] = 0u;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int c = c0 + qq * 8;
+              const uint32_t off = (c >> 6) * (AL_ROWS * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(sP + off) = make_uint4(pkp[4 * qq], pkp[4 * qq + 1], pkp[4 * qq + 2], pkp[4 * qq + 3]);
+              *reinterpret_cast<uint4*>(sDS + off) = make_uint4(pkd[4 * qq], pkd[4 * qq + 1], pkd[4 * qq + 2], pkd[4 * qq + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(sdp_empty);
+            mbar_arrive(pds_full);
+          }
+        }
+        // dV_j / dK_j: row r of the accumulators is key j*128 + r
+        mbar_wait(dkv_full, jcnt & 1);
+        tc_fence_after();
+        {
+          const int key = j * 128 + r;
+          const bool ok = key < S;
+          __half* orow = p.dqkv + (row0 + key) * p.lddq + head * HDP;
+#pragma unroll
+          for (int which = 1; which < 3; ++which) {
+            const uint32_t tsrc = (which == 1 ? tDK : tDV) + lane_off;
+            const float mul = which == 1 ? p.scale : 1.f;
+#pragma unroll
+            for (int c0 = 0; c0 < HDP; c0 += 32) {
+              uint32_t raw[32];
+              tmem_ld32(tsrc + c0, raw);
+              tmem_ld_wait();
+              if (ok) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                  uint32_t o4[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const __half2 hh = __floats2half2_rn(__uint_as_float(raw[qq * 8 + 2 * u]) * mul,
+                                                         __uint_as_float(raw[qq * 8 + 2 * u + 1]) * mul);
+                    o4[u] = *reinterpret_cast<const uint32_t*>(&hh);
+                  }
+                  *reinterpret_cast<uint4*>(orow + which * Cp + c0 + qq * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_empty);
+      }
+      // dQ_i: row r is query i*128 + r
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i < nt) {
+          const int q = i * 128 + r;
+          const bool ok = q < S;
+          __half* orow = p.dqkv + (row0 + q) * p.lddq + head * HDP;
+#pragma unroll
+          for (int c0 = 0; c0 < HDP; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32(tDQ[i] + lane_off + c0, raw);
+            tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                uint32_t o4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const __half2 hh = __floats2half2_rn(__uint_as_float(raw[qq * 8 + 2 * u]) * p.scale,
+                                                       __uint_as_float(raw[qq * 8 + 2 * u + 1]) * p.scale);
+                  o4[u] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                *reinterpret_cast<uint4*>(orow + c0 + qq * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HDP>
+static int launch_attn_loop_bwd(const CUtensorMap& tq, const CUtensorMap& td, const AttnLoopBwdParams& p, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)8 * AL_ROWS * HDP * 2 + 2 * AL_ROWS * 128 * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    FVIT_CUDA(cudaFuncSetAttribute(attn_loop_bwd_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int items = p.groups * p.heads;
+  const int sms = num_sms();
+  attn_loop_bwd_kernel<HDP><<<items < sms ? items : sms, AL_THREADS, smem, st>>>(tq, td, p);
+  return post_launch("attn_loop_bwd_kernel");
+}
+
+}  // namespace fvit
+
+extern "C" int fvit_attn_loop_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, const void* out, int64_t ldo,
+                                  const float* lse, int32_t groups, int32_t S, int32_t heads, int32_t hdp, const float* bias,
+                                  float scale, void* dqkv, int64_t lddq, float* dbias, void* stream) {
+  using namespace fvit;
+  FVIT_CHECK(qkv && dout && out && lse && dqkv && groups > 0 && heads > 0, "fvit_attn_loop_bwd: bad arguments");
+  FVIT_CHECK(S > 128 && S <= 256, "fvit_attn_loop_bwd: S=%d unsupported (129..256: two tiles of TMEM accumulators)", S);
+  FVIT_CHECK(S % 4 == 0, "fvit_attn_loop_bwd: S=%d must be a multiple of 4 (16-byte bias / dbias accesses)", S);
+  FVIT_CHECK(hdp == 32 || hdp == 64, "fvit_attn_loop_bwd: padded head dim %d unsupported", hdp);
+  FVIT_CHECK(ldq % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0, "fvit_attn_loop_bwd: bad leading dimensions");
+  AttnLoopBwdParams p;
+  p.groups = groups, p.S = S, p.heads = heads, p.nt = (S + 127) / 128;
+  p.scale = scale, p.scale_log2e = scale * 1.4426950408889634f;
+  p.bias = bias, p.dbias = dbias, p.lse = lse;
+  p.dout = (const __half*)dout, p.lddo = lddo, p.out = (const __half*)out, p.ldo = ldo;
+  p.dqkv = (__half*)dqkv, p.lddq = lddq;
+  CUtensorMap tq, td;
+  const CUtensorMapSwizzle swz = hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  uint32_t box[2] = {(uint32_t)hdp, (uint32_t)AL_ROWS};
+  {
+    uint64_t dims[2] = {(uint64_t)(3 * heads * hdp), (uint64_t)groups * S};
+    uint64_t strides[1] = {(uint64_t)ldq * 2};
+    int rc = cached_tmap_16bit(&tq, qkv, 2, dims, strides, box, swz);
+    if (rc) return rc;
+    uint64_t dims2[2] = {(uint64_t)(heads * hdp), (uint64_t)groups * S};
+    uint64_t strides2[1] = {(uint64_t)lddo * 2};
+    rc = cached_tmap_16bit(&td, dout, 2, dims2, strides2, box, swz);
+    if (rc) return rc;
+  }
+  if (hdp == 64) return launch_attn_loop_bwd<64>(tq, td, p, (cudaStream_t)stream);
+  return launch_attn_loop_bwd<32>(tq, td, p, (cudaStream_t)stream);
+}

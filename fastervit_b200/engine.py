@@ -412,6 +412,17 @@ class Plan:
         return d
 
     @staticmethod
+    def _attn_kind(S: int, hdp: int) -> str:
+        """Which attention core serves a window sequence of S tokens with padded head dim hdp: "tile" (one 128-row
+        tcgen05 tile, fvit_attn_tc_fwd), "loop" (key-loop tcgen05 kernel for longer windows: its TMA-staged bias rows
+        need S % 4 == 0) or "simt" (generic fallback for geometries neither covers)."""
+        if hdp > 64:
+            return "simt"
+        if S <= 128:
+            return "tile"
+        return "loop" if S % 4 == 0 else "simt"
+
+    @staticmethod
     def _head_pad(hd: int) -> int:
         """Padded head dim of the tensor-core attention kernel (TMA boxes need 16-byte rows; the
         kernel is instantiated for 32 and 64). Larger heads use the generic SIMT core unpadded."""
@@ -423,7 +434,7 @@ class Plan:
         Three launches: qkv GEMM (+bias), attention core, proj GEMM (+bias, layer-scale, residual)."""
         Cc, h, hd = attn.qkv.in_features, attn.num_heads, attn.head_dim
         hdp = self._head_pad(hd)
-        use_tc = S <= 128 and hdp <= 64
+        use_tc = self._attn_kind(S, hdp) != "simt"
         if not use_tc:
             hdp = hd
         Cp = h * hdp
@@ -445,7 +456,10 @@ class Plan:
                    col_shift=qb_ptr, out_f16=qkv.data_ptr(), ld_o16=3 * Cp)
         self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc  # algorithmic (un-padded heads)
         scale = float(hd ** -0.5)
-        if use_tc:
+        if use_tc and S > 128:
+            self._op(self.ops, "fvit_attn_loop_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hdp,
+                     bias_buf.data_ptr(), scale, ao.data_ptr(), Cp, None)
+        elif use_tc:
             self._op(self.ops, "fvit_attn_tc_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hdp,
                      bias_buf.data_ptr(), scale, ao.data_ptr(), Cp)
         else:

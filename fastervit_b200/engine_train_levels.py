@@ -109,7 +109,8 @@ def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, 
     branch output u = proj(...) + b can be saved (u16) for the layer-scale gradient."""
     Cc, h, hd = attn.qkv.in_features, attn.num_heads, attn.head_dim
     hdp = self._head_pad(hd)
-    use_tc = S <= 128 and hdp <= 64
+    kind = self._attn_kind(S, hdp)
+    use_tc = kind != "simt"
     if not use_tc:
         hdp = hd
     Cp = h * hdp
@@ -131,7 +132,12 @@ def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, 
                col_shift=qb_ptr, out_f16=qkv.data_ptr(), ld_o16=3 * Cp)
     self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc
     scale = float(hd ** -0.5)
-    if use_tc:
+    lse = None
+    if kind == "loop":
+        lse = self.bufs.new(nm + ".lse", (rows, h), torch.float32)   # log-sum-exp rows, read by the backward kernel
+        self._op(self.ops, "fvit_attn_loop_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hdp, bias["out"].data_ptr(),
+                 scale, ao.data_ptr(), Cp, lse.data_ptr())
+    elif use_tc:
         self._op(self.ops, "fvit_attn_tc_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hdp, bias["out"].data_ptr(),
                  scale, ao.data_ptr(), Cp)
     else:
@@ -151,7 +157,8 @@ def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, 
     self._gemm_train_branch(a=ao.data_ptr(), lda=Cp, w=wp.data_ptr(), ldw=ldp, rows=rows, n=n, k=Cp, bias=lin.bias,
                             gamma=gamma if has_ls else None, stream_buf=stream_buf, u16=u16 if has_ls else None, rs=rs)
     self.op_flops[len(self.ops) - 1] = 2.0 * rows * n * Cc
-    return dict(rs=rs, attn=attn, wq=wq, ldq=ldq, wp=wp, ldp=ldp, hd=hd, hdp=hdp, Cp=Cp, use_tc=use_tc, scale=scale, S=S,
+    return dict(rs=rs, attn=attn, wq=wq, ldq=ldq, wp=wp, ldp=ldp, hd=hd, hdp=hdp, Cp=Cp, use_tc=use_tc, kind=kind, lse=lse,
+                scale=scale, S=S,
                 groups=groups, rows=rows, qkv=qkv, ao=ao, y16=y16, bias=bias, u16=u16 if has_ls else None)
 
 
@@ -379,6 +386,22 @@ def _emit_head_bwd(self, feat: dict) -> None:
              self.G(m.norm.bias))
 
 
+def _emit_attn_core_bwd(self, at: dict, dao, dqkv, groups: int, S: int) -> None:
+    """backward of the attention core: the tcgen05 tile kernel (S <= 64), the tcgen05 key-loop kernel (128 < S <= 256,
+    needs the forward's output and log-sum-exp) or the generic SIMT kernel"""
+    attn = at["attn"]
+    h, hd, hdp, Cp = attn.num_heads, at["hd"], at["hdp"], at["Cp"]
+    ops = self.bwd_ops
+    if at.get("kind") == "loop" and S <= 256:
+        self._op(ops, "fvit_attn_loop_bwd", at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, at["ao"].data_ptr(), Cp,
+                 at["lse"].data_ptr(), groups, S, h, hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp,
+                 at["bias"]["dbias"])
+    else:
+        self._op(ops, _attn_bwd_entry(S, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, groups, S, h, hd,
+                 hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
+    self.bwd_flops[len(ops) - 1] = 10.0 * groups * h * S * S * hd
+
+
 def _attn_bwd_entry(S: int, hdp: int, use_tc: bool) -> str:
     """tensor-core attention backward when the tile fits (S <= 64, head slices of 32/64, shared memory budget)"""
     if use_tc and S <= 64 and hdp in (32, 64):
@@ -468,9 +491,7 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
     # attention core
-    self._op(ops, _attn_bwd_entry(S, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, groups, S, h, hd,
-             hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
-    self.bwd_flops[len(ops) - 1] = 10.0 * groups * h * S * S * hd
+    _emit_attn_core_bwd(self, at, dao, dqkv, groups, S)
     _bias_bwd(self, at["bias"])
     # qkv
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
@@ -572,8 +593,7 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
                      dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc, bias_done=fused)
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
-    self._op(ops, _attn_bwd_entry(n_ct, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, B, n_ct, h, hd,
-             hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
+    _emit_attn_core_bwd(self, at, dao, dqkv, B, n_ct)
     _bias_bwd(self, at["bias"])
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
     gWq, gbq = self.G(attn.qkv.weight), (self.G(attn.qkv.bias) if attn.qkv.bias is not None else None)

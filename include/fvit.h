@@ -311,6 +311,12 @@ int fvit_attn_core_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t l
 int fvit_attn_tc_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, int32_t groups, int32_t S,
                      int32_t heads, int32_t head_dim, int32_t hdp, const float* bias, float scale, void* dqkv,
                      int64_t lddq, float* dbias, void* stream);
+/* Tensor-core backward for 128 < S <= 256 (S % 4 == 0), the mirror of fvit_attn_loop_fwd: item = (window, head), two
+ * key tiles x two query tiles, dV / dK / dQ_0 / dQ_1 accumulate in TMEM; needs the forward's output `out` (for
+ * delta = rowsum(dO * O)) and its log-sum-exp vector `lse`. Same dqkv / dbias contract as fvit_attn_core_bwd. */
+int fvit_attn_loop_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, const void* out, int64_t ldo,
+                       const float* lse, int32_t groups, int32_t S, int32_t heads, int32_t hdp, const float* bias,
+                       float scale, void* dqkv, int64_t lddq, float* dbias, void* stream);
 /* dst (+)= *scalar * src with head padding removed from rows and/or columns (inverse of
  * fvit_cast_headpad_f16 for gradients). */
 int fvit_unpad_heads_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t rows_src, int32_t cols_src,
