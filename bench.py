@@ -176,6 +176,58 @@ def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float =
                 ms_per_step=1e3 * dt / n, steps_done=n, batch=bs)
 
 
+def quick_measure(workload: str, dev, pk: dict, steps: int = 8, warmup: int = 3) -> dict:
+    """One more BASELINE config measured in the same process (device-resident rotating inputs, CUDA events over
+    `steps` steps after `warmup`), with the GEMM kernel's share and roofline fraction from the per-launch table.
+    Used for the `also_measured` block so that the driver-run record covers every single-GPU config."""
+    import fastervit_b200 as F
+    entry, kwargs, batch, hw, mode = WORKLOADS[workload]
+    torch.manual_seed(0)
+    model = F.create_model(entry, **kwargs).to(dev)
+    model = model.train() if mode == "train" else model.eval()
+    g = torch.Generator(device=dev).manual_seed(11)
+    xs = [torch.randn(batch, 3, hw[0], hw[1], device=dev, generator=g) for _ in range(2)]
+    targets = torch.randint(0, 1000, (batch,), device=dev, generator=g)
+
+    def step(xb):
+        if mode == "train":
+            torch.nn.functional.cross_entropy(model(xb), targets).backward()
+            model.zero_grad(set_to_none=True)
+        else:
+            model(xb)
+    with torch.set_grad_enabled(mode == "train"):
+        for i in range(warmup):
+            step(xs[i % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(xs[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    value = batch / (ms / 1e3)
+    plan = next(iter(model._engine.plans.values()))
+    with torch.no_grad():
+        plan.profile(xs[0])
+        prof = plan.profile(xs[1])
+    gm_ms = sum(r["ms"] for r in prof if r["name"] == "fvit_gemm")
+    gm_fl = sum(r["flops"] for r in prof if r["name"] == "fvit_gemm")
+    tot = sum(r["ms"] for r in prof)
+    simt = sum(r["ms"] for r in prof if r["name"] in ("fvit_attn_core_fwd", "fvit_attn_core_bwd"))
+    alg = ALG_GFLOP_FWD[workload] * 1e9
+    out = {"workload": f"{entry} {'fwd+bwd' if mode == 'train' else 'forward'}, batch {batch}, 3x{hw[0]}x{hw[1]}",
+           "value": round(value, 1), "unit": "img/s", "ms_per_step": round(ms, 4), "steps": steps, "warmup": warmup,
+           "model_frac_of_tensor_peak": round(value * alg / 1e12 / pk["tensor"], 4),
+           "gemm": {"share_of_step": round(gm_ms / tot, 4), "achieved_tflops": round(gm_fl / (gm_ms / 1e3) / 1e12, 1),
+                    "frac": round(gm_fl / (gm_ms / 1e3) / 1e12 / pk["tensor"], 4)},
+           "simt_attention_ms": round(simt, 4),
+           "vs_baseline": round(value / PUBLISHED_IMG_S[workload], 3) if workload in PUBLISHED_IMG_S else None}
+    del plan, model, xs
+    torch.cuda.empty_cache()
+    return out
+
+
 def optimizer_leg(model, x, targets, pk) -> dict:
     """Time the fused optimizer step that follows backward in the reference loop (train.py:879-899): clip-grad-norm
     + LAMB (fv4-6) or AdamW (fv0-3) + ModelEmaV2, on the gradients of one real backward pass, CUDA events over
@@ -236,6 +288,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the also_measured block (other BASELINE configs)")
     ap.add_argument("--profile-out", default="", help="write the per-launch timing table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -259,6 +312,13 @@ def main() -> None:
         if rank != 0:
             return
         r = cpu_reference_rate(args.workload, args.steps, args.warmup, budget_s=120.0)
+        # the config this arm really ran: the same model / mode / input shape / metric (img/s is batch-normalised), but
+        # each step is a bounded sample of the workload -- a small batch on the host cores -- and it says so
+        config = {"workload": f"{entry} {what}, 3x{hw[0]}x{hw[1]} synthetic N(0,1), random-init weights; CPU sample: "
+                              f"batch {r['batch']} per step on {r['cores']} host threads (the B200 arm runs batch "
+                              f"{batch}/GPU; a full batch is ~1 min per step on these cores)",
+                  "global_batch": r["batch"], "parallelism": f"{r['cores']} CPU threads, 1 process",
+                  "sample_of": f"batch {batch}/GPU workload of the B200 arm", "l2": "n/a (CPU)"}
         line = {"impl": "reference", "metric": "images/sec", "value": r["value"], "unit": "img/s",
                 "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -454,6 +514,18 @@ def main() -> None:
                                  budget_s=float(os.environ.get("FVIT_BENCH_CPU_BUDGET_S", "15")))
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ------------------------------------------------------------------ the other single-GPU BASELINE configs
+    also = None
+    if rank == 0 and world == 1 and not args.no_also and args.workload == "fv4_train":
+        del model, xs
+        torch.cuda.empty_cache()
+        also = {}
+        for wl in ("fv0_fwd", "fv0_train", "ar0_fwd", "fv4_fwd"):
+            try:
+                also[wl] = quick_measure(wl, dev, pk)
+            except Exception as exc:  # a side measurement must not take the headline line down
+                also[wl] = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         alg = ALG_GFLOP_FWD[args.workload] * 1e9
         line = {"metric": "images/sec", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
@@ -464,7 +536,7 @@ def main() -> None:
                 "dtype": "fp16 operands, fp32 accumulate / residual / statistics", "data": "synthetic",
                 "config": config, "e2e": e2e, "gpu_launches": int(launches),
                 "launches_per_step": launches / args.steps, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "optimizer_step": opt_info, "per_kernel": prof_table,
+                "cpu_baseline": cpu, "optimizer_step": opt_info, "also_measured": also, "per_kernel": prof_table,
                 "grad_sync_check": grad_sync,
                 "model_tflops": round(value * alg / 1e12, 2),
                 "model_frac_of_tensor_peak": round(value / world * alg / 1e12 / pk["tensor"], 4)}
