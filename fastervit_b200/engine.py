@@ -79,6 +79,9 @@ class Plan:
         self._gemm_keep: list = []        # keeps ctypes structs alive
         self._x_args: list = []           # stem-conv calls that take the input pointer at run time
         self.op_flops: dict[int, float] = {}  # op index -> algorithmic FLOPs (GEMM launches)
+        # FVIT_FUSED_HAT=0 falls back to the three-launch attention (qkv GEMM, attention core, proj GEMM) for A/B runs
+        import os
+        self.fused_hat = os.environ.get("FVIT_FUSED_HAT", "1") != "0"
         self.marks: list[tuple[int, str, dict]] = []   # (ops issued so far, reference module name, where its output lives)
         self._build()
 
@@ -452,11 +455,20 @@ class Plan:
                 qbp = self.bufs.new(nm + ".qkv.bias_pad", (3 * Cp,), torch.float32)
                 self._op(self.prep_ops, "fvit_vec_headpad_f32", qb.data_ptr(), qbp.data_ptr(), 3 * Cp, hd, hdp)
                 qb_ptr = qbp.data_ptr()
-        self._gemm(a=xin.data_ptr(), a_rows=rows, lda=ld_in, b=wq.data_ptr(), ldb=ldq, m=rows, n=3 * Cp, kc=Cc,
-                   col_shift=qb_ptr, out_f16=qkv.data_ptr(), ld_o16=3 * Cp)
-        self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc  # algorithmic (un-padded heads)
         scale = float(hd ** -0.5)
-        if use_tc and S > 128:
+        fused = self.fused_hat and self._attn_kind(S, hdp) == "tile"
+        if fused:
+            # ONE kernel: qkv projection + softmax(q k^T * scale + bias) + P v; the qkv matrix never reaches HBM
+            self._op(self.ops, "fvit_hat_attn_fwd", xin.data_ptr(), ld_in, Cc, wq.data_ptr(), ldq, qb_ptr, groups, S, h,
+                     hdp, bias_buf.data_ptr(), scale, ao.data_ptr(), Cp, None, 0)
+            self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc + 4.0 * groups * h * S * S * hd
+        else:
+            self._gemm(a=xin.data_ptr(), a_rows=rows, lda=ld_in, b=wq.data_ptr(), ldb=ldq, m=rows, n=3 * Cp, kc=Cc,
+                       col_shift=qb_ptr, out_f16=qkv.data_ptr(), ld_o16=3 * Cp)
+            self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc  # algorithmic (un-padded heads)
+        if fused:
+            pass
+        elif use_tc and S > 128:
             self._op(self.ops, "fvit_attn_loop_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hdp,
                      bias_buf.data_ptr(), scale, ao.data_ptr(), Cp, None)
         elif use_tc:
@@ -465,7 +477,8 @@ class Plan:
         else:
             self._op(self.ops, "fvit_attn_core_fwd", qkv.data_ptr(), 3 * Cp, groups, S, h, hd,
                      bias_buf.data_ptr(), scale, ao.data_ptr(), Cp, None)
-        self.op_flops[len(self.ops) - 1] = 4.0 * groups * h * S * S * hd
+        if not fused:
+            self.op_flops[len(self.ops) - 1] = 4.0 * groups * h * S * S * hd
         # proj: K dimension is the (head-padded) attention output
         lin = attn.proj
         n = lin.weight.shape[0]

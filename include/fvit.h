@@ -197,6 +197,17 @@ int fvit_attn_core_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, 
 int fvit_attn_tc_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
                      const float* bias, float scale, void* out, int64_t ldo, void* stream);
 
+/* The fused hierarchical-attention kernel (north star; WindowAttention.forward faster_vit.py:557-565 with the qkv Linear
+ * of faster_vit.py:546): out = softmax((x Wq^T + bq)(x Wk^T + bk)^T * scale + bias)(x Wv^T + bv) per window and head
+ * in ONE tcgen05 kernel. xn16 [groups*S, C] is the LayerNorm-ed fp16 activation (norm1 / hat_norm1 output, row stride
+ * ldx), wqkv16 the head-padded packed qkv weight [3*heads*hdp, C] (fvit_cast_headpad_f16; row stride ldw), qkv_bias
+ * its padded bias [3*heads*hdp] or NULL, bias the relative-position bias [heads, S, S] or NULL. S <= 128, hdp in
+ * {32, 64}. out [groups*S, heads*hdp] as fvit_attn_tc_fwd. qkv_out (optional, [groups*S, 3*heads*hdp] fp16) receives
+ * the projected q | k | v for the backward pass; when NULL the qkv matrix never exists in HBM. */
+int fvit_hat_attn_fwd(const void* xn16, int64_t ldx, int32_t C, const void* wqkv16, int64_t ldw, const float* qkv_bias,
+                      int32_t groups, int32_t S, int32_t heads, int32_t hdp, const float* bias, float scale, void* out,
+                      int64_t ldo, void* qkv_out, int64_t ldq, void* stream);
+
 /* Key-loop tensor-core attention core for window sequences longer than one 128-row tile (any-res level 2:
  * S = 12*12 + 4 = 148, faster_vit_any_res.py:805-817; 21k windows S = 196 .. 2304, faster_vit.py:1253-1418):
  * work item = (window, head, 128 query rows); key tiles of 128 are visited twice (row maxima, then probabilities and

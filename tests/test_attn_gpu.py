@@ -174,3 +174,40 @@ def test_attn_loop_backward_matches_autograd(S, heads, hd, groups):
         assert err < 4e-3, (nm, err)
     err = ((dbias - bias.grad).abs().max() / bias.grad.abs().max()).item()
     assert err < 4e-3, ("dbias", err)
+
+
+@pytest.mark.parametrize("S,heads,hd,groups,C", [(53, 8, 32, 37, 256), (49, 16, 32, 20, 512), (16, 8, 32, 11, 256),
+                                                 (53, 16, 49, 9, 784), (49, 32, 49, 6, 1568), (60, 8, 32, 5, 256),
+                                                 (36, 16, 32, 31, 512), (128, 2, 64, 3, 128), (64, 4, 24, 6, 96),
+                                                 (53, 8, 32, 1024, 256), (85, 4, 16, 4, 64)])
+@pytest.mark.parametrize("save_qkv", [False, True])
+def test_fused_hat_attention_matches_unfused_math(S, heads, hd, groups, C, save_qkv):
+    """fvit_hat_attn_fwd (QKV projection + softmax(QK^T + bias) + PV in one tcgen05 kernel) against fp32 torch on
+    the same fp16 activations / head-padded weights, with q, k, v rounded to fp16 as the kernel's operand tiles are."""
+    from fastervit_b200 import lib
+    lib.load()
+    hdp = 32 if hd <= 32 else 64
+    g = torch.Generator(device="cuda").manual_seed(S * 131 + heads + C)
+    rows = groups * S
+    x = torch.randn(rows, C, device="cuda", generator=g).half()
+    w = torch.zeros(3, heads, hdp, C, device="cuda")
+    w[:, :, :hd] = torch.randn(3, heads, hd, C, device="cuda", generator=g) * C ** -0.5
+    w16 = w.reshape(3 * heads * hdp, C).half()
+    qb = torch.zeros(3, heads, hdp, device="cuda")
+    qb[:, :, :hd] = torch.randn(3, heads, hd, device="cuda", generator=g) * 0.2
+    qb = qb.reshape(-1).contiguous()
+    bias = torch.randn(heads, S, S, device="cuda", generator=g) * 2 + 4
+    scale = hd ** -0.5
+    out = torch.full((rows, heads * hdp), float("nan"), device="cuda", dtype=torch.half)
+    qkv_out = torch.full((rows, 3 * heads * hdp), float("nan"), device="cuda", dtype=torch.half) if save_qkv else None
+    lib.call("fvit_hat_attn_fwd", x.data_ptr(), x.stride(0), C, w16.data_ptr(), w16.stride(0), qb.data_ptr(), groups, S,
+             heads, hdp, bias.data_ptr(), scale, out.data_ptr(), out.stride(0),
+             qkv_out.data_ptr() if save_qkv else None, 3 * heads * hdp)
+    torch.cuda.synchronize()
+    qkv = (x.float() @ w16.float().t() + qb).half()
+    ref = _ref(qkv, groups, S, heads, hd, hdp, bias, scale)
+    assert torch.isfinite(out.float()).all()
+    err = ((out.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 2e-3, err
+    if save_qkv:
+        assert ((qkv_out.float() - qkv.float()).abs().max() / qkv.float().abs().max()).item() < 1e-3
