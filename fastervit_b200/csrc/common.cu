@@ -164,4 +164,5 @@ int fvit_abi_version(void) { return FVIT_ABI_VERSION; }
 const char* fvit_last_error(void) { return fvit::err_buf(); }
 int64_t fvit_launch_count(void) { return fvit::g_launches.load(); }
 void fvit_reset_launch_count(void) { fvit::g_launches.store(0); }
+void fvit_add_launch_count(int64_t n) { fvit::g_launches.fetch_add(n); }
 }

@@ -181,7 +181,8 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& tm,
   tm = t / p.tiles_n;
 }
 
-template <uint32_t FEAT>
+// CG = 1: one CTA per 128-row tile (no cluster instruction is compiled in); CG = 2: CTA pair (cluster launch).
+template <uint32_t FEAT, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const __grid_constant__ CUtensorMap tmap_b,
@@ -193,8 +194,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   // CTA pair: this CTA stages its 128 rows of A and its half of the B tile; the leader issues M = 256 MMAs that
   // read both CTAs' shared memory at the same offsets and write 128 accumulator rows into each CTA's TMEM
-  const int cg = p.cg;
-  const uint32_t cta_rank = cg == 2 ? cluster_ctarank() : 0u;
+  constexpr int cg = CG;
+  uint32_t cta_rank = 0u;
+  if constexpr (CG == 2) cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
   const int unit0 = blockIdx.x / cg, nunits = gridDim.x / cg;  // work units are dealt to CTAs / CTA pairs
   const int b_cols = p.tile_n / cg;                            // B rows (N columns) staged by this CTA
@@ -222,11 +224,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (cg == 2) tmem_alloc_cg2(tmem_base_slot, TMEM_COLS);
+    if constexpr (CG == 2) tmem_alloc_cg2(tmem_base_slot, TMEM_COLS);
     else tmem_alloc(tmem_base_slot, TMEM_COLS);
   }
   tc_fence_before();
-  if (cg == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+  if constexpr (CG == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* sb = sa + A_STAGE_BYTES;
           // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the whole pair
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * cg));
-          if (cg == 1) {
+          if constexpr (CG == 1) {
             if (!p.a_mn) {
               const int tap = kb / p.kb_per_tap;
               const int kc0 = (kb - tap * p.kb_per_tap) * BK;
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 tma_load_2d(sb + j * BK * 128, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BK + b_shift);
             }
           } else {
-            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);  // (only instantiated for CG == 2)
             if (!p.a_mn) {
               const int tap = kb / p.kb_per_tap;
               const int kc0 = (kb - tap * p.kb_per_tap) * BK;
@@ -328,11 +330,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
-            if (cg == 2) umma_f16_ss_cg2(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_ss_cg2(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs retire
-          if (cg == 2) umma_commit_cg2(&empty_bar[stage]);
+          if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]);
           else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
-        if (cg == 2) umma_commit_cg2(&acc_full[acc]);
+        if constexpr (CG == 2) umma_commit_cg2(&acc_full[acc]);
         else umma_commit(&acc_full[acc]);
         if (++acc == p.nacc) {
           acc = 0;
@@ -394,7 +396,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const float osum_alpha = (osum && p.osum_alpha) ? __ldg(p.osum_alpha) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t acc_empty_leader = cg == 2 ? mapa_shared(smem_u32(&acc_empty[0]), 0) : 0u;
+    uint32_t acc_empty_leader = 0u;
+    if constexpr (CG == 2) acc_empty_leader = mapa_shared(smem_u32(&acc_empty[0]), 0);
     for (int w = unit0; w < work_total; w += nunits) {
       int tm, tn, split_;
       decode_work(p, w, tm, tn, split_);
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (cg == 2) mbar_arrive_cluster(acc_empty_leader + 8u * acc);
+        if constexpr (CG == 2) mbar_arrive_cluster(acc_empty_leader + 8u * acc);
         else mbar_arrive(&acc_empty[acc]);
       }
       if (++acc == p.nacc) {
@@ -684,11 +687,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   tc_fence_before();
   __syncwarp();                     // role loops leave lane 0 behind: reconverge before the aligned barrier
-  if (cg == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory / TMEM until the very end
+  if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory / TMEM until the very end
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (cg == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
@@ -901,11 +904,21 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   const bool needs_generic = false;
 #define FVIT_GEMM_LAUNCH(F)                                                                            \
   do {                                                                                                 \
-    auto kfn = gemm_tcgen05_kernel<(F)>;                                                               \
-    static bool attr_set = false;                                                                      \
-    if (!attr_set) {                                                                                   \
-      FVIT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));  \
-      attr_set = true;                                                                                 \
+    if (cg == 1) {                                                                                     \
+      auto kfn = gemm_tcgen05_kernel<(F), 1>;                                                          \
+      static bool attr_set = false;                                                                    \
+      if (!attr_set) {                                                                                 \
+        FVIT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET)); \
+        attr_set = true;                                                                               \
+      }                                                                                                \
+      kfn<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(tma, tmb, p);                      \
+      return post_launch("gemm_tcgen05_kernel");                                                       \
+    }                                                                                                  \
+    auto kfn2 = gemm_tcgen05_kernel<(F), 2>;                                                           \
+    static bool attr_set2 = false;                                                                     \
+    if (!attr_set2) {                                                                                  \
+      FVIT_CUDA(cudaFuncSetAttribute(kfn2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET)); \
+      attr_set2 = true;                                                                                \
     }                                                                                                  \
     cudaLaunchConfig_t cfg;                                                                            \
     memset(&cfg, 0, sizeof(cfg));                                                                      \
@@ -913,9 +926,14 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
     cfg.dynamicSmemBytes = (size_t)smem_bytes, cfg.stream = (cudaStream_t)stream;                      \
     cudaLaunchAttribute attr[1];                                                                       \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                  \
-    attr[0].val.clusterDim.x = (unsigned)cg, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1; \
-    cfg.attrs = attr, cfg.numAttrs = cg == 2 ? 1 : 0;                                                  \
-    FVIT_CUDA(cudaLaunchKernelEx(&cfg, kfn, tma, tmb, p));                                             \
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;          \
+    cfg.attrs = attr, cfg.numAttrs = 1;                                                                \
+    cudaError_t le_ = cudaLaunchKernelEx(&cfg, kfn2, tma, tmb, p);                                     \
+    if (le_ != cudaSuccess) {                                                                          \
+      (void)cudaGetLastError(); /* do not leave the error behind for the next launch */                \
+      return set_error("launch of the CTA-pair gemm_tcgen05_kernel (grid %d, %d B smem) failed: %s", grid, smem_bytes, \
+                       cudaGetErrorString(le_));                                                       \
+    }                                                                                                  \
     return post_launch("gemm_tcgen05_kernel");                                                         \
   } while (0)
 #define FVIT_ACTF(x) ((uint32_t)(x) << EF_ACT_SHIFT)

@@ -191,18 +191,25 @@ class TrainPlan(Plan):
         # invalidates the state an earlier, not yet differentiated forward left behind (checked in backward)
         self.fwd_generation = getattr(self, "fwd_generation", 0) + 1
         L.bump_weights_epoch()   # BatchNorm running statistics are updated through raw pointers
-        for t in self.fwd_zero:
-            t.zero_()
-        if self.drop_specs:
-            self._gen_drop_masks()   # stochastic-depth masks of this step (torch RNG, like timm's DropPath)
-        self.run_ops(self.prep_ops, None)
-        self.run_ops(self.ops, x)
-        for bn in self._bn_modules:
-            bn.num_batches_tracked += 1
+        def body(xin):
+            for t in self.fwd_zero:
+                t.zero_()
+            if self.drop_specs:
+                self._gen_drop_masks()   # stochastic-depth masks of this step (torch RNG, like timm's DropPath)
+            self.run_ops(self.prep_ops, None)
+            self.run_ops(self.ops, xin)
+            for bn in self._bn_modules:
+                bn.num_batches_tracked += 1
+        if self.use_graphs and not getattr(self, "forced_drop_masks", None):
+            xs_ = self.static_input(x)
+            self.run_captured("train forward", lambda: body(xs_))
+        else:
+            body(x)
         return self.logits
 
-    def _bwd_start(self, dlogits: torch.Tensor) -> None:
-        self._dlogits.copy_(dlogits)
+    def _bwd_start(self, dlogits: torch.Tensor | None) -> None:
+        if dlogits is not None:
+            self._dlogits.copy_(dlogits)
         self.run_ops(self._bwd_prologue, None)
         st = L.stream_ptr()
         rc = self.lib.fvit_grad_scale_init(self._dlogits.data_ptr(), self._dlogits.numel(), 64.0, self.scal.data_ptr(), st)
@@ -211,11 +218,16 @@ class TrainPlan(Plan):
         self.run_ops(self._branch_alpha_ops, None)
 
     def run_backward(self, dlogits: torch.Tensor) -> None:
-        self._bwd_start(dlogits)
         grp = getattr(self.model, "_grad_allreduce", None)
         if grp is None:
-            self.run_ops(self.bwd_ops, None)
+            self._dlogits.copy_(dlogits)
+
+            def body():
+                self._bwd_start(None)
+                self.run_ops(self.bwd_ops, None)
+            self.run_captured("backward", body)
             return
+        self._bwd_start(dlogits)
         # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients
         # are enqueued, so NCCL (its own stream) overlaps the rest of the backward pass
         red = GradBucketReducer(self.gflat, None if grp is True else grp)

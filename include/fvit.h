@@ -28,6 +28,9 @@ const char* fvit_last_error(void);
  * "gpu_launches" evidence. */
 int64_t fvit_launch_count(void);
 void fvit_reset_launch_count(void);
+/* A launch list captured into a CUDA graph launches its kernels without passing through the entry points: the host side
+ * adds the number of kernel nodes per replay so that fvit_launch_count() stays the number of kernels that really ran. */
+void fvit_add_launch_count(int64_t n);
 
 /* ---- epilogue activation codes --------------------------------------------------------------- */
 enum {

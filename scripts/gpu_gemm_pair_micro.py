@@ -2,7 +2,11 @@
 correctness against each other and CUDA-event throughput (L2 flushed between timed launches by working on
 operands larger than L2 where the shape allows, otherwise rotating buffers)."""
 import sys
+from pathlib import Path
+
 import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from fastervit_b200 import lib as L
 
 L.load()

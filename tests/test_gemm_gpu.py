@@ -349,8 +349,9 @@ def test_gemm_pair_mn_major(a_mn, b_mn, m, n, k, tile_n):
     g = torch.Generator(device="cuda").manual_seed(m + n + k)
     A = torch.randn(m, k, device="cuda", generator=g).half()
     B = torch.randn(n, k, device="cuda", generator=g).half()
-    a = A.t().contiguous() if a_mn else A
-    b = B.t().contiguous() if b_mn else B
+    pad8 = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 8))[:, :t.shape[1]]   # row stride multiple of 8
+    a = pad8(A.t().contiguous()) if a_mn else A
+    b = pad8(B.t().contiguous()) if b_mn else B
     out = torch.zeros(m, n, device="cuda")
     lib.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_f32=out, tile_n=tile_n, cta_group=2)
     assert _rel(out, A.float() @ B.float().t()) < 2e-5
