@@ -85,6 +85,7 @@ class Plan:
         self.use_graphs = os.environ.get("FVIT_CUDA_GRAPH", "1") != "0" and device.type == "cuda"
         self._graphs: dict = {}
         self._x_static = None
+        self._deploy_mods: list = []
         self.marks: list[tuple[int, str, dict]] = []   # (ops issued so far, reference module name, where its output lives)
         self._build()
 
@@ -118,6 +119,14 @@ class Plan:
             out[name] = self._extract(where)
         self.run_ops(self.ops[done:], x)
         return out
+
+    def _deploy_guard(self, lst: list, start: int, mod) -> None:
+        """ops lst[start:] derive mod.relative_bias from its MLP: skipped once mod.switch_to_deploy() was called
+        (fv.py:263-269, 336-342 — the buffer then holds what a checkpoint or the last forward left there)"""
+        for i in range(start, len(lst)):
+            fn, args, name = lst[i]
+            lst[i] = ("unless_deploy", (mod, fn, args), name)
+        self._deploy_mods.append(mod)
 
     # ---- op emitters --------------------------------------------------------------------------
     def _op(self, target: list, name: str, *args) -> None:
@@ -230,6 +239,7 @@ class Plan:
                     self._emit_downsample_conv(i - 1, prev, lvl, to_conv=True)
                     self._mark(f"levels.{i - 1}", kind="conv", lv=lvl)
                 self._emit_conv_blocks(i, level, lvl)
+                self._mark(f"levels.{i}.out", kind="conv", lv=lvl)
                 prev = dict(kind="conv", **lvl)
             else:
                 tl = self._token_level_buffers(i, level, Cc, Hc, Wc)
@@ -241,6 +251,7 @@ class Plan:
                 self._emit_downsample_conv(i - 1, prev, tl, to_conv=False)
                 self._mark(f"levels.{i - 1}", kind="tok_map", tl=tl)
                 self._emit_token_level(i, level, tl)
+                self._mark(f"levels.{i}.out", kind="tok_map", tl=tl)
                 prev = dict(kind="tok", **tl)
                 if level.downsample is None:
                     self._mark(f"levels.{i}", kind="tok_map", tl=tl)
@@ -509,11 +520,13 @@ class Plan:
         if tuple(rpb.relative_bias.shape) != (1, rpb.num_heads, S, S):
             rpb.relative_bias = torch.zeros(1, rpb.num_heads, S, S, device=self.device)
         tgt = self.prep_ops  # batch independent: recomputed only when the weights change
+        n0 = len(tgt)
         self._op(tgt, "fvit_cpb_mlp_fwd", rpb.relative_coords_table.data_ptr(), P, rpb.cpb_mlp[0].weight.data_ptr(),
                  rpb.cpb_mlp[0].bias.data_ptr(), rpb.cpb_mlp[2].weight.data_ptr(), rpb.num_heads,
                  table.data_ptr(), None)
         self._op(tgt, "fvit_attn_bias_fwd", table.data_ptr(), rpb.relative_position_index.data_ptr(),
                  rpb.num_heads, S, rpb.window ** 2, rpb.relative_bias.data_ptr())
+        self._deploy_guard(tgt, n0, rpb)
         return rpb.relative_bias
 
     def _emit_pos_embed(self, nm: str, tpe, n_side: int, Cc: int) -> torch.Tensor:
@@ -526,9 +539,11 @@ class Plan:
         coords.copy_(grid.flatten(1).t())
         if tuple(tpe.relative_bias.shape) != (1, n_side * n_side, Cc):
             tpe.relative_bias = torch.zeros(1, n_side * n_side, Cc, device=self.device)
+        n0 = len(self.prep_ops)
         self._op(self.prep_ops, "fvit_cpb_mlp_fwd", coords.data_ptr(), n_side * n_side,
                  tpe.cpb_mlp[0].weight.data_ptr(), tpe.cpb_mlp[0].bias.data_ptr(),
                  tpe.cpb_mlp[2].weight.data_ptr(), Cc, tpe.relative_bias.data_ptr(), None)
+        self._deploy_guard(self.prep_ops, n0, tpe)
         return tpe.relative_bias
 
     def _emit_branch_out(self, nm: str, lin: nn.Linear, gamma, a, lda, rows, stream_buf, act=L.ACT_NONE,
@@ -657,7 +672,7 @@ class Plan:
             k += p._version
         for b_ in self.model.buffers():
             k += b_._version
-        return (k, L.weights_epoch())
+        return (k, L.weights_epoch(), sum(1 << (i % 60) for i, m in enumerate(self._deploy_mods) if m.deploy))
 
     def run_ops(self, ops: list, x: torch.Tensor | None) -> None:
         st = L.stream_ptr()
@@ -670,6 +685,11 @@ class Plan:
             elif fn == "zero":
                 args.zero_()
                 continue
+            elif fn == "unless_deploy":
+                mod, fn2, args2 = args
+                if mod.deploy:
+                    continue
+                rc = fn2(*args2, st)
             elif fn == "bucket":   # gradient slice [lo, hi) of the flat buffer is final (engine_train.py)
                 red = getattr(self, "_ar_active", None)
                 if red is not None:
@@ -796,6 +816,27 @@ class Engine:
             # num_classes = 0: head is nn.Identity, forward returns the pooled features (fv.py:955-958)
             return plan.pooled[:, :self.model.num_features].float()
         return plan.logits.clone()
+
+    def forward_levels(self, x: torch.Tensor, out_indices: tuple) -> tuple:
+        """Eval forward that also returns each requested level's output before its Downsample as an NCHW fp32 map
+        (the launch list is run piecewise up to the marks where those activations are live)."""
+        plan = self._plan(x)
+        if plan.training:
+            raise L.FvitError("forward_levels is an inference helper (call model.eval())")
+        with torch.cuda.device(x.device):
+            wk = plan.weights_key()
+            if self._prepped.get(id(plan)) != wk:
+                plan.run_ops(plan.prep_ops, None)
+                self._prepped[id(plan)] = wk
+            want = {f"levels.{i}.out": i for i in out_indices}
+            outs, done = {}, 0
+            for upto, name, where in plan.marks:
+                if name in want:
+                    plan.run_ops(plan.ops[done:upto], x)
+                    done = upto
+                    outs[want[name]] = plan._extract(where)
+            plan.run_ops(plan.ops[done:], x)
+        return tuple(outs[i] for i in out_indices)
 
     def forward_head(self, feats: torch.Tensor) -> torch.Tensor:
         """avgpool + flatten + head (fv.py:955-958) on the [B, C, H, W] map `forward_features` returns (an already

@@ -42,6 +42,12 @@ class TokenPosEmbed(_Holder):
         self.cpb_mlp = _cpb_mlp(dim)
         self.register_buffer("relative_bias", torch.zeros(1, seq_length, dim))
         self.seq_length = seq_length
+        self.deploy = False
+
+    def switch_to_deploy(self):
+        """fv.py:336-342: stop re-deriving the embedding from the MLP; `relative_bias` (as loaded from a checkpoint
+        or left by the last forward) is used as is."""
+        self.deploy = True
 
 
 class RelPosBias(_Holder):
@@ -61,6 +67,11 @@ class RelPosBias(_Holder):
         rel = pos[:, :, None] - pos[:, None, :] + (window - 1)
         self.register_buffer("relative_position_index", (rel[0] * (2 * window - 1) + rel[1]).contiguous())
         self.register_buffer("relative_bias", torch.zeros(1, num_heads, seq_length, seq_length))
+        self.deploy = False
+
+    def switch_to_deploy(self):
+        """fv.py:263-269: the cached `relative_bias` buffer replaces the table MLP + gather + 16*sigmoid."""
+        self.deploy = True
 
 
 class WindowAttention(_Holder):
@@ -276,6 +287,20 @@ class FasterViT(nn.Module):
         gradient buffer is averaged over `group` (default: the world) with a single NCCL all-reduce — the one
         collective of the path (train.py:551). Parameters must start identical on all ranks."""
         self._grad_allreduce = True if group is None else group
+
+    def switch_to_deploy(self):
+        """Put every positional-embedding module into deploy mode (the reference exposes `switch_to_deploy` per module,
+        fv.py:263-269, 336-342; this is the loop a user writes over `model.modules()`). Inference then reads the
+        cached `relative_bias` buffers and skips the positional MLP kernels for good."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "switch_to_deploy"):
+                m.switch_to_deploy()
+        return self
+
+    def forward_levels(self, x, out_indices=(0, 1, 2, 3)):
+        """Per-level feature maps [B, C_i, H_i, W_i] (each level's output before its Downsample), the `xo` a dense-
+        prediction backbone taps (downstream/object_detection/dino/models/dino/fastervit.py:686-709, 816-827)."""
+        return self._get_engine().forward_levels(x, tuple(out_indices))
 
     def forward_features(self, x):
         return self._get_engine().forward(x, features_only=True)
