@@ -77,61 +77,81 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   }
 }
 
-// y = act(x16[row]*scale + shift) (+ resid32[row]) for the listed rows; writes fp32 and/or fp16.
-// One thread per (row, 8 channels): 16-byte loads/stores.
-__global__ void affine_rows_kernel(const __half* __restrict__ x, long long ldx, const int* __restrict__ rows,
-                                   int nrows, int C, const float* __restrict__ scale,
-                                   const float* __restrict__ shift, int act, const float* __restrict__ resid,
-                                   long long ldr, float* __restrict__ out32, long long ldo32,
-                                   __half* __restrict__ out16, long long ldo16,
-                                   const float* __restrict__ row_scale) {
-  const int c8 = (C + 7) >> 3;
-  const long long total = (long long)nrows * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % c8) * 8;
-    const long long row = rows ? rows[i / c8] : i / c8;
-    const float rsc = row_scale ? row_scale[row] : 1.f;  // stochastic-depth mask / keep of this row
-    float v[8];
-    if (j + 8 <= C) {
+// y = act(x16[row]*scale + shift) * row_scale (+ resid32[row]) for the listed rows; writes fp32 and/or fp16.
+// One thread per (row, 8 channels) with 32-bit index math: one 16-byte fp16 load (the row stride is padded to a
+// multiple of 8, so the last chunk of C = 196 reads its 4 padding columns too), float4 scale / shift / residual
+// accesses, one 16-byte fp16 store (padding columns are written as zeros). VEC4 = every fp32 row is 16-byte aligned.
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+affine_rows_kernel(const __half* __restrict__ x, long long ldx, const int* __restrict__ rows, int nrows, int C,
+                   const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                   const float* __restrict__ resid, long long ldr, float* __restrict__ out32, long long ldo32,
+                   __half* __restrict__ out16, long long ldo16, const float* __restrict__ row_scale) {
+  const unsigned c8 = (unsigned)(C + 7) >> 3;
+  const unsigned total = (unsigned)nrows * c8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned ri = i / c8;
+    const int j = (int)(i - ri * c8) * 8;
+    const long long row = rows ? rows[ri] : (long long)ri;
+    const float rsc = row_scale ? __ldg(row_scale + row) : 1.f;  // stochastic-depth mask / keep of this row
+    const int nv = min(8, C - j);                                // valid channels of this chunk (4 or 8 with VEC4)
+    float v[8], sc[8], sh[8], rr[8];
+    {
       const uint4 pk = *reinterpret_cast<const uint4*>(x + row * ldx + j);
       const __half2* h = reinterpret_cast<const __half2*>(&pk);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        v[2 * u] = __low2float(h[u]);
-        v[2 * u + 1] = __high2float(h[u]);
+      for (int u = 0; u < 4; ++u) v[2 * u] = __low2float(h[u]), v[2 * u + 1] = __high2float(h[u]);
+    }
+    if (VEC4) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (4 * hf < nv) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(scale + j) + hf), b = __ldg(reinterpret_cast<const float4*>(shift + j) + hf);
+          sc[4 * hf] = a.x, sc[4 * hf + 1] = a.y, sc[4 * hf + 2] = a.z, sc[4 * hf + 3] = a.w;
+          sh[4 * hf] = b.x, sh[4 * hf + 1] = b.y, sh[4 * hf + 2] = b.z, sh[4 * hf + 3] = b.w;
+          if (resid) {
+            const float4 r4 = *(reinterpret_cast<const float4*>(resid + row * ldr + j) + hf);
+            rr[4 * hf] = r4.x, rr[4 * hf + 1] = r4.y, rr[4 * hf + 2] = r4.z, rr[4 * hf + 3] = r4.w;
+          }
+        }
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = j + u < C ? __half2float(x[row * ldx + j + u]) : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        if (u < nv) {
+          sc[u] = __ldg(scale + j + u), sh[u] = __ldg(shift + j + u);
+          if (resid) rr[u] = resid[row * ldr + j + u];
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      if (j + u < C) {
-        float y = fmaf(v[u], scale[j + u], shift[j + u]);
+      float y = 0.f;
+      if (u < nv) {
+        y = fmaf(v[u], sc[u], sh[u]);
         if (act == FVIT_ACT_RELU) y = fmaxf(y, 0.f);
         else if (act == FVIT_ACT_GELU) y = fvit_gelu(y);
         y *= rsc;
-        if (resid) y += resid[row * ldr + j + u];
-        v[u] = y;
+        if (resid) y += rr[u];
       }
+      v[u] = y;
     }
     if (out32) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (j + u < C) out32[row * ldo32 + j + u] = v[u];
-    }
-    if (out16) {
-      if (j + 8 <= C) {
-        __half2 h[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
-        *reinterpret_cast<uint4*>(out16 + row * ldo16 + j) = *reinterpret_cast<const uint4*>(h);
+      float* o = out32 + row * ldo32 + j;
+      if (VEC4) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        if (nv > 4) *(reinterpret_cast<float4*>(o) + 1) = make_float4(v[4], v[5], v[6], v[7]);
       } else {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (j + u < C) out16[row * ldo16 + j + u] = __float2half_rn(v[u]);
+          if (u < nv) o[u] = v[u];
       }
+    }
+    if (out16) {
+      __half2 h[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+      *reinterpret_cast<uint4*>(out16 + row * ldo16 + j) = *reinterpret_cast<const uint4*>(h);   // j + 8 <= ldo16
     }
   }
 }
@@ -1046,6 +1066,185 @@ bn_bwd_apply_v4_kernel(const void* __restrict__ gin, long long ldg, const int* _
   }
 }
 
+// ---- 8-channel (16-byte fp16 / 2 x float4 fp32) versions: a lane owns 8 channels of a row, vpr lanes cover a row
+// (C = 196 -> 25 chunks -> 32 lanes), 256 / vpr rows per block pass, two rows per trip. Rows are padded to multiples
+// of 8 columns, so the last chunk reads (and writes, as zeros) its padding columns.
+template <int G16>
+__device__ __forceinline__ void bn_load_dy8(const void* g, long long off, int nv, float (&d)[8]) {
+  if (G16) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g) + off);
+    const __half2* h = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[2 * u] = __low2float(h[u]), d[2 * u + 1] = __high2float(h[u]);
+  } else {
+    const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g) + off);
+    const float4 a = p4[0];
+    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
+    if (nv > 4) {
+      const float4 b = p4[1];
+      d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+    } else {
+      d[4] = d[5] = d[6] = d[7] = 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void bn_load_x8(const __half* p, float (&x)[8]) {
+  const uint4 pk = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) x[2 * u] = __low2float(h[u]), x[2 * u + 1] = __high2float(h[u]);
+}
+struct BnCols8 {
+  float mu[8], rs[8], wc[8], bc[8], cm[8];
+};
+__device__ __forceinline__ void bn_load_cols8(BnCols8& k, int c, int nv, const float* mean, const float* rstd, const float* w,
+                                              const float* b, const float* colmul) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const bool in = u < nv;
+    k.mu[u] = in ? __ldg(mean + c + u) : 0.f, k.rs[u] = in ? __ldg(rstd + c + u) : 0.f;
+    k.wc[u] = in ? __ldg(w + c + u) : 0.f, k.bc[u] = in ? __ldg(b + c + u) : 0.f;
+    k.cm[u] = in ? (colmul ? __ldg(colmul + c + u) : 1.f) : 0.f;
+  }
+}
+template <int G16>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_v8_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
+                        const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows, int nrows, int C,
+                        int vpr, const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ w, const float* __restrict__ b, int act,
+                        const float* __restrict__ colmul, float* __restrict__ s1, float* __restrict__ s2,
+                        const float* __restrict__ row_scale) {
+  __shared__ float red[2][8][257];
+  const int cx = threadIdx.x % vpr, rl = threadIdx.x / vpr, RL = 256 / vpr;
+  const int c = (blockIdx.y * vpr + cx) * 8;
+  const int nv = min(8, C - c);
+  float a1[8], a2[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a1[u] = a2[u] = 0.f;
+  if (nv > 0) {
+    BnCols8 k;
+    bn_load_cols8(k, c, nv, mean, rstd, w, b, colmul);
+    const bool relu = act == FVIT_ACT_RELU;
+    const bool same_rows = g_rows == r_rows;
+    const int rstep = gridDim.x * RL;
+    for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += 2 * rstep) {
+      long long rg[2], rr[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int r = r0 + t * rstep;
+        rg[t] = r < nrows ? (g_rows ? (long long)g_rows[r] : (long long)r) : -1;
+        rr[t] = same_rows ? rg[t] : (r < nrows ? (r_rows ? (long long)r_rows[r] : (long long)r) : -1);
+      }
+      float dy[2][8], x[2][8], rsc[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (rg[t] >= 0) {
+          bn_load_dy8<G16>(gin, rg[t] * ldg + c, nv, dy[t]);
+          bn_load_x8(raw + rr[t] * ldr + c, x[t]);
+          rsc[t] = row_scale ? row_scale[rg[t]] : 1.f;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dy[t][u] = 0.f, x[t][u] = 0.f;
+          rsc[t] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float xh = (x[t][u] - k.mu[u]) * k.rs[u];
+          float d = dy[t][u] * k.cm[u] * rsc[t];
+          if (relu && fmaf(xh, k.wc[u], k.bc[u]) <= 0.f) d = 0.f;
+          a1[u] += d;
+          a2[u] = fmaf(d, xh, a2[u]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[0][u][threadIdx.x] = a1[u], red[1][u][threadIdx.x] = a2[u];
+  __syncthreads();
+  // 2 x 8 x vpr column sums of RL partials each
+  for (int q = threadIdx.x; q < 16 * vpr; q += 256) {
+    const int which = q / (8 * vpr), u = (q / vpr) & 7, lane = q % vpr;
+    const int cc = (blockIdx.y * vpr + lane) * 8 + u;
+    if (cc < C) {
+      float t = 0.f;
+      for (int kk = 0; kk < RL; ++kk) t += red[which][u][kk * vpr + lane];
+      atomicAdd((which ? s2 : s1) + cc, t);
+    }
+  }
+}
+template <int G16>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_v8_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
+                       const __half* __restrict__ raw, long long ldr, const int* __restrict__ r_rows, int nrows, int C,
+                       int vpr, float inv_count, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ w, const float* __restrict__ b, int act,
+                       const float* __restrict__ colmul, const float* __restrict__ s1, const float* __restrict__ s2,
+                       const float* __restrict__ scalar, __half* __restrict__ out, long long ldo,
+                       const int* __restrict__ o_rows, float* __restrict__ dw, float* __restrict__ db,
+                       const float* __restrict__ row_scale) {
+  const int cx = threadIdx.x % vpr, rl = threadIdx.x / vpr, RL = 256 / vpr;
+  const int c = (blockIdx.y * vpr + cx) * 8;
+  const int nv = min(8, C - c);
+  if (nv <= 0) return;
+  BnCols8 k;
+  bn_load_cols8(k, c, nv, mean, rstd, w, b, colmul);
+  float m1[8], m2[8], kk[8], t1[8], t2[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    t1[u] = u < nv ? s1[c + u] : 0.f, t2[u] = u < nv ? s2[c + u] : 0.f;
+    m1[u] = t1[u] * inv_count, m2[u] = t2[u] * inv_count, kk[u] = k.wc[u] * k.rs[u];
+  }
+  const bool relu = act == FVIT_ACT_RELU;
+  const bool same_rows = g_rows == r_rows, same_out = o_rows == g_rows;
+  const int rstep = gridDim.x * RL;
+  for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += 2 * rstep) {
+    long long rg[2], rr[2], ro[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int r = r0 + t * rstep;
+      const bool ok = r < nrows;
+      rg[t] = ok ? (g_rows ? (long long)g_rows[r] : (long long)r) : -1;
+      rr[t] = same_rows ? rg[t] : (ok ? (r_rows ? (long long)r_rows[r] : (long long)r) : -1);
+      ro[t] = same_out ? rg[t] : (ok ? (o_rows ? (long long)o_rows[r] : (long long)r) : -1);
+    }
+    float dy[2][8], x[2][8], rsc[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (rg[t] >= 0) {
+        bn_load_dy8<G16>(gin, rg[t] * ldg + c, nv, dy[t]);
+        bn_load_x8(raw + rr[t] * ldr + c, x[t]);
+        rsc[t] = row_scale ? row_scale[rg[t]] : 1.f;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (rg[t] < 0) continue;
+      float o[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float xh = (x[t][u] - k.mu[u]) * k.rs[u];
+        float d = dy[t][u] * k.cm[u] * rsc[t];
+        if (relu && fmaf(xh, k.wc[u], k.bc[u]) <= 0.f) d = 0.f;
+        o[u] = u < nv ? kk[u] * (d - m1[u] - xh * m2[u]) : 0.f;
+      }
+      __half2 h[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(o[2 * u], o[2 * u + 1]);
+      *reinterpret_cast<uint4*>(out + ro[t] * ldo + c) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+  if (blockIdx.x == 0 && rl == 0) {
+    const float sc = scalar ? __ldg(scalar) : 1.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (u < nv) dw[c + u] += t2[u] * sc, db[c + u] += t1[u] * sc;
+  }
+}
+
 // conv weight gradient repack: dst[co][ci][tap] += src[co][tap * cin + ci] (src row stride ld)
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int cout,
                                         int cin) {
@@ -1269,9 +1468,20 @@ int fvit_affine_rows(const void* x16, int64_t ldx, const int32_t* rows, int32_t 
   FVIT_CHECK(x16 && scale && shift && nrows > 0 && C > 0 && (out32 || out16), "fvit_affine_rows: bad arguments");
   FVIT_CHECK(ldx % 8 == 0 && (!out16 || ldo16 % 8 == 0), "fvit_affine_rows: fp16 strides must be multiples of 8");
   const long long total = (long long)nrows * ((C + 7) / 8);
-  affine_rows_kernel<<<grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)x16, ldx, rows, nrows, C, scale, shift, act, resid, ldr, out32, ldo32, (__half*)out16, ldo16,
-      row_scale);
+  FVIT_CHECK(total < (1LL << 31), "fvit_affine_rows: %lld chunks exceed the 32-bit index range", total);
+  FVIT_CHECK((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (!out16 || (reinterpret_cast<uintptr_t>(out16) & 15) == 0),
+             "fvit_affine_rows: fp16 buffers must be 16-byte aligned");
+  // float4 accesses of the fp32 vectors / rows: C % 4 == 0 keeps every 8-chunk at 4 or 8 valid channels
+  const bool vec4 = C % 4 == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0 &&
+                    (!resid || (ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0)) &&
+                    (!out32 || (ldo32 % 4 == 0 && (reinterpret_cast<uintptr_t>(out32) & 15) == 0));
+  const int grid = grid_cap(total, 256, 16);
+  if (vec4)
+    affine_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x16, ldx, rows, nrows, C, scale, shift, act,
+                                                                     resid, ldr, out32, ldo32, (__half*)out16, ldo16, row_scale);
+  else
+    affine_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x16, ldx, rows, nrows, C, scale, shift, act,
+                                                                      resid, ldr, out32, ldo32, (__half*)out16, ldo16, row_scale);
   return post_launch("affine_rows_kernel");
 }
 
@@ -1499,6 +1709,37 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
   const bool vec = C % 4 == 0 && ldg % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(gin) % 16 == 0) && (reinterpret_cast<uintptr_t>(raw16) % 8 == 0) &&
                    (reinterpret_cast<uintptr_t>(out16) % 8 == 0);
+  const bool vec8 = vec && ldr % 8 == 0 && ldo % 8 == 0 && (g_is_f16 ? ldg % 8 == 0 : true) &&
+                    (reinterpret_cast<uintptr_t>(raw16) % 16 == 0) && (reinterpret_cast<uintptr_t>(out16) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(gin) % 16 == 0);
+  if (vec8) {
+    const int c8 = (C + 7) / 8;
+    int vpr = 1;
+    while (vpr < 64 && vpr < c8) vpr *= 2;
+    const unsigned gy = (unsigned)((c8 + vpr - 1) / vpr);
+    const int RL = 256 / vpr;
+    long long gx = ((long long)num_sms() * 6 + gy - 1) / gy;
+    const long long gx_max = ((long long)nrows + RL * 2 - 1) / (RL * 2);
+    if (gx > gx_max) gx = gx_max;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, gy);
+    const float inv = 1.f / (float)nrows;
+    if (g_is_f16) {
+      bn_bwd_reduce_v8_kernel<1><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                       mean, rstd, w, b, act, colmul, s1, s2, row_scale);
+      bn_bwd_apply_v8_kernel<1><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                      inv, mean, rstd, w, b, act, colmul, s1, s2, scalar,
+                                                      (__half*)out16, ldo, o_rows, dw, db, row_scale);
+    } else {
+      bn_bwd_reduce_v8_kernel<0><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                       mean, rstd, w, b, act, colmul, s1, s2, row_scale);
+      bn_bwd_apply_v8_kernel<0><<<grid, 256, 0, st>>>(gin, ldg, g_rows, (const __half*)raw16, ldr, r_rows, nrows, C, vpr,
+                                                      inv, mean, rstd, w, b, act, colmul, s1, s2, scalar,
+                                                      (__half*)out16, ldo, o_rows, dw, db, row_scale);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return post_launch("bn_bwd v8 kernels");
+  }
   if (vec) {
     int vpr = 1;
     while (vpr < 64 && vpr < C / 4) vpr *= 2;

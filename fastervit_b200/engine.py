@@ -80,8 +80,12 @@ class Plan:
         self._x_args: list = []           # stem-conv calls that take the input pointer at run time
         self.op_flops: dict[int, float] = {}  # op index -> algorithmic FLOPs (GEMM launches)
         # FVIT_FUSED_HAT=0 falls back to the three-launch attention (qkv GEMM, attention core, proj GEMM) for A/B runs
+        # FVIT_FUSED_HAT: "0" = always the three-launch attention (qkv GEMM, attention core, proj GEMM), "1" = the fused
+        # kernel wherever it applies; default = fused for 64-wide (padded) heads, where its one epilogue warpgroup keeps
+        # up with the projection MMAs (fv4 forward: 4.19 ms vs 2.48 + 1.95 ms; measured r02d) — with 32-wide heads the
+        # per-item projection is 4x shorter and the two-CTA-per-SM attention core wins (fv0: 1.80 vs 0.66 + 0.99 ms)
         import os
-        self.fused_hat = os.environ.get("FVIT_FUSED_HAT", "1") != "0"
+        self.fused_hat = os.environ.get("FVIT_FUSED_HAT", "auto")
         self.use_graphs = os.environ.get("FVIT_CUDA_GRAPH", "1") != "0" and device.type == "cuda"
         self._graphs: dict = {}
         self._x_static = None
@@ -470,7 +474,8 @@ class Plan:
                 self._op(self.prep_ops, "fvit_vec_headpad_f32", qb.data_ptr(), qbp.data_ptr(), 3 * Cp, hd, hdp)
                 qb_ptr = qbp.data_ptr()
         scale = float(hd ** -0.5)
-        fused = self.fused_hat and self._attn_kind(S, hdp) == "tile"
+        fused = (self._attn_kind(S, hdp) == "tile" and self.fused_hat != "0"
+                 and (self.fused_hat == "1" or hdp == 64))
         if fused:
             # ONE kernel: qkv projection + softmax(q k^T * scale + bias) + P v; the qkv matrix never reaches HBM
             self._op(self.ops, "fvit_hat_attn_fwd", xin.data_ptr(), ld_in, Cc, wq.data_ptr(), ldq, qb_ptr, groups, S, h,

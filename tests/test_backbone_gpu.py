@@ -60,9 +60,10 @@ def test_backbone_interface():
         assert (o - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
     d = bb(x, mask)
     assert set(d) == {0, 1, 2} and d[2][1].shape == (2, 5, 7) and d[0][1][1, :, -1].all() and not d[0][1][0].any()
-    # a second input size builds a second plan (dynamic H x W per batch)
-    x2 = O.synth_input(1, [192, 160], 4, torch.float32).cuda()
-    assert [tuple(o.shape) for o in bb.forward_raw(x2)] == [(1, 32, 24, 20), (1, 64, 12, 10), (1, 128, 6, 5)]
+    # a second input size builds a second plan (dynamic H x W per batch; like the reference any-res model the carrier
+    # grid is fixed at construction, so the size must give the same number of level-2 windows: 10 x 14 -> 2 x 3)
+    x2 = O.synth_input(1, [152, 216], 4, torch.float32).cuda()
+    assert [tuple(o.shape) for o in bb.forward_raw(x2)] == [(1, 32, 19, 27), (1, 64, 10, 14), (1, 128, 5, 7)]
 
 
 def test_switch_to_deploy_freezes_positional_tables():

@@ -77,30 +77,35 @@ def test_ln_bwd_matches_autograd(rows, C, mapped):
     _close(dx, xr.grad, 3e-3, "formula")
 
 
-@pytest.mark.parametrize("rows,C,act", [(784, 64, 0), (300, 200, 1), (1568, 392, 0), (50, 16, 1)])
+@pytest.mark.parametrize("rows,C,act", [(784, 64, 0), (300, 200, 1), (1568, 392, 0), (50, 16, 1), (900, 196, 0), (333, 36, 1)])
 @pytest.mark.parametrize("g_is_f16", [0, 1])
 def test_bn_bwd_matches_autograd(rows, C, act, g_is_f16):
-    """fvit_bn_bwd vs autograd of train-mode BatchNorm (+ReLU) over a list of rows of a raw convolution output."""
+    """fvit_bn_bwd vs autograd of train-mode BatchNorm (+ReLU) over a list of rows of a raw convolution output; fp16
+    rows are padded to a multiple of 8 columns like the level buffers (fv4: C = 196 -> 200)."""
     from fastervit_b200 import lib as L
     g = torch.Generator().manual_seed(rows + C + act)
     pad = 5   # the row lists address a larger, bordered buffer
-    raw16 = (torch.randn(rows + pad, C, generator=g) * 2 + 0.5).half()
+    ld = (C + 7) // 8 * 8
+    raw16 = torch.zeros(rows + pad, ld, dtype=torch.float16)
+    raw16[:, :C] = (torch.randn(rows + pad, C, generator=g) * 2 + 0.5).half()
     r_rows = (torch.randperm(rows + pad, generator=g)[:rows]).to(torch.int32)
     gin = torch.randn(rows + pad, C, generator=g) * 0.3
-    gin = gin.half() if g_is_f16 else gin
+    if g_is_f16:
+        g16 = torch.zeros(rows + pad, ld, dtype=torch.float16)
+        g16[:, :C] = gin.half()
+        gin_dev, ldg, gin = g16, ld, g16[:, :C]
+    else:
+        gin_dev, ldg = gin, C
     g_rows = (torch.randperm(rows + pad, generator=g)[:rows]).to(torch.int32)
     o_rows = (torch.randperm(rows + pad, generator=g)[:rows]).to(torch.int32)
     w = torch.rand(C, generator=g) + 0.5
     b = torch.randn(C, generator=g) * 0.2
     colmul = torch.rand(C, generator=g) + 0.5
     rsc = (torch.rand(rows + pad, generator=g) > 0.3).float() * 1.25
-    xr = raw16[r_rows.long()].double().requires_grad_(True)
+    xr = raw16[r_rows.long(), :C].double().requires_grad_(True)
     mean, var = xr.mean(0), xr.var(0, unbiased=False)
     eps = 1e-5
     rstd = (var + eps).rsqrt()
-    y = (xr - mean) * rstd * w.double() + b.double()
-    if act == 1:
-        y = torch.relu(y)
     wd = w.double().clone().requires_grad_(True)   # separate leaves for dw / db
     bd = b.double().clone().requires_grad_(True)
     y2 = (xr - mean) * rstd * wd + bd
@@ -109,46 +114,50 @@ def test_bn_bwd_matches_autograd(rows, C, act, g_is_f16):
     upstream = gin[g_rows.long()].double() * colmul.double() * rsc[g_rows.long()].double().view(-1, 1)
     y2.backward(upstream)
     scal = 0.5
-    out16 = torch.zeros(rows + pad, C, dtype=torch.float16, device="cuda")
+    out16 = torch.zeros(rows + pad, ld, dtype=torch.float16, device="cuda")
     s1, s2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dw, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    L.call("fvit_bn_bwd", _dev(gin), g_is_f16, C, _dev(g_rows), _dev(raw16), C,
+    L.call("fvit_bn_bwd", _dev(gin_dev), g_is_f16, ldg, _dev(g_rows), _dev(raw16), ld,
            _dev(r_rows), rows, C, _dev(mean.detach().float()), _dev(rstd.detach().float()),
            _dev(w), _dev(b), act, _dev(colmul), s1.data_ptr(), s2.data_ptr(),
-           _scalar(scal).data_ptr(), out16.data_ptr(), C, _dev(o_rows), dw.data_ptr(), db.data_ptr(),
+           _scalar(scal).data_ptr(), out16.data_ptr(), ld, _dev(o_rows), dw.data_ptr(), db.data_ptr(),
            _dev(rsc))
     torch.cuda.synchronize()
-    _close(out16[o_rows.long().cuda()], xr.grad, 2e-3, "dx")
+    _close(out16[o_rows.long().cuda()][:, :C], xr.grad, 2e-3, "dx")
     _close(dw, scal * wd.grad, 2e-4, "dw")
     _close(db, scal * bd.grad, 2e-4, "db")
 
 
-@pytest.mark.parametrize("rows,C,act", [(640, 64, 2), (333, 200, 1), (100, 392, 0)])
+@pytest.mark.parametrize("rows,C,act", [(640, 64, 2), (333, 200, 1), (100, 392, 0), (500, 196, 2), (77, 36, 1)])
 def test_affine_rows_matches_torch(rows, C, act):
-    """fvit_affine_rows: y = act(x16*scale + shift) * row_scale (+ resid) over a row list, fp32 and fp16 outputs."""
+    """fvit_affine_rows: y = act(x16*scale + shift) * row_scale (+ resid) over a row list, fp32 and fp16 outputs.
+    fp16 rows are padded to a multiple of 8 columns like the level buffers (fv4: C = 196 -> 200)."""
     from fastervit_b200 import lib as L
     g = torch.Generator().manual_seed(rows + C)
     total = rows + 7
-    x16 = (torch.randn(total, C, generator=g) * 1.5).half()
+    ld = (C + 7) // 8 * 8
+    x16 = torch.zeros(total, ld, dtype=torch.float16)
+    x16[:, :C] = (torch.randn(total, C, generator=g) * 1.5).half()
     rowsel = torch.randperm(total, generator=g)[:rows].to(torch.int32)
     scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
     resid = torch.randn(total, C, generator=g)
     rsc = (torch.rand(total, generator=g) > 0.3).float() / 0.7
-    v = x16.double() * scale.double() + shift.double()
+    v = x16[:, :C].double() * scale.double() + shift.double()
     if act == 1:
         v = torch.relu(v)
     elif act == 2:
         v = torch.nn.functional.gelu(v)
     ref = v * rsc.double().view(-1, 1) + resid.double()
     o32 = torch.zeros(total, C, device="cuda")
-    o16 = torch.zeros(total, C, dtype=torch.float16, device="cuda")
-    L.call("fvit_affine_rows", _dev(x16), C, _dev(rowsel), rows, C, _dev(scale),
-           _dev(shift), act, _dev(resid), C, o32.data_ptr(), C, o16.data_ptr(), C,
-           _dev(rsc))
+    o16 = torch.full((total, ld), 3.0, dtype=torch.float16, device="cuda")
+    L.call("fvit_affine_rows", _dev(x16), ld, _dev(rowsel), rows, C, _dev(scale), _dev(shift), act, _dev(resid), C,
+           o32.data_ptr(), C, o16.data_ptr(), ld, _dev(rsc))
     torch.cuda.synchronize()
     sel = rowsel.long()
     _close(o32[sel.cuda()], ref[sel], 2e-6 if act != 2 else 2e-6 + 3e-7, "out32")   # A-S erf: |error| < 1.5e-7 absolute
-    _close(o16[sel.cuda()], ref[sel], 1e-3, "out16")
+    _close(o16[sel.cuda()][:, :C], ref[sel], 1e-3, "out16")
+    if ld > C:
+        assert o16[sel.cuda()][:, C:].abs().max().item() == 0.0      # padding columns are written as zeros
     untouched = torch.ones(total, dtype=torch.bool)
     untouched[sel] = False
     assert o32[untouched.cuda()].abs().max().item() == 0.0
