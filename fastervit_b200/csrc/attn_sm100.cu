@@ -434,13 +434,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     mbar_init(tmem_empty, 4);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // scores / dP and the three gradient accumulators live in disjoint TMEM columns: the S / dP MMAs of item i+1 are
+  // issued while the softmax warps still drain the gradients of item i
   const uint32_t tS = tmem_base, tDP = tmem_base + 128;
-  const uint32_t tDV = tmem_base, tDK = tmem_base + 64, tDQ = tmem_base + 128;
+  const uint32_t tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
   const int items = p.tiles * p.heads;
   const int nslots = AT_ROWS / p.slot;
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&ld_full[st], ph);
-        mbar_wait(tmem_empty, (it & 1) ^ 1);
+        // (S / dP of the previous item were consumed before its P / dS tiles were published: pds_full, waited below)
         tc_fence_after();
         const uint32_t sQ = smem_u32(smem + st * STAGE_BYTES);
         const uint32_t sK = sQ + TILE_BYTES, sV = sQ + 2 * TILE_BYTES, sDO = sQ + 3 * TILE_BYTES;
@@ -492,6 +494,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         }
         umma_commit(sdp_full);
         mbar_wait(pds_full, it & 1);
+        mbar_wait(tmem_empty, (it & 1) ^ 1);  // the previous item's dV / dK / dQ have been read out
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows in steps of 16
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -17,8 +17,12 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent
 PKG = CSRC.parent
 ROOT = PKG.parent
-LIB_PATH = PKG / "libfvit_sm100.so"
-OBJ_DIR = CSRC / "build"
+# A/B builds: FVIT_BUILD_DEFINES="-DFVIT_GEMM_NEPI=12" FVIT_BUILD_OUT=libfvit_sm100_e12.so python -m fastervit_b200.csrc.build
+# (select at run time with FVIT_LIB=<path>); the default build takes neither.
+_EXTRA = os.environ.get("FVIT_BUILD_DEFINES", "").split()
+_OUT = os.environ.get("FVIT_BUILD_OUT", "libfvit_sm100.so")
+LIB_PATH = PKG / _OUT
+OBJ_DIR = CSRC / ("build" if _OUT == "libfvit_sm100.so" else "build_" + Path(_OUT).stem)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -26,6 +30,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-I", str(ROOT / "include"),
+    *_EXTRA,
 ]
 
 

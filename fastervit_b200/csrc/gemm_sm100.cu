@@ -28,7 +28,13 @@ namespace fvit {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B: one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
+#ifndef FVIT_GEMM_NEPI
+#define FVIT_GEMM_NEPI 8
+#endif
+constexpr int NEPI = FVIT_GEMM_NEPI;            // epilogue warps: a multiple of 4 (one TMEM lane quadrant each)
+constexpr int EPI_THREADS = 32 * NEPI;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;  // TMA warp + MMA warp + the epilogue warps
+static_assert(NEPI % 4 == 0 && NEPI >= 8 && NEPI <= 16, "epilogue warps come in groups of four");
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int TMEM_COLS = 512;
@@ -37,7 +43,7 @@ constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem base, placed after the stage ring
 constexpr int SMEM_ALIGN_SLACK = 1024;
 constexpr int STG_LD = 36;  // floats per staging row: 32 + 4 pad -> conflict-free float4 access both ways
-constexpr int SMEM_STG_BYTES = 8 * 32 * STG_LD * 4;  // one 32x32 fp32 staging tile per epilogue warp
+constexpr int SMEM_STG_BYTES = NEPI * 32 * STG_LD * 4;  // one 32x32 fp32 staging tile per epilogue warp
 constexpr int STATS_MAX_N = 1024;                    // widest GEMM with per-column statistics (BatchNorm channels)
 constexpr int SMEM_STATS_BYTES = 2 * STATS_MAX_N * 4;
 
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int s = 0; s < p.nacc; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8 * cg);  // the leader's copy collects the epilogue warps of both CTAs
+      mbar_init(&acc_empty[s], NEPI * cg);  // the leader's copy collects the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -387,11 +393,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const float alpha = has_aptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     if (stats) {
       for (int i = threadIdx.x - 64; i < 2 * p.n; i += GEMM_THREADS - 64) stat_s[i] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // the epilogue warps only
     }
     if (osum) {  // tile-local column sums: stat_s[0 .. tile_n)
-      stat_s[threadIdx.x - 64] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x - 64 < 256) stat_s[threadIdx.x - 64] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
     }
     const float osum_alpha = (osum && p.osum_alpha) ? __ldg(p.osum_alpha) : 1.f;
     int acc = 0;
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       bool waited = false;
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16);
 
-      for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 64) {
+      for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 32 * (NEPI / 4)) {
         const int nbase = n0 + c0;
         if (nbase >= n_end) break;  // warp-uniform
         const int col = nbase + 4 * c4;            // first of this lane's 4 columns
@@ -652,14 +658,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_fence_after();
       }
       if (osum) {  // flush this tile's column sums: one global atomic per column per tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         const int lc = threadIdx.x - 64;
         if (lc < p.tile_n && n0 + lc < n_end) {
           const float a = stat_s[lc];
           if (a != 0.f) atomicAdd(p.osum + n0 + lc, a * osum_alpha);
         }
-        stat_s[lc] = 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lc < 256) stat_s[lc] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       }
       // hand the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -674,7 +680,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
     if (stats) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       for (int i = threadIdx.x - 64; i < p.n; i += GEMM_THREADS - 64) {
         const float a = stat_s[i], b = stat_s[p.n + i];
         if (a != 0.f || b != 0.f) {

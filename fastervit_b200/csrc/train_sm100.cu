@@ -1069,27 +1069,33 @@ bn_bwd_apply_v4_kernel(const void* __restrict__ gin, long long ldg, const int* _
 // ---- 8-channel (16-byte fp16 / 2 x float4 fp32) versions: a lane owns 8 channels of a row, vpr lanes cover a row
 // (C = 196 -> 25 chunks -> 32 lanes), 256 / vpr rows per block pass, two rows per trip. Rows are padded to multiples
 // of 8 columns, so the last chunk reads (and writes, as zeros) its padding columns.
+// a row's 8-channel chunk is held packed (uint4 of halves, or two float4) between the load and the math so that four
+// rows can be in flight per thread without spilling
 template <int G16>
-__device__ __forceinline__ void bn_load_dy8(const void* g, long long off, int nv, float (&d)[8]) {
-  if (G16) {
-    const uint4 pk = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g) + off);
-    const __half2* h = reinterpret_cast<const __half2*>(&pk);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) d[2 * u] = __low2float(h[u]), d[2 * u + 1] = __high2float(h[u]);
-  } else {
-    const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g) + off);
-    const float4 a = p4[0];
-    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w;
-    if (nv > 4) {
-      const float4 b = p4[1];
-      d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+struct BnDy8 {
+  uint4 a, b;  // G16: a = 8 halves; fp32: a, b = 2 x 4 floats
+  __device__ __forceinline__ void load(const void* g, long long off, int nv) {
+    if (G16) {
+      a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g) + off);
     } else {
-      d[4] = d[5] = d[6] = d[7] = 0.f;
+      const uint4* p4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(g) + off);
+      a = p4[0];
+      b = nv > 4 ? p4[1] : make_uint4(0u, 0u, 0u, 0u);
     }
   }
-}
-__device__ __forceinline__ void bn_load_x8(const __half* p, float (&x)[8]) {
-  const uint4 pk = *reinterpret_cast<const uint4*>(p);
+  __device__ __forceinline__ void zero() { a = b = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void unpack(float (&d)[8]) const {
+    if (G16) {
+      const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[2 * u] = __low2float(h[u]), d[2 * u + 1] = __high2float(h[u]);
+    } else {
+      d[0] = __uint_as_float(a.x), d[1] = __uint_as_float(a.y), d[2] = __uint_as_float(a.z), d[3] = __uint_as_float(a.w);
+      d[4] = __uint_as_float(b.x), d[5] = __uint_as_float(b.y), d[6] = __uint_as_float(b.z), d[7] = __uint_as_float(b.w);
+    }
+  }
+};
+__device__ __forceinline__ void bn_unpack_x8(const uint4& pk, float (&x)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&pk);
 #pragma unroll
   for (int u = 0; u < 4; ++u) x[2 * u] = __low2float(h[u]), x[2 * u + 1] = __high2float(h[u]);
@@ -1107,6 +1113,7 @@ __device__ __forceinline__ void bn_load_cols8(BnCols8& k, int c, int nv, const f
     k.cm[u] = in ? (colmul ? __ldg(colmul + c + u) : 1.f) : 0.f;
   }
 }
+constexpr int BN8_ROWS = 4;  // rows per trip: all index loads, then all data loads, then the math
 template <int G16>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_v8_kernel(const void* __restrict__ gin, long long ldg, const int* __restrict__ g_rows,
@@ -1128,33 +1135,38 @@ bn_bwd_reduce_v8_kernel(const void* __restrict__ gin, long long ldg, const int* 
     const bool relu = act == FVIT_ACT_RELU;
     const bool same_rows = g_rows == r_rows;
     const int rstep = gridDim.x * RL;
-    for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += 2 * rstep) {
-      long long rg[2], rr[2];
+    for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += BN8_ROWS * rstep) {
+      long long rg[BN8_ROWS], rr[BN8_ROWS];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < BN8_ROWS; ++t) {
         const int r = r0 + t * rstep;
         rg[t] = r < nrows ? (g_rows ? (long long)g_rows[r] : (long long)r) : -1;
         rr[t] = same_rows ? rg[t] : (r < nrows ? (r_rows ? (long long)r_rows[r] : (long long)r) : -1);
       }
-      float dy[2][8], x[2][8], rsc[2];
+      BnDy8<G16> dyp[BN8_ROWS];
+      uint4 xp[BN8_ROWS];
+      float rsc[BN8_ROWS];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < BN8_ROWS; ++t) {
         if (rg[t] >= 0) {
-          bn_load_dy8<G16>(gin, rg[t] * ldg + c, nv, dy[t]);
-          bn_load_x8(raw + rr[t] * ldr + c, x[t]);
+          dyp[t].load(gin, rg[t] * ldg + c, nv);
+          xp[t] = *reinterpret_cast<const uint4*>(raw + rr[t] * ldr + c);
           rsc[t] = row_scale ? row_scale[rg[t]] : 1.f;
         } else {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) dy[t][u] = 0.f, x[t][u] = 0.f;
+          dyp[t].zero();
+          xp[t] = make_uint4(0u, 0u, 0u, 0u);
           rsc[t] = 0.f;
         }
       }
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < BN8_ROWS; ++t) {
+        float dyt[8], xt[8];
+        dyp[t].unpack(dyt);
+        bn_unpack_x8(xp[t], xt);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const float xh = (x[t][u] - k.mu[u]) * k.rs[u];
-          float d = dy[t][u] * k.cm[u] * rsc[t];
+          const float xh = (xt[u] - k.mu[u]) * k.rs[u];
+          float d = dyt[u] * k.cm[u] * rsc[t];
           if (relu && fmaf(xh, k.wc[u], k.bc[u]) <= 0.f) d = 0.f;
           a1[u] += d;
           a2[u] = fmaf(d, xh, a2[u]);
@@ -1201,33 +1213,37 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ gin, long long ldg, const int* _
   const bool relu = act == FVIT_ACT_RELU;
   const bool same_rows = g_rows == r_rows, same_out = o_rows == g_rows;
   const int rstep = gridDim.x * RL;
-  for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += 2 * rstep) {
-    long long rg[2], rr[2], ro[2];
+  for (int r0 = blockIdx.x * RL + rl; r0 < nrows; r0 += BN8_ROWS * rstep) {
+    long long rg[BN8_ROWS], rr[BN8_ROWS], ro[BN8_ROWS];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < BN8_ROWS; ++t) {
       const int r = r0 + t * rstep;
       const bool ok = r < nrows;
       rg[t] = ok ? (g_rows ? (long long)g_rows[r] : (long long)r) : -1;
       rr[t] = same_rows ? rg[t] : (ok ? (r_rows ? (long long)r_rows[r] : (long long)r) : -1);
       ro[t] = same_out ? rg[t] : (ok ? (o_rows ? (long long)o_rows[r] : (long long)r) : -1);
     }
-    float dy[2][8], x[2][8], rsc[2];
+    BnDy8<G16> dyp[BN8_ROWS];
+    uint4 xp[BN8_ROWS];
+    float rsc[BN8_ROWS];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < BN8_ROWS; ++t) {
       if (rg[t] >= 0) {
-        bn_load_dy8<G16>(gin, rg[t] * ldg + c, nv, dy[t]);
-        bn_load_x8(raw + rr[t] * ldr + c, x[t]);
+        dyp[t].load(gin, rg[t] * ldg + c, nv);
+        xp[t] = *reinterpret_cast<const uint4*>(raw + rr[t] * ldr + c);
         rsc[t] = row_scale ? row_scale[rg[t]] : 1.f;
       }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < BN8_ROWS; ++t) {
       if (rg[t] < 0) continue;
-      float o[8];
+      float o[8], dyt[8], xt[8];
+      dyp[t].unpack(dyt);
+      bn_unpack_x8(xp[t], xt);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float xh = (x[t][u] - k.mu[u]) * k.rs[u];
-        float d = dy[t][u] * k.cm[u] * rsc[t];
+        const float xh = (xt[u] - k.mu[u]) * k.rs[u];
+        float d = dyt[u] * k.cm[u] * rsc[t];
         if (relu && fmaf(xh, k.wc[u], k.bc[u]) <= 0.f) d = 0.f;
         o[u] = u < nv ? kk[u] * (d - m1[u] - xh * m2[u]) : 0.f;
       }
@@ -1709,7 +1725,12 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
   const bool vec = C % 4 == 0 && ldg % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(gin) % 16 == 0) && (reinterpret_cast<uintptr_t>(raw16) % 8 == 0) &&
                    (reinterpret_cast<uintptr_t>(out16) % 8 == 0);
-  const bool vec8 = vec && ldr % 8 == 0 && ldo % 8 == 0 && (g_is_f16 ? ldg % 8 == 0 : true) &&
+  static int bn_v8 = -1;  // FVIT_BN_V8=0 selects the 4-channel kernels (A/B)
+  if (bn_v8 < 0) {
+    const char* e = getenv("FVIT_BN_V8");
+    bn_v8 = e ? atoi(e) : 1;
+  }
+  const bool vec8 = bn_v8 && vec && ldr % 8 == 0 && ldo % 8 == 0 && (g_is_f16 ? ldg % 8 == 0 : true) &&
                     (reinterpret_cast<uintptr_t>(raw16) % 16 == 0) && (reinterpret_cast<uintptr_t>(out16) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(gin) % 16 == 0);
   if (vec8) {
@@ -1719,7 +1740,7 @@ int fvit_bn_bwd(const void* gin, int32_t g_is_f16, int64_t ldg, const int32_t* g
     const unsigned gy = (unsigned)((c8 + vpr - 1) / vpr);
     const int RL = 256 / vpr;
     long long gx = ((long long)num_sms() * 6 + gy - 1) / gy;
-    const long long gx_max = ((long long)nrows + RL * 2 - 1) / (RL * 2);
+    const long long gx_max = ((long long)nrows + RL * BN8_ROWS - 1) / (RL * BN8_ROWS);
     if (gx > gx_max) gx = gx_max;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, gy);

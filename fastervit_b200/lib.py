@@ -11,7 +11,9 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libfvit_sm100.so"
+import os as _os
+
+LIB_PATH = Path(_os.environ["FVIT_LIB"]) if _os.environ.get("FVIT_LIB") else _PKG / "libfvit_sm100.so"   # (A/B builds)
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_BWD, ACT_RELU_BWD, ACT_MUL_AUX = 0, 1, 2, 3, 4, 5
 
