@@ -411,8 +411,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   const int S = p.S;
   const int SS = (S * S * 4 + 15) & ~15;
   float* bias_s = reinterpret_cast<float*>(smem + BIAS_OFF);
-  float* dbias_s = reinterpret_cast<float*>(smem + BIAS_OFF + SS);
-  uint8_t* ctrl = smem + BIAS_OFF + 2 * SS;
+  uint8_t* ctrl = smem + BIAS_OFF + SS;
   uint64_t* ld_full = reinterpret_cast<uint64_t*>(ctrl);  // [2]
   uint64_t* ld_empty = ld_full + 2;                        // [2]
   uint64_t* sdp_full = ld_empty + 2;                       // [1]
@@ -444,16 +443,32 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   const uint32_t tS = tmem_base, tDP = tmem_base + 128;
   const uint32_t tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
-  const int items = p.tiles * p.heads;
   const int nslots = AT_ROWS / p.slot;
+  // Item order: with at least one CTA per head every CTA stays on ONE head (CTA c: head c % heads, every n_h-th tile
+  // of it), so a thread's share of dbias[head] -- row j of its window slot -- accumulates in registers over all of
+  // the CTA's items and is flushed with one global atomic per element at the end. Smaller grids walk head-major.
+  const bool by_head = (int)gridDim.x >= p.heads;
+  const int my_head = by_head ? (int)blockIdx.x % p.heads : 0;
+  const int n_h = by_head ? ((int)gridDim.x - my_head + p.heads - 1) / p.heads : 1;
+  const int q_h = (int)blockIdx.x / p.heads;
+  const int n_items = by_head ? (q_h < p.tiles ? (p.tiles - q_h + n_h - 1) / n_h : 0)
+                              : (p.tiles * p.heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto item_of = [&](int it, int& head, int& tile) {
+    if (by_head) {
+      head = my_head, tile = q_h + it * n_h;
+    } else {
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      head = w / p.tiles, tile = w % p.tiles;
+    }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
-      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+      for (int it = 0; it < n_items; ++it) {
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        const int head = w / p.tiles, tile = w % p.tiles;
+        int head, tile;
+        item_of(it, head, tile);
         mbar_wait(&ld_empty[st], ph ^ 1);
         uint8_t* base = smem + st * STAGE_BYTES;
         mbar_expect_tx(&ld_full[st], STAGE_BYTES);
@@ -473,8 +488,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       const uint32_t id_tn = make_idesc_f16(128, HDP, 1, 1);  // A = tile read MN-major (M = keys), B MN-major
       const uint32_t id_dq = make_idesc_f16(128, HDP, 0, 1);
       const uint32_t sP = smem_u32(smem + P_OFF), sDS = smem_u32(smem + DS_OFF);
-      int it = 0;
-      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+      for (int it = 0; it < n_items; ++it) {
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&ld_full[st], ph);
@@ -535,22 +549,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         *reinterpret_cast<uint4*>(sDS + off) = make_uint4(0, 0, 0, 0);
       }
     }
-    int it = 0;
     int staged_head = -1;
+    float dacc[64];  // this thread's share of dbias[head]: row j, the 64 key columns of its chunks
+#pragma unroll
+    for (int u = 0; u < 64; ++u) dacc[u] = 0.f;
     auto flush_dbias = [&](int head) {
       if (p.dbias == nullptr || head < 0) return;
-      named_bar_sync(1, 128);
-      float* dst = p.dbias + (long long)head * S * S;
-      for (int i = tid; i < S * S; i += 128) {
-        const float v = dbias_s[i];
-        if (v != 0.f) atomicAdd(dst + i, v);
-        dbias_s[i] = 0.f;
+      if (j < S && sl < p.gpt) {
+        float* dst = p.dbias + ((long long)head * S + j) * S;
+#pragma unroll
+        for (int u = 0; u < 64; ++u) {
+          const int kk = wlo + u - lo;
+          if (u < 32 * nch && kk >= 0 && kk < S && dacc[u] != 0.f) atomicAdd(dst + kk, dacc[u]);
+        }
       }
-      named_bar_sync(1, 128);
+#pragma unroll
+      for (int u = 0; u < 64; ++u) dacc[u] = 0.f;
     };
-    for (int i = tid; i < S * S; i += 128) dbias_s[i] = 0.f;
-    for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
-      const int head = w / p.tiles, tile = w % p.tiles;
+    for (int it = 0; it < n_items; ++it) {
+      int head, tile;
+      item_of(it, head, tile);
       const int grp = tile * p.gpt + sl;
       const bool row_ok = j < S && sl < p.gpt && grp < p.groups;
       if (head != staged_head) {
@@ -581,7 +599,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       const uint32_t ts = tS + ((uint32_t)(quad * 32) << 16);
       const uint32_t tdp = tDP + ((uint32_t)(quad * 32) << 16);
       const float* brow = bias_s + (row_ok ? j : 0) * S;
-      float* dbrow = dbias_s + (row_ok ? j : 0) * S;
       const bool use_bias = p.bias != nullptr;
       float e[64];
       float mx = -INFINITY;
@@ -645,8 +662,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
             for (int t = 0; t < 2; ++t) {
               const float pv = e[32 * ch + u + t];
               ds[t] = pv * (__uint_as_float(raw[u + t]) - delta);
-              const int kk = c0 + u + t - lo;
-              if (p.dbias && row_ok && kk >= 0 && kk < S) atomicAdd(dbrow + kk, ds[t]);
+              dacc[32 * ch + u + t] += ds[t];   // (pv = 0 outside the window / for rows that are not real queries)
             }
             const __half2 hp = __floats2half2_rn(e[32 * ch + u], e[32 * ch + u + 1]);
             const __half2 hd = __floats2half2_rn(ds[0], ds[1]);
@@ -761,7 +777,7 @@ extern "C" int fvit_attn_tc_bwd(const void* qkv, int64_t ldq, const void* dout, 
     if (rc) return rc;
   }
   const size_t ss = ((size_t)S * S * 4 + 15) / 16 * 16;
-  const size_t smem = 1024 + (size_t)2 * 4 * AT_ROWS * hdp * 2 + 2 * AT_ROWS * 128 * 2 + 2 * ss + 128;
+  const size_t smem = 1024 + (size_t)2 * 4 * AT_ROWS * hdp * 2 + 2 * AT_ROWS * 128 * 2 + ss + 128;
   FVIT_CHECK(smem <= 227 * 1024, "fvit_attn_tc_bwd: needs %zu B of shared memory", smem);
   if (hdp == 64) return launch_attn_bwd<64>(tq, td, p, smem, (cudaStream_t)stream);
   return launch_attn_bwd<32>(tq, td, p, smem, (cudaStream_t)stream);

@@ -28,8 +28,11 @@ namespace fvit {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B: one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
+// 12 epilogue warps: the epilogue is latency- and issue-bound (TMEM load, shared-memory transpose, global loads of the
+// residual / aux rows), three warps per scheduler hide it better than two -- measured r02f: fv4 fwd+bwd GEMM time
+// 47.5 -> 46.5 ms, fv0 14.7 -> 14.1 ms (A/B of two builds: -DFVIT_GEMM_NEPI=8 vs 12)
 #ifndef FVIT_GEMM_NEPI
-#define FVIT_GEMM_NEPI 8
+#define FVIT_GEMM_NEPI 12
 #endif
 constexpr int NEPI = FVIT_GEMM_NEPI;            // epilogue warps: a multiple of 4 (one TMEM lane quadrant each)
 constexpr int EPI_THREADS = 32 * NEPI;

@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256)
 constexpr int LNB_MAXV = 7;  // 8-half vectors per lane: C <= 32 * 8 * 7 = 1792
 // Vectorised dx part (C % 8 == 0): one warp per row, the row's dy / xhat live in registers between the two
 // passes. MAXV (vectors per lane) is a template parameter so narrow rows do not pay for wide rows' registers.
-template <int MAXV>
+template <int MAXV, bool PREFETCH_G>
 __global__ void __launch_bounds__(256)
     ln_bwd_dx_kernel(const __half* __restrict__ dy, long long lddy, const int* __restrict__ dy_map,
                      const __half* __restrict__ xhat, long long ldxh, const float* __restrict__ rstd,
@@ -463,12 +463,15 @@ __global__ void __launch_bounds__(256)
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + rdy * lddy);
     const uint4* xr = reinterpret_cast<const uint4*>(xhat + (long long)r * ldxh);
     float d[MAXV][8], xh[MAXV][8];
+    float4 ga[MAXV][2];  // the row's incoming gradient, fetched with the operands (not after the warp reductions)
+    const float4* grp = reinterpret_cast<const float4*>(g + (long long)r * ldg);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       const int i = lane + 32 * j;
       if (i < nv) {
         const uint4 a = dyr[i], b = xr[i];
+        if (PREFETCH_G && use_g) ga[j][0] = grp[2 * i], ga[j][1] = grp[2 * i + 1];
         const __half2* ha = reinterpret_cast<const __half2*>(&a);
         const __half2* hb = reinterpret_cast<const __half2*>(&b);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i);
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = rs * (d[j][u] - s1 - xh[j][u] * s2);
         if (use_g) {
-          const float4 a = reinterpret_cast<const float4*>(gr)[2 * i], b = reinterpret_cast<const float4*>(gr)[2 * i + 1];
+          const float4 a = PREFETCH_G ? ga[j][0] : grp[2 * i], b = PREFETCH_G ? ga[j][1] : grp[2 * i + 1];
           v[0] += a.x, v[1] += a.y, v[2] += a.z, v[3] += a.w, v[4] += b.x, v[5] += b.y, v[6] += b.z, v[7] += b.w;
         }
         if (clear_moved && src != r) {
@@ -1595,18 +1598,25 @@ int fvit_ln_bwd(const void* dy16, int64_t lddy, const int32_t* dy_map, const voi
     const __half* dyh = (const __half*)dy16;
     const __half* xhh = (const __half*)xhat16;
     const int nvl = (C / 8 + 31) / 32;
-    if (nvl <= 1)
-      ln_bwd_dx_kernel<1><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, ldg,
-                                                            in_map, use_g, clear_moved);
-    else if (nvl <= 2)
-      ln_bwd_dx_kernel<2><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, ldg,
-                                                            in_map, use_g, clear_moved);
-    else if (nvl <= 4)
-      ln_bwd_dx_kernel<4><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, ldg,
-                                                            in_map, use_g, clear_moved);
-    else
-      ln_bwd_dx_kernel<LNB_MAXV><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g,
-                                                                   ldg, in_map, use_g, clear_moved);
+    static int prefetch_g = -1;  // FVIT_LN_PREFETCH=1: fetch g with the operands (more registers, fewer resident warps)
+    if (prefetch_g < 0) {
+      const char* e = getenv("FVIT_LN_PREFETCH");
+      prefetch_g = e ? atoi(e) : 0;
+    }
+#define FVIT_LN_DX(MV)                                                                                              \
+  do {                                                                                                              \
+    if (prefetch_g)                                                                                                 \
+      ln_bwd_dx_kernel<MV, true><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, \
+                                                                   ldg, in_map, use_g, clear_moved);                \
+    else                                                                                                            \
+      ln_bwd_dx_kernel<MV, false><<<(unsigned)grid, block, 0, st>>>(dyh, lddy, dy_map, xhh, ldxh, rstd, gamma, rows, C, g, \
+                                                                    ldg, in_map, use_g, clear_moved);               \
+  } while (0)
+    if (nvl <= 1) FVIT_LN_DX(1);
+    else if (nvl <= 2) FVIT_LN_DX(2);
+    else if (nvl <= 4) FVIT_LN_DX(4);
+    else FVIT_LN_DX(LNB_MAXV);
+#undef FVIT_LN_DX
     int vpr = 1;
     while (vpr < 32 && vpr < C / 8) vpr *= 2;
     const unsigned gy = (unsigned)((C / 8 + vpr - 1) / vpr);
