@@ -341,6 +341,9 @@ def main() -> None:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line contract)
+        # NCCL's CTAs cannot share an SM with a GEMM CTA: keep their number small and known, the backward launches in
+        # the shadow of an all-reduce are capped to 148 - FVIT_NCCL_CTAS SMs (engine_train._allreduce_shadow)
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("FVIT_NCCL_CTAS", "16"))
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)

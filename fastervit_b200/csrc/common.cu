@@ -24,6 +24,8 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 
+static std::atomic<int> g_sm_limit{0};
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -33,7 +35,8 @@ int num_sms() {
     if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
     n = p.multiProcessorCount;
   }
-  return n;
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -165,4 +168,5 @@ const char* fvit_last_error(void) { return fvit::err_buf(); }
 int64_t fvit_launch_count(void) { return fvit::g_launches.load(); }
 void fvit_reset_launch_count(void) { fvit::g_launches.store(0); }
 void fvit_add_launch_count(int64_t n) { fvit::g_launches.fetch_add(n); }
+void fvit_set_sm_limit(int32_t n) { fvit::g_sm_limit.store(n > 0 ? n : 0); }
 }

@@ -682,7 +682,11 @@ class Plan:
     def run_ops(self, ops: list, x: torch.Tensor | None) -> None:
         st = L.stream_ptr()
         lib = self.lib
-        for fn, args, name in ops:
+        shadow = getattr(self, "_ar_shadow", None) if getattr(self, "_ar_active", None) is not None else None
+        for idx, (fn, args, name) in enumerate(ops):
+            if shadow is not None and ops is self.bwd_ops:
+                # launches in the shadow of a gradient all-reduce leave NCCL's SMs alone (engine_train.py)
+                lib.fvit_set_sm_limit(shadow.get(idx, 0))
             if fn == "im2col":
                 a = self._x_args[args]
                 rc = lib.fvit_stem_im2col(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),
@@ -703,7 +707,10 @@ class Plan:
             else:
                 rc = fn(*args, st)
             if rc != 0:
+                lib.fvit_set_sm_limit(0)
                 raise L.FvitError(f"{name}: {lib.fvit_last_error().decode()}")
+        if shadow is not None:
+            lib.fvit_set_sm_limit(0)
 
 
     @staticmethod

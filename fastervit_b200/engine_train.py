@@ -231,12 +231,41 @@ class TrainPlan(Plan):
         # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients
         # are enqueued, so NCCL (its own stream) overlaps the rest of the backward pass
         red = GradBucketReducer(self.gflat, None if grp is True else grp)
+        if getattr(self, "_ar_shadow", None) is None:
+            self._ar_shadow = self._allreduce_shadow(red.world)
         self._ar_active = red
         try:
             self.run_ops(self.bwd_ops, None)
         finally:
             self._ar_active = None
         red.finish(self.grad_buckets)
+
+    def _allreduce_shadow(self, world: int) -> dict:
+        """{backward op index: SM cap} for the launches that run while a bucket's all-reduce is in flight. NCCL's CTAs
+        cannot co-reside with a GEMM CTA (227 KB of shared memory, one per SM): a full-width persistent grid launched
+        into the reduction would run its last CTAs as a second wave, doubling that launch. The window is estimated at
+        plan time: bucket bytes over the measured all-reduce bus bandwidth (B200_PROFILING.md: 725 GB/s at 8 ranks)
+        against the launches' algorithmic FLOPs at the model's typical 700 TFLOP/s; those launches are capped to
+        148 - FVIT_NCCL_CTAS SMs (default 16 = NCCL_MAX_CTAS set by enable_grad_allreduce callers such as bench.py)."""
+        import os
+        reserve = int(os.environ.get("FVIT_NCCL_CTAS", "16"))
+        if world <= 1 or reserve <= 0:
+            return {}
+        cap = max(8, 148 - reserve)
+        shadow: dict[int, int] = {}
+        busbw = 600e9 * (1.0 if world >= 4 else 0.7)
+        for i, op in enumerate(self.bwd_ops):
+            if op[0] != "bucket":
+                continue
+            lo, hi = op[1]
+            t_need = 1.5 * 2.0 * (world - 1) / world * (hi - lo) * 4 / busbw   # seconds, with margin
+            t = 0.0
+            for j in range(i + 1, len(self.bwd_ops)):
+                if t >= t_need:
+                    break
+                shadow[j] = cap
+                t += max(self.bwd_flops.get(j, 0.0) / 700e12, 8e-6)
+        return shadow
 
     def profile(self, x: torch.Tensor) -> list[dict]:
         """Per-launch CUDA-event timing of one training step (forward list, then backward list with the

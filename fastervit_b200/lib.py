@@ -65,6 +65,8 @@ def load() -> C.CDLL:
     lib.fvit_last_error.restype = C.c_char_p
     lib.fvit_launch_count.restype = C.c_int64
     lib.fvit_reset_launch_count.restype = None
+    lib.fvit_set_sm_limit.restype = None
+    lib.fvit_set_sm_limit.argtypes = [C.c_int32]
     lib.fvit_add_launch_count.restype = None
     lib.fvit_add_launch_count.argtypes = [C.c_int64]
     lib.fvit_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]

@@ -31,6 +31,10 @@ void fvit_reset_launch_count(void);
 /* A launch list captured into a CUDA graph launches its kernels without passing through the entry points: the host side
  * adds the number of kernel nodes per replay so that fvit_launch_count() stays the number of kernels that really ran. */
 void fvit_add_launch_count(int64_t n);
+/* Persistent kernels (GEMM, attention) size their grids to the SM count; n > 0 caps that count for the launches that
+ * follow (0 = no cap). Used while a gradient all-reduce is in flight: NCCL's CTAs cannot share an SM with a 227 KB GEMM
+ * CTA, so a full-width grid would run its last CTAs as a second wave. */
+void fvit_set_sm_limit(int32_t n);
 
 /* ---- epilogue activation codes --------------------------------------------------------------- */
 enum {
