@@ -728,6 +728,53 @@ static int forced_cg() {  // FVIT_GEMM_CG=1|2 forces the mode where legal (A/B e
   }
   return v;
 }
+static int cost_model() {  // FVIT_GEMM_COST=0: the round-1 wave model (A/B); default: the clock model below
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVIT_GEMM_COST");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+// Clock model of one work unit (SM clocks): per 64-deep K block the tensor pipe needs ~2*tile_n clocks for 128 rows
+// (4096 MAC/clk/SM), the operand stream needs bytes_per_CTA * concurrently_streaming_CTAs / 6300 B/clk (chip-wide
+// L2 -> SM delivery, B300_MICROARCH.md "LTS throughput cap"; the measured ceiling of this kernel's main loop), and the
+// epilogue ~1500 + 12 * tile_n clocks per tile, overlapped with the next unit's main loop except for the last unit.
+// Narrow tiles on all 148 SMs are L2-bound (a 128 x 96 tile streams 140 B/clk per SM): fewer, wider tiles win for the
+// small-M GEMMs of the carrier branch.
+static double unit_clocks(int cg, int bn, int num_kb, long long active_ctas) {
+  const double mma = 2.0 * bn;
+  const double bytes = (128.0 + (double)bn / cg) * 128.0;
+  const double l2 = bytes * (double)active_ctas / 6300.0;
+  return num_kb * (mma > l2 ? mma : l2);
+}
+static TileChoice pick_tile_clk(int m, int n, int split_k, int num_kb, int sms, int want_cg, int want_tile_n) {
+  TileChoice best{1, 16};
+  double best_cost = 1e30;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (want_cg && cg != want_cg) continue;
+    if (cg == 2 && m <= BM) continue;
+    const int tiles_m = ceil_div(m, BM * cg);
+    const int step = 16 * cg;
+    for (int bn = step; bn <= 256; bn += step) {
+      if (want_tile_n > 0 && bn != want_tile_n) continue;
+      const int tiles_n = ceil_div(n, bn);
+      const long long work = (long long)tiles_m * tiles_n * split_k;
+      const int slots = sms / cg;
+      const long long waves = (work + slots - 1) / slots;
+      const long long active = (work < slots ? work : slots) * cg;
+      const int kb = num_kb / (split_k > 0 ? split_k : 1) > 0 ? num_kb / (split_k > 0 ? split_k : 1) : 1;
+      const double main = unit_clocks(cg, bn, kb, active);
+      const double epi = 1500.0 + 12.0 * bn;
+      const double cost = (double)waves * (main > epi ? main : epi) + epi + 2500.0;
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best = TileChoice{cg, bn};
+      }
+    }
+  }
+  return best;
+}
 static TileChoice pick_tile(int m, int n, int split_k, int sms, int want_cg, int want_tile_n) {
   TileChoice best{1, 16};
   double best_cost = 1e30;
@@ -793,7 +840,11 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   const int sms = num_sms();
   int want_cg = a->cta_group == 1 || a->cta_group == 2 ? a->cta_group : forced_cg();
   if (want_cg == 2 && (a->m <= BM || (a->tile_n > 0 && a->tile_n % 32 != 0))) want_cg = 1;
-  const TileChoice tc = pick_tile(a->m, a->n, split_k * b_ntaps, sms, want_cg, a->tile_n > 0 ? a->tile_n : 0);
+  const int num_kb_all = ceil_div(a->kc, BK) * a->ntaps;
+  const TileChoice tc = cost_model()
+                            ? pick_tile_clk(a->m, a->n, split_k * b_ntaps, num_kb_all * b_ntaps, sms, want_cg,
+                                            a->tile_n > 0 ? a->tile_n : 0)
+                            : pick_tile(a->m, a->n, split_k * b_ntaps, sms, want_cg, a->tile_n > 0 ? a->tile_n : 0);
   const int tile_n = tc.tile_n, cg = tc.cg;
   FVIT_CHECK(tile_n >= 16 && tile_n <= 256 && tile_n % (16 * cg) == 0, "fvit_gemm: tile_n=%d invalid (cta_group %d)",
              tile_n, cg);

@@ -227,18 +227,28 @@ class TrainPlan(Plan):
                 self.run_ops(self.bwd_ops, None)
             self.run_captured("backward", body)
             return
-        self._bwd_start(dlogits)
         # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients
-        # are enqueued, so NCCL (its own stream) overlaps the rest of the backward pass
-        red = GradBucketReducer(self.gflat, None if grp is True else grp)
-        if getattr(self, "_ar_shadow", None) is None:
-            self._ar_shadow = self._allreduce_shadow(red.world)
-        self._ar_active = red
-        try:
-            self.run_ops(self.bwd_ops, None)
-        finally:
-            self._ar_active = None
-        red.finish(self.grad_buckets)
+        # are enqueued, so NCCL (its own stream) overlaps the rest of the backward pass. The whole list -- kernels,
+        # all-reduces and the stream dependencies between them -- is captured into one CUDA graph like the
+        # single-GPU backward (NCCL collectives are capturable); a failed capture falls back to eager launches.
+        self._dlogits.copy_(dlogits)
+
+        def body():
+            self._bwd_start(None)
+            red = GradBucketReducer(self.gflat, None if grp is True else grp)
+            if getattr(self, "_ar_shadow", None) is None:
+                self._ar_shadow = self._allreduce_shadow(red.world)
+            self._ar_active = red
+            try:
+                self.run_ops(self.bwd_ops, None)
+            finally:
+                self._ar_active = None
+            red.finish(self.grad_buckets)
+        import os
+        if os.environ.get("FVIT_DDP_GRAPH", "1") != "0":
+            self.run_captured("backward + all-reduce", body)
+        else:
+            body()
 
     def _allreduce_shadow(self, world: int) -> dict:
         """{backward op index: SM cap} for the launches that run while a bucket's all-reduce is in flight. NCCL's CTAs
@@ -253,7 +263,9 @@ class TrainPlan(Plan):
             return {}
         cap = max(8, 148 - reserve)
         shadow: dict[int, int] = {}
-        busbw = 600e9 * (1.0 if world >= 4 else 0.7)
+        # all-reduce bus bandwidth with NCCL_MAX_CTAS = 16: 8 ranks ~600 GB/s (NVLS), fewer ranks ring over fewer links
+        # (timeline at 2 ranks, profiles/r02h_ddp_timeline.json: the 790 MB level-2 bucket shadows ~6 ms of launches)
+        busbw = {2: 200e9, 3: 300e9, 4: 400e9}.get(world, 600e9)
         for i, op in enumerate(self.bwd_ops):
             if op[0] != "bucket":
                 continue

@@ -51,6 +51,11 @@ CASES = {
     "tiny_21k": ("faster_vit_4_21k_384", dict(dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
         dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 24, 12],
         ct_size=2, mlp_ratio=4, resolution=384, hat=[False, False, False, False], do_propagation=True)),
+    # faster_vit_4_21k_224 reduced (fv.py:1253-1290): one 14 x 14 window at level 2 (S = 196: the key-loop tensor-core
+    # attention forward AND backward, two 128-row tiles), 7 x 7 at level 3 -- the member of the 21k family that trains
+    "tiny_21k224": ("faster_vit_4_21k_224", dict(dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=24, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 14, 7],
+        ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, False, False], do_propagation=True)),
 }
 
 
