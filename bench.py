@@ -545,7 +545,22 @@ def main() -> None:
                 "model_frac_of_tensor_peak": round(value / world * alg / 1e12 / pk["tensor"], 4)}
         print(json.dumps(line))
     if dist is not None:
+        # orderly teardown with a watchdog: release the captured launch lists first, and never let a stuck
+        # communicator teardown keep the ranks alive after the result line is out
+        sys.stdout.flush()
+        import gc
+        try:
+            for plan in list(model._engine.plans.values()):
+                plan._graphs.clear()
+        except Exception:  # noqa: BLE001
+            pass
+        gc.collect()
+        torch.cuda.synchronize()
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

@@ -743,7 +743,7 @@ static int cost_model() {  // FVIT_GEMM_COST=0: the round-1 wave model (A/B); de
 // Narrow tiles on all 148 SMs are L2-bound (a 128 x 96 tile streams 140 B/clk per SM): fewer, wider tiles win for the
 // small-M GEMMs of the carrier branch.
 static double unit_clocks(int cg, int bn, int num_kb, long long active_ctas) {
-  const double mma = 2.0 * bn;
+  const double mma = (cg == 2 ? 3.6 : 2.0) * bn;  // (pair main loop measured: 1250 TF/s on 8192^3 = 3.7 * tile_n clocks per K block)
   const double bytes = (128.0 + (double)bn / cg) * 128.0;
   const double l2 = bytes * (double)active_ctas / 6300.0;
   return num_kb * (mma > l2 ? mma : l2);

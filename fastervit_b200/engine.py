@@ -643,7 +643,8 @@ class Plan:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = L.launch_count()
-                with torch.cuda.graph(g):
+                # thread_local: other threads (NCCL's watchdog polling its events) must not invalidate the capture
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     fn()
                 self._graphs[key] = (g, L.launch_count() - n0)
                 st = self._graphs[key]
@@ -683,10 +684,11 @@ class Plan:
         st = L.stream_ptr()
         lib = self.lib
         shadow = getattr(self, "_ar_shadow", None) if getattr(self, "_ar_active", None) is not None else None
+        base = getattr(self, "_op_base", 0)
         for idx, (fn, args, name) in enumerate(ops):
-            if shadow is not None and ops is self.bwd_ops:
+            if shadow is not None:
                 # launches in the shadow of a gradient all-reduce leave NCCL's SMs alone (engine_train.py)
-                lib.fvit_set_sm_limit(shadow.get(idx, 0))
+                lib.fvit_set_sm_limit(shadow.get(base + idx, 0))
             if fn == "im2col":
                 a = self._x_args[args]
                 rc = lib.fvit_stem_im2col(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3),

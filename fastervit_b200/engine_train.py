@@ -227,28 +227,40 @@ class TrainPlan(Plan):
                 self.run_ops(self.bwd_ops, None)
             self.run_captured("backward", body)
             return
-        # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients
-        # are enqueued, so NCCL (its own stream) overlaps the rest of the backward pass. The whole list -- kernels,
-        # all-reduces and the stream dependencies between them -- is captured into one CUDA graph like the
-        # single-GPU backward (NCCL collectives are capturable); a failed capture falls back to eager launches.
+        # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients are
+        # enqueued, so NCCL (its own stream) overlaps the rest of the backward pass. The launch list is cut at the
+        # bucket points: every segment is one CUDA graph (like the single-GPU backward), the all-reduces in between are
+        # ordinary NCCL calls -- collectives captured INTO a graph work too, but live graphs holding NCCL work make
+        # destroy_process_group() hang at exit (seen on 2 x B200, r02j), so they stay outside.
         self._dlogits.copy_(dlogits)
-
-        def body():
-            self._bwd_start(None)
-            red = GradBucketReducer(self.gflat, None if grp is True else grp)
-            if getattr(self, "_ar_shadow", None) is None:
-                self._ar_shadow = self._allreduce_shadow(red.world)
-            self._ar_active = red
-            try:
-                self.run_ops(self.bwd_ops, None)
-            finally:
-                self._ar_active = None
-            red.finish(self.grad_buckets)
-        import os
-        if os.environ.get("FVIT_DDP_GRAPH", "1") != "0":
-            self.run_captured("backward + all-reduce", body)
-        else:
-            body()
+        red = GradBucketReducer(self.gflat, None if grp is True else grp)
+        if getattr(self, "_ar_shadow", None) is None:
+            self._ar_shadow = self._allreduce_shadow(red.world)
+        if getattr(self, "_bwd_segments", None) is None:
+            segs, start = [], 0
+            for i, op in enumerate(self.bwd_ops):
+                if op[0] == "bucket":
+                    segs.append((start, i, op[1]))
+                    start = i + 1
+            segs.append((start, len(self.bwd_ops), None))
+            self._bwd_segments = segs
+        self._ar_active = red
+        try:
+            for n, (lo, hi, bucket) in enumerate(self._bwd_segments):
+                def body(lo=lo, hi=hi, first=(n == 0)):
+                    if first:
+                        self._bwd_start(None)
+                    self._op_base = lo
+                    try:
+                        self.run_ops(self.bwd_ops[lo:hi], None)
+                    finally:
+                        self._op_base = 0
+                self.run_captured(f"backward segment {n}", body)
+                if bucket is not None:
+                    red.reduce(*bucket)
+        finally:
+            self._ar_active = None
+        red.finish(self.grad_buckets)
 
     def _allreduce_shadow(self, world: int) -> dict:
         """{backward op index: SM cap} for the launches that run while a bucket's all-reduce is in flight. NCCL's CTAs
