@@ -732,10 +732,13 @@ static int cost_model() {  // FVIT_GEMM_COST=0: the round-1 wave model (A/B); de
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FVIT_GEMM_COST");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
+// (measured r02k, fv4 / fv0 fwd+bwd and fv0 / ar0 forward: the wave model below stays the default -- the clock model
+// wins only on the N <= 64 stem / level-0 GEMMs, by not pairing CTAs there, which the wave model now does too, and
+// loses 0.3 ms each on the qkv projection (picks 192 instead of 256) and the fc2 weight gradient (pairs M = 784))
 // Clock model of one work unit (SM clocks): per 64-deep K block the tensor pipe needs ~2*tile_n clocks for 128 rows
 // (4096 MAC/clk/SM), the operand stream needs bytes_per_CTA * concurrently_streaming_CTAs / 6300 B/clk (chip-wide
 // L2 -> SM delivery, B300_MICROARCH.md "LTS throughput cap"; the measured ceiling of this kernel's main loop), and the
@@ -781,6 +784,7 @@ static TileChoice pick_tile(int m, int n, int split_k, int sms, int want_cg, int
   for (int cg = 1; cg <= 2; ++cg) {
     if (want_cg && cg != want_cg) continue;
     if (cg == 2 && m <= BM) continue;  // the second CTA of the pair would only see padding rows
+    if (cg == 2 && n <= 64 && !want_cg) continue;  // nothing to share: B is a few KB, the pair only adds its barriers
     const int tiles_m = ceil_div(m, BM * cg);
     const int step = 16 * cg;  // each CTA of a pair stages tile_n / 2 columns of B: keep that a multiple of 16
     for (int bn = step; bn <= 256; bn += step) {
