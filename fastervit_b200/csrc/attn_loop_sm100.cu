@@ -28,7 +28,7 @@ constexpr int AL_ROWS = 128;
 constexpr int AL_NKV = 4;    // K / V tile ring depth
 constexpr int AL_NB = 3;     // bias unit ring depth
 constexpr int AL_BUNIT = 64; // key columns per bias unit
-constexpr int AL_BUNIT_BYTES = AL_ROWS * AL_BUNIT * 4;
+
 
 struct AttnLoopParams {
   int groups, S, heads, nqt, nkt;
@@ -56,30 +56,40 @@ __device__ __forceinline__ void pass2_tile(int t, int nkt, bool& is_v, int& j) {
   }
 }
 
-template <int HDP>
-__global__ void __launch_bounds__(AL_THREADS, 1)
+// DUAL = two CTAs per SM (32-wide heads: 104 KB of shared memory, 256 TMEM columns each): a 2-stage K / V ring, bias
+// units of 32 key columns and ONE score stage -- the other CTA's MMAs and TMA loads fill this CTA's softmax phases,
+// which one warp per scheduler cannot hide on its own. !DUAL = one CTA per SM with the deeper rings (64-wide heads).
+template <int HDP, bool DUAL>
+__global__ void __launch_bounds__(AL_THREADS, DUAL ? 2 : 1)
     attn_loop_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_bias,
                      const __grid_constant__ AttnLoopParams p) {
   constexpr uint32_t SWZ = HDP == 64 ? SWZ_128B : SWZ_64B;
   constexpr uint32_t ROW_BYTES = HDP * 2;
   constexpr uint32_t SBO_QKV = 8 * ROW_BYTES;
   constexpr int TILE_BYTES = AL_ROWS * HDP * 2;
+  constexpr int NKV = DUAL ? 2 : AL_NKV;          // K / V tile ring depth
+  constexpr int NB = AL_NB;                       // bias unit ring depth
+  constexpr int BUNIT = DUAL ? 32 : AL_BUNIT;     // key columns per bias unit
+  constexpr int BUNIT_BYTES = AL_ROWS * BUNIT * 4;
+  constexpr int UNITS = 128 / BUNIT;              // bias units per key tile
+  constexpr int NS = DUAL ? 1 : 2;                // score stages in TMEM
+  constexpr uint32_t TMEM_COLS = DUAL ? 256 : 512;
   constexpr int Q_OFF = 0;
   constexpr int KV_OFF = TILE_BYTES;
-  constexpr int P_OFF = KV_OFF + AL_NKV * TILE_BYTES;
+  constexpr int P_OFF = KV_OFF + NKV * TILE_BYTES;
   constexpr int BIAS_OFF = P_OFF + AL_ROWS * 128 * 2;
-  constexpr int CTRL_OFF = BIAS_OFF + AL_NB * AL_BUNIT_BYTES;
+  constexpr int CTRL_OFF = BIAS_OFF + NB * BUNIT_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, nkt = p.nkt;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + CTRL_OFF);
   uint64_t* q_empty = q_full + 1;
-  uint64_t* kv_full = q_empty + 1;         // [AL_NKV]
-  uint64_t* kv_empty = kv_full + AL_NKV;   // [AL_NKV]
-  uint64_t* b_full = kv_empty + AL_NKV;    // [AL_NB]
-  uint64_t* b_empty = b_full + AL_NB;      // [AL_NB]
-  uint64_t* s_full = b_empty + AL_NB;      // [2]
+  uint64_t* kv_full = q_empty + 1;         // [NKV]
+  uint64_t* kv_empty = kv_full + AL_NKV;   // [NKV] (sized for the deeper ring)
+  uint64_t* b_full = kv_empty + AL_NKV;    // [NB]
+  uint64_t* b_empty = b_full + AL_NB;      // [NB]
+  uint64_t* s_full = b_empty + AL_NB;      // [NS]
   uint64_t* s_empty = s_full + 2;          // [2]
   uint64_t* p_full = s_empty + 2;
   uint64_t* p_empty = p_full + 1;
@@ -91,19 +101,19 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
     tma_prefetch_desc(&tmap_qkv);
     if (p.has_bias) tma_prefetch_desc(&tmap_bias);
     mbar_init(q_full, 1), mbar_init(q_empty, 1);
-    for (int i = 0; i < AL_NKV; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-    for (int i = 0; i < AL_NB; ++i) mbar_init(&b_full[i], 1), mbar_init(&b_empty[i], 4);
+    for (int i = 0; i < NKV; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
+    for (int i = 0; i < NB; ++i) mbar_init(&b_full[i], 1), mbar_init(&b_empty[i], 4);
     for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 4);
     mbar_init(p_full, 4), mbar_init(p_empty, 1), mbar_init(o_full, 1), mbar_init(o_empty, 4);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tmem_O = tmem_base + 256;
+  const uint32_t tmem_S[2] = {tmem_base, tmem_base + (NS == 2 ? 128u : 0u)};
+  const uint32_t tmem_O = tmem_base + 128u * NS;
 
   const int items = p.groups * p.heads * p.nqt;
   // item -> (head, q tile) outer, window inner: CTAs running side by side share the bias tiles in L2
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
     qi = hq % p.nqt;
     head = hq / p.nqt;
   };
-  auto units_of = [&](int j) { return (S - j * 128) > AL_BUNIT ? 2 : 1; };  // bias units of key tile j
+  auto units_of = [&](int j) { return min(UNITS, (min(128, S - j * 128) + BUNIT - 1) / BUNIT); };  // live bias units of key tile j
 
   if (warp == 0) {
     if (lane == 0) {
@@ -134,8 +144,8 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
             bool is_v = false;
             int j = t;
             if (pass == 1) pass2_tile(t, nkt, is_v, j);
-            const int st = kv_cnt % AL_NKV;
-            mbar_wait(&kv_empty[st], ((kv_cnt / AL_NKV) & 1) ^ 1);
+            const int st = kv_cnt % NKV;
+            mbar_wait(&kv_empty[st], ((kv_cnt / NKV) & 1) ^ 1);
             mbar_expect_tx(&kv_full[st], TILE_BYTES);
             tma_load_2d(smem + KV_OFF + st * TILE_BYTES, &tmap_qkv, &kv_full[st],
                         ((is_v ? 2 : 1) * p.heads + head) * HDP, row0 + j * 128);
@@ -143,13 +153,13 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
             if (p.has_bias && !is_v && bias_j <= j) {
               for (; bias_j <= j; ++bias_j) {
                 for (int u = 0; u < units_of(bias_j); ++u) {
-                  const int bs = b_cnt % AL_NB;
-                  mbar_wait(&b_empty[bs], ((b_cnt / AL_NB) & 1) ^ 1);
-                  mbar_expect_tx(&b_full[bs], AL_BUNIT_BYTES);
-                  uint8_t* dst = smem + BIAS_OFF + bs * AL_BUNIT_BYTES;
-                  const int c0 = bias_j * 128 + u * AL_BUNIT;
+                  const int bs = b_cnt % NB;
+                  mbar_wait(&b_empty[bs], ((b_cnt / NB) & 1) ^ 1);
+                  mbar_expect_tx(&b_full[bs], BUNIT_BYTES);
+                  uint8_t* dst = smem + BIAS_OFF + bs * BUNIT_BYTES;
+                  const int c0 = bias_j * 128 + u * BUNIT;
                   tma_load_2d(dst, &tmap_bias, &b_full[bs], c0, head * S + qi * 128);
-                  tma_load_2d(dst + AL_ROWS * 128, &tmap_bias, &b_full[bs], c0 + 32, head * S + qi * 128);
+                  if (BUNIT == 64) tma_load_2d(dst + AL_ROWS * 128, &tmap_bias, &b_full[bs], c0 + 32, head * S + qi * 128);
                   ++b_cnt;
                 }
               }
@@ -166,10 +176,10 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
       const uint32_t sP = smem_u32(smem + P_OFF);
       uint32_t kv_cnt = 0, s_cnt = 0, p_cnt = 0, it = 0;
       auto issue_s = [&]() {  // S = Q K^T from the next ring stage into the next score stage
-        const int st = kv_cnt % AL_NKV;
-        mbar_wait(&kv_full[st], (kv_cnt / AL_NKV) & 1);
-        const int ss = s_cnt & 1;
-        mbar_wait(&s_empty[ss], ((s_cnt >> 1) & 1) ^ 1);
+        const int st = kv_cnt % NKV;
+        mbar_wait(&kv_full[st], (kv_cnt / NKV) & 1);
+        const int ss = s_cnt % NS;
+        mbar_wait(&s_empty[ss], ((s_cnt / NS) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sK = smem_u32(smem + KV_OFF + st * TILE_BYTES);
 #pragma unroll
@@ -181,8 +191,8 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
         ++kv_cnt, ++s_cnt;
       };
       auto issue_pv = [&](bool first) {  // O (+)= P V from the next ring stage
-        const int st = kv_cnt % AL_NKV;
-        mbar_wait(&kv_full[st], (kv_cnt / AL_NKV) & 1);
+        const int st = kv_cnt % NKV;
+        mbar_wait(&kv_full[st], (kv_cnt / NKV) & 1);
         mbar_wait(p_full, p_cnt & 1);
         tc_fence_after();
         const uint32_t sV = smem_u32(smem + KV_OFF + st * TILE_BYTES);
@@ -221,23 +231,23 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
       float mx = -INFINITY, sum = 0.f;
       for (int pass = 0; pass < 2; ++pass) {
         for (int j = 0; j < nkt; ++j) {
-          const int ss = s_cnt & 1;
-          mbar_wait(&s_full[ss], (s_cnt >> 1) & 1);
+          const int ss = s_cnt % NS;
+          mbar_wait(&s_full[ss], (s_cnt / NS) & 1);
           tc_fence_after();
           const uint32_t ts = tmem_S[ss] + ((uint32_t)(quad * 32) << 16);
           const int ncols = min(128, S - j * 128);  // valid keys of this tile
           if (pass == 1) mbar_wait(p_empty, (p_cnt & 1) ^ 1);  // the previous P V MMA has consumed the P tile
-          for (int u = 0; u < 2; ++u) {
-            const bool unit_live = u * AL_BUNIT < ncols;
+          for (int u = 0; u < UNITS; ++u) {
+            const bool unit_live = u * BUNIT < ncols;
             const uint8_t* bunit = nullptr;
             if (use_bias && unit_live) {
-              const int bs = b_cnt % AL_NB;
-              mbar_wait(&b_full[bs], (b_cnt / AL_NB) & 1);
-              bunit = smem + BIAS_OFF + bs * AL_BUNIT_BYTES;
+              const int bs = b_cnt % NB;
+              mbar_wait(&b_full[bs], (b_cnt / NB) & 1);
+              bunit = smem + BIAS_OFF + bs * BUNIT_BYTES;
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = u * AL_BUNIT + h * 32;  // first key column of this 32-wide chunk
+            for (int h = 0; h < BUNIT / 32; ++h) {
+              const int c0 = u * BUNIT + h * 32;  // first key column of this 32-wide chunk
               if (pass == 0 && c0 >= ncols) continue;
               uint32_t raw[32];
               float sc[32];
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
             }
             if (use_bias && unit_live) {
               __syncwarp();
-              if (lane == 0) mbar_arrive(&b_empty[b_cnt % AL_NB]);
+              if (lane == 0) mbar_arrive(&b_empty[b_cnt % NB]);
               ++b_cnt;
             }
           }
@@ -340,21 +350,24 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int HDP>
+template <int HDP, bool DUAL>
 static int launch_attn_loop(const CUtensorMap& tq, const CUtensorMap& tb, const AttnLoopParams& p, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)(1 + AL_NKV) * AL_ROWS * HDP * 2 + AL_ROWS * 128 * 2 + AL_NB * AL_BUNIT_BYTES + 256;
+  constexpr int NKV = DUAL ? 2 : AL_NKV;
+  constexpr int BUNIT_BYTES = AL_ROWS * (DUAL ? 32 : AL_BUNIT) * 4;
+  constexpr size_t smem = 1024 + (size_t)(1 + NKV) * AL_ROWS * HDP * 2 + AL_ROWS * 128 * 2 + AL_NB * BUNIT_BYTES + 256;
+  static_assert(!DUAL || smem <= 113 * 1024, "two CTAs per SM need <= 113 KB each");
   static bool configured = false;
   if (!configured) {
-    FVIT_CUDA(cudaFuncSetAttribute(attn_loop_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FVIT_CUDA(cudaFuncSetAttribute(attn_loop_kernel<HDP, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long items = (long long)p.groups * p.heads * p.nqt;
-  const int sms = num_sms();
-  attn_loop_kernel<HDP><<<(unsigned)(items < sms ? items : sms), AL_THREADS, smem, st>>>(tq, tb, p);
+  const int slots = num_sms() * (DUAL ? 2 : 1);
+  attn_loop_kernel<HDP, DUAL><<<(unsigned)(items < slots ? items : slots), AL_THREADS, smem, st>>>(tq, tb, p);
   return post_launch("attn_loop_kernel");
 }
 
@@ -395,8 +408,14 @@ extern "C" int fvit_attn_loop_fwd(const void* qkv, int64_t ldq, int32_t groups, 
   } else {
     tb = tq;
   }
-  if (hdp == 64) return launch_attn_loop<64>(tq, tb, p, (cudaStream_t)stream);
-  return launch_attn_loop<32>(tq, tb, p, (cudaStream_t)stream);
+  if (hdp == 64) return launch_attn_loop<64, false>(tq, tb, p, (cudaStream_t)stream);
+  static int dual = -1;  // FVIT_ATTN_LOOP_DUAL=0: one CTA per SM for 32-wide heads too (A/B)
+  if (dual < 0) {
+    const char* e = getenv("FVIT_ATTN_LOOP_DUAL");
+    dual = e ? atoi(e) : 1;
+  }
+  if (dual) return launch_attn_loop<32, true>(tq, tb, p, (cudaStream_t)stream);
+  return launch_attn_loop<32, false>(tq, tb, p, (cudaStream_t)stream);
 }
 
 // =====================================================================================================
