@@ -255,7 +255,8 @@ class TrainPlan(Plan):
                         self.run_ops(self.bwd_ops[lo:hi], None)
                     finally:
                         self._op_base = 0
-                self.run_captured(f"backward segment {n}", body)
+                if hi > lo or n == 0:   # (the list ends with a bucket point: nothing to capture after it)
+                    self.run_captured(f"backward segment {n}", body)
                 if bucket is not None:
                     red.reduce(*bucket)
         finally:
