@@ -209,7 +209,7 @@ class TrainPlan(Plan):
 
     def _bwd_start(self, dlogits: torch.Tensor | None) -> None:
         if dlogits is not None:
-            self._dlogits.copy_(dlogits)
+            self._dlogits[:, :self._ncls].copy_(dlogits)
         self.run_ops(self._bwd_prologue, None)
         st = L.stream_ptr()
         rc = self.lib.fvit_grad_scale_init(self._dlogits.data_ptr(), self._dlogits.numel(), 64.0, self.scal.data_ptr(), st)
@@ -220,7 +220,7 @@ class TrainPlan(Plan):
     def run_backward(self, dlogits: torch.Tensor) -> None:
         grp = getattr(self.model, "_grad_allreduce", None)
         if grp is None:
-            self._dlogits.copy_(dlogits)
+            self._dlogits[:, :self._ncls].copy_(dlogits)
 
             def body():
                 self._bwd_start(None)
@@ -232,7 +232,7 @@ class TrainPlan(Plan):
         # bucket points: every segment is one CUDA graph (like the single-GPU backward), the all-reduces in between are
         # ordinary NCCL calls -- collectives captured INTO a graph work too, but live graphs holding NCCL work make
         # destroy_process_group() hang at exit (seen on 2 x B200, r02j), so they stay outside.
-        self._dlogits.copy_(dlogits)
+        self._dlogits[:, :self._ncls].copy_(dlogits)
         red = GradBucketReducer(self.gflat, None if grp is True else grp)
         if getattr(self, "_ar_shadow", None) is None:
             self._ar_shadow = self._allreduce_shadow(red.world)
@@ -314,7 +314,7 @@ class TrainPlan(Plan):
                timed("gradient hand-off copy", lambda: self.grad_views())]
         for ops, flops, tag in ((self.ops, self.op_flops, ""), (self.bwd_ops, self.bwd_flops, "")):
             if ops is self.bwd_ops:
-                self._bwd_start(torch.full_like(self._dlogits, 1.0 / self.B))
+                self._bwd_start(torch.full((self.B, self._ncls), 1.0 / self.B, device=self._dlogits.device))
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)]
             torch.cuda.synchronize()
             torch.cuda._sleep(int(8e8))

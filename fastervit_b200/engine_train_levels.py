@@ -361,17 +361,16 @@ def _emit_head_bwd(self, feat: dict) -> None:
     hs = self.head_sv
     nf, ncls, T = hs["nf"], m.num_classes, hs["T"]
     ldl = _ru(ncls, 8)
-    self._dlogits = nb.new("grad.dlogits", (B, ncls), torch.float32)
+    ncp = _ru(ncls, 4)   # the loss gradient is kept in rows padded to 16 bytes (any num_classes; padding stays zero)
+    self._dlogits = nb.new("grad.dlogits", (B, ncp), torch.float32)
+    self._ncls = ncls
     dl16 = nb.new("grad.dl16", (B, ldl), torch.float16)
     dpool = nb.new("grad.dpool", (B, nf), torch.float32)
     inv = ("scal", 1)
     ops = self.bwd_ops
-    if ncls % 4 == 0:
-        self._op(ops, "fvit_cast_scale_f16", self._dlogits.data_ptr(), ncls, None, B, ncls, None, ("scal", 0),
-                 dl16.data_ptr(), ldl, None)
-    else:
-        raise L.FvitError("num_classes must be a multiple of 4 for the training kernels")
-    self._op(ops, "fvit_colsum", self._dlogits.data_ptr(), 0, ncls, None, None, 0, B, ncls, None, None,
+    self._op(ops, "fvit_cast_scale_f16", self._dlogits.data_ptr(), ncp, None, B, ncp, None, ("scal", 0),
+             dl16.data_ptr(), ldl, None)
+    self._op(ops, "fvit_colsum", self._dlogits.data_ptr(), 0, ncp, None, None, 0, B, ncls, None, None,
              self.G(m.head.bias), None)
     # dW_head = dl^T pooled ; dpooled = dl W_head
     self._bgemm(a=dl16.data_ptr(), a_rows=B, lda=ldl, a_mn=True, b=hs["pooled"].data_ptr(), b_rows=B,

@@ -185,3 +185,30 @@ def test_gradient_buckets_partition_the_flat_buffer():
     for p in model.parameters():
         o = plan._goff[id(p)]
         assert sum(1 for lo, hi in plan.grad_buckets if lo <= o and o + p.numel() <= hi) == 1
+
+
+def test_train_step_with_num_classes_not_a_multiple_of_four():
+    """The loss gradient is kept in 16-byte padded rows, so any `num_classes` trains (a 10-class fine-tuning head):
+    loss, logits and every gradient against the fp64 oracle."""
+    import fastervit_b200 as F
+    from oracle import fastervit_oracle as O
+    from oracle.configs import cfg_of
+    kw = dict(dim=32, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], num_classes=10)
+    model = F.create_model("faster_vit_0_224", drop_path_rate=0.0, **kw)
+    O.synth_fill_(model.state_dict(), 99)
+    sd64 = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    x = O.synth_input(3, 224, 12, torch.float32)
+    target = torch.tensor([3, 9, 0])
+    logits = model(x.cuda())
+    assert logits.shape == (3, 10)
+    loss = torch.nn.functional.cross_entropy(logits, target.cuda())
+    loss.backward()
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd64, cfg_of("tiny_a"), x.double(), target, training=True)
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * abs(ref_loss.item()) + 1e-4
+    assert ((logits.double().cpu() - ref_logits).abs().max() / ref_logits.abs().max()).item() < 3e-3
+    gmax = max(v.abs().max().item() for v in ref_grads.values())
+    for k, p in model.named_parameters():
+        want = ref_grads[k]
+        err = (p.grad.double().cpu() - want).norm().item() / max(want.norm().item(), 1e-3 * gmax * want.numel() ** 0.5)
+        assert err < (6e-2 if k.startswith("patch_embed.") else 4e-2), (k, err)
