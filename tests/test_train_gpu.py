@@ -212,3 +212,23 @@ def test_train_step_with_num_classes_not_a_multiple_of_four():
         want = ref_grads[k]
         err = (p.grad.double().cpu() - want).norm().item() / max(want.norm().item(), 1e-3 * gmax * want.numel() ** 0.5)
         assert err < (6e-2 if k.startswith("patch_embed.") else 4e-2), (k, err)
+
+
+def test_stochastic_depth_draws_fresh_masks_inside_the_captured_step():
+    """With drop_path_rate > 0 the per-step Bernoulli masks are drawn inside the launch list; once that list is a CUDA
+    graph (third call onwards) every replay must still draw NEW masks from torch's CUDA generator."""
+    import fastervit_b200 as F
+    kw = dict(dim=32, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8])
+    torch.manual_seed(0)
+    model = F.create_model("faster_vit_0_224", drop_path_rate=0.5, **kw).cuda().train()
+    x = torch.randn(4, 3, 224, 224, device="cuda")
+    outs = []
+    for _ in range(5):
+        logits = model(x)
+        logits.sum().backward()
+        model.zero_grad(set_to_none=True)
+        outs.append(logits.detach().clone())
+    assert all(torch.isfinite(o).all() for o in outs)
+    # same input, same weights (no optimizer): only the masks differ from step to step
+    diffs = [(outs[i] - outs[i + 1]).abs().max().item() for i in range(4)]
+    assert min(diffs[2:]) > 1e-4 * outs[0].abs().max().item(), diffs
