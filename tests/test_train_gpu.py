@@ -231,4 +231,5 @@ def test_stochastic_depth_draws_fresh_masks_inside_the_captured_step():
     assert all(torch.isfinite(o).all() for o in outs)
     # same input, same weights (no optimizer): only the masks differ from step to step
     diffs = [(outs[i] - outs[i + 1]).abs().max().item() for i in range(4)]
-    assert min(diffs[2:]) > 1e-4 * outs[0].abs().max().item(), diffs
+    # (atomics make identical-mask steps differ by ~2e-3 of max|logits|; different masks move them by O(0.1 .. 1))
+    assert min(diffs[2:]) > 3e-2 * outs[0].abs().max().item(), diffs
