@@ -135,11 +135,13 @@ __global__ void __launch_bounds__(AL_THREADS, DUAL ? 2 : 1)
         mbar_wait(q_empty, (it & 1) ^ 1);
         mbar_expect_tx(q_full, TILE_BYTES);
         tma_load_2d(smem + Q_OFF, &tmap_qkv, q_full, head * HDP, row0 + qi * 128);
-        // K / V tiles and bias units are produced in lock step with their consumers' order; the two streams are
-        // merged so that neither ring starves the other: per key tile first its K (and V) boxes, then its bias
+        // K / V tiles and bias units are produced in the order their consumers need them. The bias units of key tile j
+        // go out only after everything the softmax warps need to CONSUME them has been issued -- K_j (for S_j) and, in
+        // pass 2, V_{j-1} (the softmax of tile j first waits for the P V MMA of tile j-1 to release the P buffer):
+        // pass 1: K_0 b_0 K_1 b_1 ...; pass 2: K_0 b_0 K_1 V_0 b_1 K_2 V_1 b_2 ... A producer blocked on a full bias
+        // ring therefore never holds back a tile the ring's consumers are waiting for.
         for (int pass = 0; pass < 2; ++pass) {
           const int ntiles = pass == 0 ? nkt : 2 * nkt;
-          int bias_j = 0;  // next key tile whose bias units have not been issued in this pass
           for (int t = 0; t < ntiles; ++t) {
             bool is_v = false;
             int j = t;
@@ -150,8 +152,10 @@ __global__ void __launch_bounds__(AL_THREADS, DUAL ? 2 : 1)
             tma_load_2d(smem + KV_OFF + st * TILE_BYTES, &tmap_qkv, &kv_full[st],
                         ((is_v ? 2 : 1) * p.heads + head) * HDP, row0 + j * 128);
             ++kv_cnt;
-            if (p.has_bias && !is_v && bias_j <= j) {
-              for (; bias_j <= j; ++bias_j) {
+            // which tile's bias follows this box: pass 1 -> the K tile itself; pass 2 -> K_0 itself, V_{j} -> tile j+1
+            const int bias_j = pass == 0 ? j : (is_v ? j + 1 : (j == 0 ? 0 : -1));
+            if (p.has_bias && bias_j >= 0 && bias_j < nkt) {
+              {
                 for (int u = 0; u < units_of(bias_j); ++u) {
                   const int bs = b_cnt % NB;
                   mbar_wait(&b_empty[bs], ((b_cnt / NB) & 1) ^ 1);
