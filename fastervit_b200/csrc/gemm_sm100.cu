@@ -54,6 +54,7 @@ struct GemmParams {
   int m, n;
   int num_kb;      // K-blocks (of 64) over all taps
   int kb_per_tap;  // ceil(kc / 64)
+  int k_tail16;    // 16-wide MMA steps that hold real K columns in a tap's last K-block (1..4); the rest is zero fill
   int a_mn, b_mn;
   int a_row_off, b_row_off;
   int tile_n;
@@ -335,8 +336,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + A_STAGE_BYTES;
+          // a tap's last K-block is zero beyond kc (TMA out-of-bounds fill / zero-padded weights): its all-zero
+          // 16-wide steps are not issued (K = 196 per conv tap: 13 instead of 16 MMAs; K = 784: 49 instead of 52)
+          const int nk = (kb + 1) % p.kb_per_tap == 0 ? p.k_tail16 : BK / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if (k >= nk) break;
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
             if constexpr (CG == 2) umma_f16_ss_cg2(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
@@ -859,6 +864,15 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   p.n = a->n;
   p.kb_per_tap = ceil_div(a->kc, BK);
   p.num_kb = p.kb_per_tap * a->ntaps;
+  {
+    static int kskip = -1;  // FVIT_GEMM_KSKIP=0: issue the zero-filled K steps too (A/B)
+    if (kskip < 0) {
+      const char* e = getenv("FVIT_GEMM_KSKIP");
+      kskip = e ? atoi(e) : 1;
+    }
+    const int tail = a->kc - (p.kb_per_tap - 1) * BK;  // 1..64 real columns in the last block
+    p.k_tail16 = kskip ? ceil_div(tail, UMMA_K) : BK / UMMA_K;
+  }
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
   p.a_row_off = a->a_row_off;

@@ -87,6 +87,11 @@ class Plan:
         import os
         self.fused_hat = os.environ.get("FVIT_FUSED_HAT", "auto")
         self.use_graphs = os.environ.get("FVIT_CUDA_GRAPH", "1") != "0" and device.type == "cuda"
+        # independent launches (weight re-packing, leaf gradient chains) as parallel branches of the launch graph
+        # (FVIT_SIDE_BRANCHES=0 off, 2 = re-packing only, 3 = backward leaf chains only: A/B switches)
+        sb = os.environ.get("FVIT_SIDE_BRANCHES", "1") if self.use_graphs else "0"
+        self.side_branches = sb in ("1", "3")
+        self.prep_branches = sb in ("1", "2")
         self._graphs: dict = {}
         self._x_static = None
         self._deploy_mods: list = []
@@ -680,11 +685,19 @@ class Plan:
             k += b_._version
         return (k, L.weights_epoch(), sum(1 << (i % 60) for i, m in enumerate(self._deploy_mods) if m.deploy))
 
-    def run_ops(self, ops: list, x: torch.Tensor | None) -> None:
+    def run_ops(self, ops: list, x: torch.Tensor | None, side: set | None = None) -> None:
+        """Enqueue a launch list on the current stream. `side` (absolute op indices, engine_train.py) names leaf
+        launches that go to the plan's side stream instead: forked after everything enqueued so far, joined at the
+        next bucket point and at the end of the list -- under graph capture these become parallel branches."""
         st = L.stream_ptr()
         lib = self.lib
         shadow = getattr(self, "_ar_shadow", None) if getattr(self, "_ar_active", None) is not None else None
         base = getattr(self, "_op_base", 0)
+        cur = side_stream = None
+        forked = False
+        if side:
+            cur = torch.cuda.current_stream()
+            side_stream = self._side_streams(1)[0]
         for idx, (fn, args, name) in enumerate(ops):
             if shadow is not None:
                 # launches in the shadow of a gradient all-reduce leave NCCL's SMs alone (engine_train.py)
@@ -702,18 +715,86 @@ class Plan:
                     continue
                 rc = fn2(*args2, st)
             elif fn == "bucket":   # gradient slice [lo, hi) of the flat buffer is final (engine_train.py)
+                if forked:
+                    cur.wait_stream(side_stream)
+                    forked = False
                 red = getattr(self, "_ar_active", None)
                 if red is not None:
                     red.reduce(*args)
                 continue
+            elif side and (base + idx) in side:
+                side_stream.wait_stream(cur)
+                forked = True
+                rc = fn(*args, side_stream.cuda_stream)
             else:
                 rc = fn(*args, st)
             if rc != 0:
                 lib.fvit_set_sm_limit(0)
                 raise L.FvitError(f"{name}: {lib.fvit_last_error().decode()}")
+        if forked:
+            cur.wait_stream(side_stream)
         if shadow is not None:
             lib.fvit_set_sm_limit(0)
 
+    def _side_streams(self, n: int) -> list:
+        ss = getattr(self, "_sides", None)
+        if ss is None:
+            ss = self._sides = []
+        while len(ss) < n:
+            ss.append(torch.cuda.Stream(device=self.device))
+        return ss[:n]
+
+    def run_ops_branches(self, ops: list, n_streams: int = 8) -> None:
+        """Enqueue a list of plain launches whose only mutual dependencies are shared pointer arguments (weight
+        re-packing: every launch writes its own operand buffer) as `n_streams` parallel branches: launches that
+        share a device pointer stay in order on one stream, the rest are dealt round-robin. A few hundred small
+        launches then cost the HBM time of the large ones instead of a serial chain of launch latencies."""
+        chains = getattr(self, "_branch_chains", {}).get(id(ops))
+        if chains is None:
+            parent = list(range(len(ops)))
+
+            def find(i):
+                while parent[i] != i:
+                    parent[i] = parent[parent[i]]
+                    i = parent[i]
+                return i
+            owner: dict[int, int] = {}
+            plain = True
+            for i, (fn, args, _) in enumerate(ops):
+                if isinstance(fn, str) or not isinstance(args, tuple):
+                    plain = False
+                    break
+                for a in args:
+                    if isinstance(a, int) and a > (1 << 32):   # device pointers (sizes and strides are far below)
+                        j = owner.setdefault(a, i)
+                        if j != i:
+                            parent[find(i)] = find(j)
+            groups: dict[int, list[int]] = {}
+            if plain:
+                for i in range(len(ops)):
+                    groups.setdefault(find(i), []).append(i)
+            chains = list(groups.values()) if plain else []
+            if not hasattr(self, "_branch_chains"):
+                self._branch_chains = {}
+            self._branch_chains[id(ops)] = chains
+        if len(chains) < 2 * n_streams:
+            self.run_ops(ops, None)
+            return
+        cur = torch.cuda.current_stream()
+        streams = self._side_streams(n_streams)
+        lib = self.lib
+        for s in streams:
+            s.wait_stream(cur)
+        try:
+            for k, chain in enumerate(chains):
+                sp = streams[k % n_streams].cuda_stream
+                for i in chain:
+                    fn, args, name = ops[i]
+                    if fn(*args, sp) != 0:
+                        raise L.FvitError(f"{name}: {lib.fvit_last_error().decode()}")
+        finally:
+            for s in streams:
+                cur.wait_stream(s)
 
     @staticmethod
     def _op_desc(op) -> dict:

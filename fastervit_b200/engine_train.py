@@ -41,6 +41,7 @@ class TrainPlan(Plan):
         self._goff = offs
         self.scratch_n = 0
         self._scratch_req: list[tuple[str, int]] = []
+        self._bwd_side: set[int] = set()     # backward launches that run as a side branch (engine_train_levels.py)
         # device scalars: [0] S, [1] 1/S, [2] 1.0, then per-branch (s_b, 1/s_b, 1/(S s_b))
         self._nscal = 3
         self._branch_slots: list[tuple[int, object]] = []
@@ -196,7 +197,10 @@ class TrainPlan(Plan):
                 t.zero_()
             if self.drop_specs:
                 self._gen_drop_masks()   # stochastic-depth masks of this step (torch RNG, like timm's DropPath)
-            self.run_ops(self.prep_ops, None)
+            if self.prep_branches:
+                self.run_ops_branches(self.prep_ops)
+            else:
+                self.run_ops(self.prep_ops, None)
             self.run_ops(self.ops, xin)
             for bn in self._bn_modules:
                 bn.num_batches_tracked += 1
@@ -224,7 +228,7 @@ class TrainPlan(Plan):
 
             def body():
                 self._bwd_start(None)
-                self.run_ops(self.bwd_ops, None)
+                self.run_ops(self.bwd_ops, None, side=self._bwd_side if self.side_branches else None)
             self.run_captured("backward", body)
             return
         # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients are
@@ -252,7 +256,7 @@ class TrainPlan(Plan):
                         self._bwd_start(None)
                     self._op_base = lo
                     try:
-                        self.run_ops(self.bwd_ops[lo:hi], None)
+                        self.run_ops(self.bwd_ops[lo:hi], None, side=self._bwd_side if self.side_branches else None)
                     finally:
                         self._op_base = 0
                 if hi > lo or n == 0:   # (the list ends with a bucket point: nothing to capture after it)

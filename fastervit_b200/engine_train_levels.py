@@ -412,18 +412,25 @@ def _attn_bwd_entry(S: int, hdp: int, use_tc: bool) -> str:
 
 def _posemb_bwd(self, pe: dict) -> None:
     mod = pe["mod"]
+    n0 = len(self.bwd_ops)
     self._op(self.bwd_ops, "fvit_cpb_mlp_bwd", pe["coords"].data_ptr(), pe["npts"], mod.cpb_mlp[2].weight.data_ptr(),
              pe["hidden"].data_ptr(), pe["dout"], pe["D"], None, self.G(mod.cpb_mlp[0].weight),
              self.G(mod.cpb_mlp[0].bias), self.G(mod.cpb_mlp[2].weight))
+    self._bwd_side.update(range(n0, len(self.bwd_ops)))
 
 
 def _bias_bwd(self, bs: dict) -> None:
+    """Gradient of the relative-position bias MLP. Its inputs (this block's dbias / dtable scratch slices) are written
+    once per backward pass and its outputs are parameter gradients nobody downstream reads: a leaf chain, run as a
+    side branch of the launch graph (TrainPlan._bwd_side) so that these small latency-bound launches overlap the GEMMs."""
     rpb = bs["mod"]
+    n0 = len(self.bwd_ops)
     self._op(self.bwd_ops, "fvit_attn_bias_bwd", bs["dbias"], bs["out"].data_ptr(), rpb.relative_position_index.data_ptr(),
              rpb.num_heads, bs["S"], rpb.window ** 2, ("scal", 1), bs["dtable"])
     self._op(self.bwd_ops, "fvit_cpb_mlp_bwd", rpb.relative_coords_table.data_ptr(), bs["npts"],
              rpb.cpb_mlp[2].weight.data_ptr(), bs["hidden"].data_ptr(), bs["dtable"], rpb.num_heads, None,
              self.G(rpb.cpb_mlp[0].weight), self.G(rpb.cpb_mlp[0].bias), self.G(rpb.cpb_mlp[2].weight))
+    self._bwd_side.update(range(n0, len(self.bwd_ops)))
 
 
 def _mlp_bwd(self, tl: dict, ms: dict, gamma, g_ptr: int, rows: int, ln: nn.LayerNorm, xh, rs, in_map=None) -> None:
@@ -489,6 +496,7 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
                      dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc, bias_done=fused)
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
+        self._bwd_side.add(len(ops) - 1)   # fresh scratch in, parameter gradient out: leaf launch
     # attention core
     _emit_attn_core_bwd(self, at, dao, dqkv, groups, S)
     _bias_bwd(self, at["bias"])
@@ -504,6 +512,7 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     if padded:
         if attn.qkv.bias is not None:
             self._op(ops, "fvit_unpad_heads_f32", gbq, 1, self.G(attn.qkv.bias), 1, 3 * Cp, 1, hd, hdp, 1, 0, None)
+            self._bwd_side.add(len(ops) - 1)   # fresh scratch in, parameter gradient out: leaf launch
     # LayerNorm (with the gather routing of the forward)
     self._op(ops, "fvit_ln_bwd", dy.data_ptr(), Cc, None, xh.data_ptr(), Cc, rs.data_ptr(), ln.weight.data_ptr(), rows, Cc,
              g_ptr, Cc, in_map, 1, 1 if clear_moved else 0, ("scal", 1), self.G(ln.weight), self.G(ln.bias))
@@ -592,6 +601,7 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
                      dx16=dao.data_ptr(), lddx=Cp, flops_k=Cc, bias_done=fused)
     if padded:
         self._op(ops, "fvit_unpad_heads_f32", gWp, Cp, self.G(attn.proj.weight), Cc, Cc, Cp, hd, hdp, 0, 1, None)
+        self._bwd_side.add(len(ops) - 1)   # fresh scratch in, parameter gradient out: leaf launch
     _emit_attn_core_bwd(self, at, dao, dqkv, B, n_ct)
     _bias_bwd(self, at["bias"])
     one = dict(gamma=None, s=None, inv_s=("scal", 2), w_alpha=("scal", 1))
@@ -605,6 +615,7 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
     if padded:
         if attn.qkv.bias is not None:
             self._op(ops, "fvit_unpad_heads_f32", gbq, 1, self.G(attn.qkv.bias), 1, 3 * Cp, 1, hd, hdp, 1, 0, None)
+            self._bwd_side.add(len(ops) - 1)   # fresh scratch in, parameter gradient out: leaf launch
     # hat_norm1: rows r of the raster buffer = level rows ctr0 + r; gradient at (ct + hat_pe) first
     # accumulated in place (identity map), summed over images for hat_pos_embed, then moved to the
     # xs carrier rows it was gathered from
