@@ -541,6 +541,11 @@ def main() -> None:
                 "launches_per_step": launches / args.steps, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "optimizer_step": opt_info, "also_measured": also, "per_kernel": prof_table,
                 "grad_sync_check": grad_sync,
+                "data_parallel": ({"grad_buckets": len(getattr(plan, "grad_buckets", [])),
+                                   "allreduce_busbw_gbs": round(getattr(plan, "ar_busbw", 0.0) / 1e9, 1),
+                                   "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
+                                   "sm_capped_launches": len(getattr(plan, "_ar_shadow", None) or {})}
+                                  if world > 1 and mode == "train" else None),
                 "model_tflops": round(value * alg / 1e12, 2),
                 "model_frac_of_tensor_peak": round(value / world * alg / 1e12 / pk["tensor"], 4)}
         print(json.dumps(line))

@@ -31,6 +31,7 @@ constexpr int HT_MAX_STAGES = 4;
 struct HatParams {
   int groups, S, heads, gpt, tiles, slot;
   int num_kb;   // ceil(C / 64)
+  int k_tail16; // 16-wide MMA steps with real columns in the last K-block (the rest is TMA zero fill: not issued)
   int stages;
   int Cp;       // heads * hdp
   float scale_log2e;
@@ -131,10 +132,13 @@ __global__ void __launch_bounds__(HT_THREADS, 1)
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+          const int nk = kb + 1 == p.num_kb ? p.k_tail16 : HT_BK / 16;
 #pragma unroll
-          for (int k = 0; k < HT_BK / 16; ++k)
+          for (int k = 0; k < HT_BK / 16; ++k) {
+            if (k >= nk) break;
             umma_f16_ss(tmem_acc[a], make_smem_desc(sa + k * 32, 16, 1024, SWZ_128B),
                         make_smem_desc(sb + k * 32, 16, 1024, SWZ_128B), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) stage = 0, phase ^= 1;
         }
@@ -386,6 +390,7 @@ extern "C" int fvit_hat_attn_fwd(const void* xn16, int64_t ldx, int32_t C, const
   p.gpt = HT_ROWS / p.slot;
   p.tiles = (groups + p.gpt - 1) / p.gpt;
   p.num_kb = (C + HT_BK - 1) / HT_BK;
+  p.k_tail16 = (C - (p.num_kb - 1) * HT_BK + 15) / 16;
   p.Cp = heads * hdp;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.qkv_bias = qkv_bias, p.bias = bias;

@@ -66,6 +66,33 @@ class _Bufs:
         return t
 
 
+def dependency_chains(ops: list) -> list[list[int]]:
+    """Partition a list of plain launches (fn, args, name) into chains that may run concurrently: two launches that
+    share a device-pointer argument (one writes what the other reads, e.g. the bias-table MLP and the gather that
+    follows it) stay in list order inside one chain. Anything that is not a plain launch (host-side pseudo ops) makes
+    the whole list one serial chain-less result ([]): the caller then runs it in order."""
+    parent = list(range(len(ops)))
+
+    def find(i: int) -> int:
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+    owner: dict[int, int] = {}
+    for i, (fn, args, _) in enumerate(ops):
+        if isinstance(fn, str) or not isinstance(args, tuple):
+            return []
+        for a in args:
+            if isinstance(a, int) and not isinstance(a, bool) and a >= (1 << 40):   # CUDA device pointers (0x7f.. range); sizes / strides are far below
+                j = owner.setdefault(a, i)
+                if j != i:
+                    parent[find(i)] = find(j)
+    groups: dict[int, list[int]] = {}
+    for i in range(len(ops)):
+        groups.setdefault(find(i), []).append(i)
+    return list(groups.values())
+
+
 class Plan:
     """Static launch list for one (batch, height, width, training) signature."""
     STEM_LD = 32  # fp16 row width of the stem im2col matrix (27 taps zero padded to 32; TMA zero-fills the rest of the K block)
@@ -749,34 +776,10 @@ class Plan:
         re-packing: every launch writes its own operand buffer) as `n_streams` parallel branches: launches that
         share a device pointer stay in order on one stream, the rest are dealt round-robin. A few hundred small
         launches then cost the HBM time of the large ones instead of a serial chain of launch latencies."""
-        chains = getattr(self, "_branch_chains", {}).get(id(ops))
+        cache = self.__dict__.setdefault("_branch_chains", {})
+        chains = cache.get(id(ops))
         if chains is None:
-            parent = list(range(len(ops)))
-
-            def find(i):
-                while parent[i] != i:
-                    parent[i] = parent[parent[i]]
-                    i = parent[i]
-                return i
-            owner: dict[int, int] = {}
-            plain = True
-            for i, (fn, args, _) in enumerate(ops):
-                if isinstance(fn, str) or not isinstance(args, tuple):
-                    plain = False
-                    break
-                for a in args:
-                    if isinstance(a, int) and a > (1 << 32):   # device pointers (sizes and strides are far below)
-                        j = owner.setdefault(a, i)
-                        if j != i:
-                            parent[find(i)] = find(j)
-            groups: dict[int, list[int]] = {}
-            if plain:
-                for i in range(len(ops)):
-                    groups.setdefault(find(i), []).append(i)
-            chains = list(groups.values()) if plain else []
-            if not hasattr(self, "_branch_chains"):
-                self._branch_chains = {}
-            self._branch_chains[id(ops)] = chains
+            chains = cache[id(ops)] = dependency_chains(ops)
         if len(chains) < 2 * n_streams:
             self.run_ops(ops, None)
             return

@@ -239,7 +239,7 @@ class TrainPlan(Plan):
         self._dlogits[:, :self._ncls].copy_(dlogits)
         red = GradBucketReducer(self.gflat, None if grp is True else grp)
         if getattr(self, "_ar_shadow", None) is None:
-            self._ar_shadow = self._allreduce_shadow(red.world)
+            self._ar_shadow = self._allreduce_shadow(red.world, red.measure_busbw())
         if getattr(self, "_bwd_segments", None) is None:
             segs, start = [], 0
             for i, op in enumerate(self.bwd_ops):
@@ -267,7 +267,7 @@ class TrainPlan(Plan):
             self._ar_active = None
         red.finish(self.grad_buckets)
 
-    def _allreduce_shadow(self, world: int) -> dict:
+    def _allreduce_shadow(self, world: int, busbw: float | None = None) -> dict:
         """{backward op index: SM cap} for the launches that run while a bucket's all-reduce is in flight. NCCL's CTAs
         cannot co-reside with a GEMM CTA (227 KB of shared memory, one per SM): a full-width persistent grid launched
         into the reduction would run its last CTAs as a second wave, doubling that launch. The window is estimated at
@@ -282,7 +282,10 @@ class TrainPlan(Plan):
         shadow: dict[int, int] = {}
         # all-reduce bus bandwidth with NCCL_MAX_CTAS = 16: 8 ranks ~600 GB/s (NVLS), fewer ranks ring over fewer links
         # (timeline at 2 ranks, profiles/r02h_ddp_timeline.json: the 790 MB level-2 bucket shadows ~6 ms of launches)
-        busbw = {2: 200e9, 3: 300e9, 4: 400e9}.get(world, 600e9)
+        # -- measured once per plan on the idle fabric (GradBucketReducer.measure_busbw); the table is the fallback
+        if not busbw or busbw <= 0:
+            busbw = {2: 200e9, 3: 300e9, 4: 400e9}.get(world, 600e9)
+        self.ar_busbw = busbw
         for i, op in enumerate(self.bwd_ops):
             if op[0] != "bucket":
                 continue
@@ -354,6 +357,25 @@ class GradBucketReducer:
         op = self.dist.ReduceOp.AVG if self.avg else self.dist.ReduceOp.SUM
         self.pending.append(self.dist.all_reduce(self.flat[lo:hi], op=op, group=self.group, async_op=True))
         self.done.append((lo, hi))
+
+    def measure_busbw(self, nbytes: int = 64 << 20) -> float | None:
+        """All-reduce bus bandwidth (bytes/s) of this group as configured (NCCL_MAX_CTAS, topology), timed once on a
+        slice of the flat buffer before the backward pass zeroes it: sizes the SM cap windows of the launch list."""
+        if self.world == 1 or not self.avg or not self.flat.is_cuda:
+            return None
+        n = min(self.flat.numel(), nbytes // 4)
+        buf = self.flat[:n]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(3):   # two warm-ups (channel setup), one timed
+            if i == 2:
+                ev[0].record()
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.AVG, group=self.group)
+        ev[1].record()
+        ev[1].synchronize()
+        ms = ev[0].elapsed_time(ev[1])
+        bw = torch.tensor([2.0 * (self.world - 1) / self.world * n * 4 / (ms * 1e-3)], device=self.flat.device)
+        self.dist.all_reduce(bw, op=self.dist.ReduceOp.MIN, group=self.group)   # every rank plans the same windows
+        return float(bw.item())
 
     def finish(self, buckets: list[tuple[int, int]]) -> None:
         for lo, hi in buckets:

@@ -332,28 +332,54 @@ def _build_backward(self) -> None:
     # gradient buckets of the data-parallel all-reduce, in completion order. The flat buffer follows
     # .parameters() order (patch_embed, levels.0 .. levels.n, norm, head); the backward pass finishes
     # [levels.n, norm, head] first, then one transformer level at a time, then the conv part.
+    # Transformer levels are cut further: a bucket point after every group of blocks whose gradients add up to
+    # FVIT_BUCKET_MB (default 100 MB; fv4: every 2 level-2 blocks / every level-3 block), so that the reduction of a
+    # level overlaps that level's own backward and no single burst lands on the few large conv weight-gradient launches
+    # at the end. The rest of a level (downsample, tokenizer) goes with the level-end point.
+    import os
     first = {}
     for name, p in m.named_parameters():
         if name.startswith("levels."):
             first.setdefault(int(name.split(".")[1]), self._goff[id(p)])
     total = self.gflat.numel()
+    group_floats = int(float(os.environ.get("FVIT_BUCKET_MB", "100")) * 1e6 / 4)
     self.grad_buckets = []
+
+    def point(lo: int, hi: int) -> None:
+        if hi > lo:
+            self.grad_buckets.append((lo, hi))
+            self.bwd_ops.append(("bucket", (lo, hi), "grad_bucket"))
+
     self._emit_head_bwd(self.feat)
     toks = [lv for lv in self.lv]
     n_conv = len(m.levels) - len(toks)
     hi = total
     for idx in range(len(toks) - 1, -1, -1):
         tl = toks[idx]
-        self._emit_token_level_bwd(tl)
         lo = first.get(n_conv + idx, hi)
-        self.grad_buckets.append((lo, hi))
-        self.bwd_ops.append(("bucket", (lo, hi), "grad_bucket"))
+        # offsets of the level's blocks in the flat buffer (module order = offset order, contiguous)
+        spans = []
+        for blk in m.levels[tl["level_index"]].blocks:
+            offs = [(self._goff[id(q)], q.numel()) for q in blk.parameters()]
+            spans.append((min(o for o, _ in offs), max(o + _ru(n, 64) for o, n in offs)))
+        contiguous = all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans and lo <= spans[0][0] and spans[-1][1] <= hi
+        state = dict(top=spans[-1][1] if spans else hi)   # blocks above `top` have been handed to a bucket already
+
+        def after_block(k: int, spans=spans, state=state) -> None:
+            if group_floats > 0 and contiguous and k > 0 and state["top"] - spans[k][0] >= group_floats:
+                point(spans[k][0], state["top"])
+                state["top"] = spans[k][0]
+        self._emit_token_level_bwd(tl, after_block)
+        if contiguous and state["top"] < spans[-1][1]:   # some block groups are out already: the rest in two pieces
+            point(spans[-1][1], hi)
+            point(lo, state["top"])
+        else:
+            point(lo, hi)
         hi = lo
         src = toks[idx - 1] if idx > 0 else self.conv_out
         self._emit_downsample_bwd(tl["ds"], src, tl)
     self._emit_conv_part_bwd()
-    self.grad_buckets.append((0, hi))
-    self.bwd_ops.append(("bucket", (0, hi), "grad_bucket"))
+    point(0, hi)
 
 
 def _emit_head_bwd(self, feat: dict) -> None:
@@ -531,7 +557,7 @@ def _unpad_row_map(self, heads3: int, hd: int, hdp: int) -> int:
     return cache[key].data_ptr()
 
 
-def _emit_token_level_bwd(self, tl: dict) -> None:
+def _emit_token_level_bwd(self, tl: dict, after_block=None) -> None:
     B, Cc, S, ncw, ws = self.B, tl["C"], tl["S"], tl["ncw"], tl["ws"]
     nW, n_ct = tl["nW"], tl["n_ct"]
     ops = self.bwd_ops
@@ -560,6 +586,8 @@ def _emit_token_level_bwd(self, tl: dict) -> None:
             # carrier attention; its LayerNorm gathered from the xs carrier rows (ct_dewindow): the
             # gradient goes back there (row indices are relative to the level's g buffer)
             _attn_bwd_carrier(self, tl, sv, blk, gc_ptr, g_ptr)
+        if after_block is not None:
+            after_block(tl["blocks_sv"].index(sv))   # this block's parameter gradients are final
     level = self.model.levels[tl["level_index"]]
     if level.do_gt and has_ct:
         tk = level.global_tokenizer
