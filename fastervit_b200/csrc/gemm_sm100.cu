@@ -113,6 +113,22 @@ __device__ __forceinline__ uint32_t pack2_16(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 256-bit global accesses (sm_100: one full 32-byte sector per lane and instruction)
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ float2 unpack2_16(uint32_t w, int bf16) {
+  if (bf16) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+
 __device__ __forceinline__ float4 ld_vec4_guard(const float* p, int valid, float fill) {
   if (valid >= 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
   float4 r = make_float4(fill, fill, fill, fill);
@@ -174,6 +190,7 @@ enum : uint32_t {
   EF_RS = 1u << 12,
   EF_OSUM = 1u << 13,        // per-column sum of the rounded 16-bit output (bias gradient of the next layer)
   EF_PREGRAD = 1u << 14,     // out_pre16 receives gelu'(v) (consumed by FVIT_ACT_MUL_AUX in the backward pass)
+  EF_DIRECT = 1u << 15,      // 16-bit outputs only: row-per-thread epilogue straight from TMEM (no staging tile), 32-byte stores
 };
 // work unit -> (M tile, N tile, K split). Plain GEMMs keep the K splits of a tile adjacent; the tap-in-N mode
 // walks all tiles of one K range first so concurrently running CTAs share the A / B slices in L2.
@@ -436,6 +453,127 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       bool waited = false;
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(quad * 32) << 16);
 
+      if constexpr ((FEAT & EF_DIRECT) != 0) {
+        // Row-per-thread epilogue for launches that only write 16-bit outputs (qkv / fc1 / data gradients): lane l
+        // owns tile row quad*32 + l, computes on the 32 accumulator columns tcgen05.ld hands it and stores them as
+        // two 32-byte sectors per output -- no staging tile, no per-row address math, one bounds check per 16 columns.
+        // (n, the leading dimensions and the base pointers are multiples of 16 elements: checked by the launcher.)
+        const int my_row = row_base + lane;
+        const long long my_orow =
+            my_row < p.m ? (p.row_map ? (long long)p.row_map[my_row] : (long long)my_row) : -1;
+        uint16_t* const orow16 = reinterpret_cast<uint16_t*>(p.out_f16) + (my_orow >= 0 ? my_orow : 0) * p.ld_o16;
+        uint16_t* const prow16 = reinterpret_cast<uint16_t*>(p.out_pre16) + (long long)my_row * p.ld_pre16;
+        const uint16_t* const arow16 = reinterpret_cast<const uint16_t*>(p.aux) + (long long)my_row * p.ld_aux;
+        for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 32 * (NEPI / 4)) {
+          const int nbase = n0 + c0;
+          if (nbase >= n_end) break;  // warp-uniform
+          const int nvalid = min(min(32, n_end - nbase), p.tile_n - c0);   // 16 or 32
+          uint32_t axw[2][8];
+          if (use_aux && my_orow >= 0) {
+            ld_global_256(arow16 + nbase, axw[0]);
+            if (nvalid > 16) ld_global_256(arow16 + nbase + 16, axw[1]);
+          }
+          if (!waited) {
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t raw[32];
+          if (nvalid > 16) {
+            tmem_ld32(taddr + c0, raw);
+          } else {
+            uint32_t lo[16];
+            tmem_ld16(taddr + c0, lo);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) raw[i] = lo[i], raw[16 + i] = 0u;
+          }
+          tmem_ld_wait();
+          float osv[32];  // rounded outputs for the column sums
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (hf * 16 >= nvalid) {
+              if (osum) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) osv[hf * 16 + i] = 0.f;
+              }
+              continue;
+            }
+            const int col = nbase + hf * 16;
+            uint32_t ow[8], pw[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 4 columns at a time: per-column vectors are warp-uniform 16-byte loads
+              float4 cs = make_float4(alpha, alpha, alpha, alpha), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.col_scale) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.col_scale + col) + q);
+                cs.x *= t.x, cs.y *= t.y, cs.z *= t.z, cs.w *= t.w;
+              }
+              if (p.col_shift) sh = __ldg(reinterpret_cast<const float4*>(p.col_shift + col) + q);
+              float v[4] = {fmaf(__uint_as_float(raw[hf * 16 + 4 * q]), cs.x, sh.x),
+                            fmaf(__uint_as_float(raw[hf * 16 + 4 * q + 1]), cs.y, sh.y),
+                            fmaf(__uint_as_float(raw[hf * 16 + 4 * q + 2]), cs.z, sh.z),
+                            fmaf(__uint_as_float(raw[hf * 16 + 4 * q + 3]), cs.w, sh.w)};
+              float pv[4] = {v[0], v[1], v[2], v[3]};
+              if (act == FVIT_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              } else if (act == FVIT_ACT_GELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (has_pre && pregrad) v[e] = fvit_gelu_both(v[e], pv[e]);
+                  else v[e] = gelu_erf(v[e]);
+                }
+              }
+              if (use_aux) {
+                const float2 a01 = unpack2_16(axw[hf][2 * q], p.bf16), a23 = unpack2_16(axw[hf][2 * q + 1], p.bf16);
+                float a[4] = {a01.x, a01.y, a23.x, a23.y};
+                if (act == FVIT_ACT_MUL_AUX) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[e] *= a[e];
+                } else {
+                  if (p.aux_scale) {
+                    const float4 asc = __ldg(reinterpret_cast<const float4*>(p.aux_scale + col) + q);
+                    const float4 ash = __ldg(reinterpret_cast<const float4*>(p.aux_shift + col) + q);
+                    a[0] = fmaf(a[0], asc.x, ash.x), a[1] = fmaf(a[1], asc.y, ash.y), a[2] = fmaf(a[2], asc.z, ash.z),
+                    a[3] = fmaf(a[3], asc.w, ash.w);
+                  }
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    if (act == FVIT_ACT_GELU_BWD) v[e] *= gelu_erf_grad(a[e]);
+                    else v[e] = a[e] > 0.f ? v[e] : 0.f;
+                  }
+                }
+              }
+              ow[2 * q] = pack2_16(v[0], v[1], p.bf16), ow[2 * q + 1] = pack2_16(v[2], v[3], p.bf16);
+              if (has_pre) pw[2 * q] = pack2_16(pv[0], pv[1], p.bf16), pw[2 * q + 1] = pack2_16(pv[2], pv[3], p.bf16);
+              if (osum) {
+                const float2 r01 = unpack2_16(ow[2 * q], p.bf16), r23 = unpack2_16(ow[2 * q + 1], p.bf16);
+                const bool okr = my_orow >= 0;
+                osv[hf * 16 + 4 * q] = okr ? r01.x : 0.f, osv[hf * 16 + 4 * q + 1] = okr ? r01.y : 0.f;
+                osv[hf * 16 + 4 * q + 2] = okr ? r23.x : 0.f, osv[hf * 16 + 4 * q + 3] = okr ? r23.y : 0.f;
+              }
+            }
+            if (my_orow >= 0) {
+              st_global_256(orow16 + col, ow);
+              if (has_pre) st_global_256(prow16 + col, pw);
+            }
+          }
+          if (osum) {
+            // column sums over the warp's 32 rows: butterfly that halves the live values per step; lane l ends
+            // up with column c0 + l
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool up = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < sft; ++i) {
+                const float send = up ? osv[i] : osv[i + sft];
+                const float keep = up ? osv[i + sft] : osv[i];
+                osv[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+              }
+            }
+            if (lane < nvalid && osv[0] != 0.f) atomicAdd(stat_s + c0 + lane, osv[0]);
+          }
+        }
+      } else
       for (int c0 = chunk_par * 32; c0 < p.tile_n; c0 += 32 * (NEPI / 4)) {
         const int nbase = n0 + c0;
         if (nbase >= n_end) break;  // warp-uniform
@@ -979,6 +1117,40 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
   if (a->row_scale) feat |= EF_RS;
   if (a->out_colsum) feat |= EF_OSUM;
   if (p.pre_is_grad) feat |= EF_PREGRAD;
+  {
+    // row-per-thread epilogue (EF_DIRECT): 16-bit outputs only, everything a lane touches in 32-byte pieces
+    static int direct = -1;  // FVIT_GEMM_DIRECT=0: staging-tile epilogue everywhere (A/B)
+    if (direct < 0) {
+      const char* e = getenv("FVIT_GEMM_DIRECT");
+      direct = e ? atoi(e) : 1;
+    }
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    const uint32_t allowed = EF_O16 | EF_PRE | EF_PREGRAD | EF_ALPHAPTR | EF_OSUM | (7u << EF_ACT_SHIFT);
+    const bool ok = direct && (feat & ~allowed) == 0 && (feat & EF_O16) && b_ntaps == 1 && a->n % 16 == 0 &&
+                    a->ld_out_f16 % 16 == 0 && al32(a->out_f16) &&
+                    (!a->out_pre16 || (a->ld_out_pre16 % 16 == 0 && al32(a->out_pre16))) &&
+                    (!a->aux || (a->ld_aux % 16 == 0 && al32(a->aux))) &&
+                    (!a->col_scale || (reinterpret_cast<uintptr_t>(a->col_scale) & 15) == 0) &&
+                    (!a->col_shift || (reinterpret_cast<uintptr_t>(a->col_shift) & 15) == 0) &&
+                    (!a->aux_scale || ((reinterpret_cast<uintptr_t>(a->aux_scale) & 15) == 0 &&
+                                       (reinterpret_cast<uintptr_t>(a->aux_shift) & 15) == 0));
+    if (ok) {
+      switch (feat) {   // the combinations with a direct specialisation (launch table below)
+        case (0u << EF_ACT_SHIFT) | EF_O16:
+        case (1u << EF_ACT_SHIFT) | EF_O16:
+        case (2u << EF_ACT_SHIFT) | EF_O16:
+        case (2u << EF_ACT_SHIFT) | EF_O16 | EF_PRE | EF_PREGRAD:
+        case (0u << EF_ACT_SHIFT) | EF_O16 | EF_ALPHAPTR:
+        case (3u << EF_ACT_SHIFT) | EF_O16:
+        case (5u << EF_ACT_SHIFT) | EF_O16 | EF_ALPHAPTR:
+        case (5u << EF_ACT_SHIFT) | EF_O16 | EF_ALPHAPTR | EF_OSUM:
+          feat |= EF_DIRECT;
+          break;
+        default:
+          break;
+      }
+    }
+  }
   const bool needs_generic = false;
 #define FVIT_GEMM_LAUNCH(F)                                                                            \
   do {                                                                                                 \
@@ -1047,6 +1219,17 @@ extern "C" int fvit_gemm(const fvit_gemm_args* a, void* stream) {
       case FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR);   // fc2 dgrad * saved gelu'
       case FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR | EF_OSUM:
         FVIT_GEMM_LAUNCH(FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR | EF_OSUM);                                  // ... + fc1 bias gradient
+      // ---- row-per-thread epilogue variants of the 16-bit-output launches
+      case EF_DIRECT | FVIT_ACTF(0) | EF_O16: FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(0) | EF_O16);
+      case EF_DIRECT | FVIT_ACTF(1) | EF_O16: FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(1) | EF_O16);
+      case EF_DIRECT | FVIT_ACTF(2) | EF_O16: FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(2) | EF_O16);
+      case EF_DIRECT | FVIT_ACTF(2) | EF_O16 | EF_PRE | EF_PREGRAD:
+        FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(2) | EF_O16 | EF_PRE | EF_PREGRAD);
+      case EF_DIRECT | FVIT_ACTF(0) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(0) | EF_O16 | EF_ALPHAPTR);
+      case EF_DIRECT | FVIT_ACTF(3) | EF_O16: FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(3) | EF_O16);
+      case EF_DIRECT | FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR: FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR);
+      case EF_DIRECT | FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR | EF_OSUM:
+        FVIT_GEMM_LAUNCH(EF_DIRECT | FVIT_ACTF(5) | EF_O16 | EF_ALPHAPTR | EF_OSUM);
       default: break;
     }
   }

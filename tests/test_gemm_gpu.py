@@ -436,3 +436,91 @@ def test_gemm_pair_conv3x3_taps(cin, cout, hw):
     got = out.view(bsz, Hp, Wp, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
     ref = torch.nn.functional.conv2d(x.float().cpu(), w.float().cpu(), padding=1).cuda()
     assert _rel(got, ref) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Row-per-thread epilogue (EF_DIRECT): launches that only write 16-bit outputs take it when every leading dimension
+# is a multiple of 16 elements; the same call on 8-element-padded views goes through the staging-tile epilogue. Both
+# must produce the same bits (same arithmetic, different data movement).
+def _wide(m, n, pad, gen=None, scale=1.0):
+    buf = torch.zeros(m, n + pad, device="cuda", dtype=torch.float16)
+    if gen is not None:
+        buf[:, :n] = (torch.randn(m, n, device="cuda", generator=gen) * scale).half()
+    return buf[:, :n]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("m,n,k,tile_n", [(512, 256, 128, 0), (1000, 3136, 200, 0), (333, 784, 72, 0), (700, 400, 136, 0),
+                                          (300, 208, 64, 48), (2050, 1024, 784, 160)])
+@pytest.mark.parametrize("variant", ["plain", "bias_gelu", "gelu_pregrad", "dgrad_alpha", "mul_aux_osum", "gelu_bwd_aux"])
+def test_gemm_direct_epilogue_matches_staged(variant, m, n, k, tile_n, cg):
+    lib = _lib()
+    if cg == 2 and tile_n % 32:
+        tile_n = 0
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.1).half()
+    bias = torch.randn(n, device="cuda", generator=g)
+    scale = torch.rand(n, device="cuda", generator=g) + 0.5
+    alpha = torch.full((1,), 0.75, device="cuda")
+    outs = {}
+    for pad in (0, 8):   # 0: leading dimensions % 16 == 0 -> direct; 8: staged
+        g2 = torch.Generator(device="cuda").manual_seed(99)
+        o16 = _wide(m, n, pad)
+        kw = dict(out_f16=o16, tile_n=tile_n, cta_group=cg)
+        extra = []
+        if variant == "bias_gelu":
+            kw.update(act=lib.ACT_GELU, col_shift=bias, col_scale=scale)
+        elif variant == "gelu_pregrad":
+            p16 = _wide(m, n, pad)
+            kw.update(act=lib.ACT_GELU, col_shift=bias, out_pre16=p16, pre_is_grad=True)
+            extra.append(p16)
+        elif variant == "dgrad_alpha":
+            kw.update(alpha_ptr=alpha)
+        elif variant == "mul_aux_osum":
+            osum = torch.zeros(n, device="cuda")
+            kw.update(act=lib.ACT_MUL_AUX, aux=_wide(m, n, pad, g2), alpha_ptr=alpha, out_colsum=osum, out_colsum_alpha=alpha)
+            extra.append(osum)
+        elif variant == "gelu_bwd_aux":
+            kw.update(act=lib.ACT_GELU_BWD, aux=_wide(m, n, pad, g2), aux_scale=scale, aux_shift=bias)
+        lib.gemm(a, b, **kw)
+        torch.cuda.synchronize()
+        outs[pad] = [o16.clone()] + [e.clone() for e in extra]
+    assert torch.equal(outs[0][0], outs[8][0])
+    if variant == "gelu_pregrad":
+        assert torch.equal(outs[0][1], outs[8][1])
+    if variant == "mul_aux_osum":   # float atomics in a different order
+        want = 0.75 * outs[0][0].double().sum(0)
+        for o in (outs[0][1], outs[8][1]):
+            assert (o.double() - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
+    ref = a.double() @ b.double().t()
+    if variant == "plain":
+        assert _rel(outs[0][0], ref) < 1e-3
+    if variant == "dgrad_alpha":
+        assert _rel(outs[0][0], 0.75 * ref) < 1e-3
+    if variant == "bias_gelu":
+        assert _rel(outs[0][0], torch.nn.functional.gelu(ref * scale.double() + bias.double())) < 1.5e-3
+
+
+def test_gemm_direct_epilogue_row_map_scatter():
+    """The direct epilogue writes row r of the tile to out[row_map[r]] (window-major -> raster scatter of the conv
+    data gradients): permuted and dropped (-1) rows, against the staged path on a padded view."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    m, n, k = 900, 256, 96
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.1).half()
+    perm = torch.randperm(m, device="cuda", generator=g).int()
+    perm[::7] = -1
+    res = []
+    for pad in (0, 8):
+        o16 = _wide(m, n, pad)
+        lib.gemm(a, b, row_map=perm, out_f16=o16)
+        res.append(o16.clone())
+    assert torch.equal(res[0], res[1])
+    ref = (a.float() @ b.float().t()).half()
+    keep = perm >= 0
+    assert _rel(res[0][perm[keep].long()], ref[keep]) < 1e-3
+    dropped = torch.ones(m, dtype=torch.bool, device="cuda")
+    dropped[perm[keep].long()] = False
+    assert (res[0][dropped] == 0).all()
