@@ -38,6 +38,11 @@ WORKLOADS = {
     # depth is a per-window mask multiply: same FLOPs) ; no optimizer (the metric is fwd+bwd img/s)
     "fv0_train": ("faster_vit_0_224", dict(drop_path_rate=0.0), 256, (224, 224), "train"),
     "fv4_train": ("faster_vit_4_224", dict(drop_path_rate=0.0), 128, (224, 224), "train"),
+    # side measurements of the `also_measured` block (not BASELINE configs): small-batch latency of the forward launch
+    # graph, and a training step of a 21k fine-tuning model whose 24 x 24 windows (S = 576) take the long-window
+    # attention backward (fvit_attn_loop_bwd_long)
+    "fv0_fwd_b8": ("faster_vit_0_224", {}, 8, (224, 224), "fwd"),
+    "fv4_21k_384_train": ("faster_vit_4_21k_384", dict(drop_path_rate=0.0), 32, (384, 384), "train"),
 }
 ORACLE_CASE = {"fv0_fwd": "fv0", "fv4_fwd": "fv4", "ar0_fwd": "ar0", "fv0_train": "fv0", "fv4_train": "fv4"}
 # algorithmic forward GFLOP per image (measured on the reference with FlopCounterMode)
@@ -215,14 +220,30 @@ def quick_measure(workload: str, dev, pk: dict, steps: int = 8, warmup: int = 3)
     gm_fl = sum(r["flops"] for r in prof if r["name"] == "fvit_gemm")
     tot = sum(r["ms"] for r in prof)
     simt = sum(r["ms"] for r in prof if r["name"] in ("fvit_attn_core_fwd", "fvit_attn_core_bwd"))
-    alg = ALG_GFLOP_FWD[workload] * 1e9
+    alg = ALG_GFLOP_FWD.get(workload, 0.0) * 1e9   # (0: no algorithmic FLOP count in BASELINE.md for this config)
     out = {"workload": f"{entry} {'fwd+bwd' if mode == 'train' else 'forward'}, batch {batch}, 3x{hw[0]}x{hw[1]}",
            "value": round(value, 1), "unit": "img/s", "ms_per_step": round(ms, 4), "steps": steps, "warmup": warmup,
-           "model_frac_of_tensor_peak": round(value * alg / 1e12 / pk["tensor"], 4),
+           "model_frac_of_tensor_peak": round(value * alg / 1e12 / pk["tensor"], 4) if alg else None,
            "gemm": {"share_of_step": round(gm_ms / tot, 4), "achieved_tflops": round(gm_fl / (gm_ms / 1e3) / 1e12, 1),
                     "frac": round(gm_fl / (gm_ms / 1e3) / 1e12 / pk["tensor"], 4)},
            "simt_attention_ms": round(simt, 4),
            "vs_baseline": round(value / PUBLISHED_IMG_S[workload], 3) if workload in PUBLISHED_IMG_S else None}
+    long_bwd = [r["ms"] for r in prof if r["name"] == "fvit_attn_loop_bwd_long"]
+    if long_bwd:
+        out["attn_loop_bwd_long"] = {"launches": len(long_bwd), "ms": round(sum(long_bwd), 4)}
+    if batch <= 16 and mode == "fwd":
+        # latency of ONE synchronous call through model(x) (host enqueue of the graph launch + device time + the wait)
+        with torch.no_grad():
+            lat = []
+            for i in range(30):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                model(xs[i % 2])
+                torch.cuda.synchronize()
+                lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        out["latency_ms"] = {"median": round(lat[len(lat) // 2], 4), "p10": round(lat[3], 4), "p90": round(lat[26], 4),
+                             "what": "wall clock of one synchronous model(x) call, 30 calls"}
     del plan, model, xs
     torch.cuda.empty_cache()
     return out
@@ -283,7 +304,7 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="fv4_train", choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default="fv4_train", choices=sorted(ORACLE_CASE),
                     help="default: BASELINE.json configs[2]/[4] (the metric is fwd+bwd images/sec); fv0_fwd = configs[1]")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
@@ -523,7 +544,7 @@ def main() -> None:
         del model, xs
         torch.cuda.empty_cache()
         also = {}
-        for wl in ("fv0_fwd", "fv0_train", "ar0_fwd", "fv4_fwd"):
+        for wl in ("fv0_fwd", "fv0_train", "ar0_fwd", "fv4_fwd", "fv0_fwd_b8", "fv4_21k_384_train"):
             try:
                 also[wl] = quick_measure(wl, dev, pk)
             except Exception as exc:  # a side measurement must not take the headline line down

@@ -768,6 +768,356 @@ static int launch_attn_loop_bwd(const CUtensorMap& tq, const CUtensorMap& td, co
   return post_launch("attn_loop_bwd_kernel");
 }
 
+
+// =====================================================================================================
+// fvit_attn_loop_bwd_long: the same backward for windows of more than two tiles (S > 256: the 21k models' 24 x 24,
+// 32 x 32 and 48 x 48 windows, fv.py:1253-1418). Work item = (window, head); key tiles j outside, query tiles i inside:
+//   S = Q_i K_j^T, dP = dO_i V_j^T -> P, dS (as above) -> dV_j += P^T dO_i, dK_j += dS^T Q_i (TMEM, over the query loop)
+//   and the PARTIAL dQ_i = dS K_j of this pair in its own TMEM region (not accumulated: nt tiles of dQ do not fit).
+// The thread that owns query row r of every tile adds the partial to its row of an fp32 scratch matrix
+// dq_scratch[groups * S, heads * HDP] (plain 16-byte stores for j = 0, 16-byte reductions afterwards) and converts
+// the row to fp16 once the key loop is over. Only one CTA ever touches a (window, head) slice and only one thread a
+// row of it, so the reductions need no initialisation and no ordering beyond program order. Q_i / dO_i stream through
+// a two-stage ring (L2 hits after the first key tile); delta and the log-sum-exp rows sit in shared memory.
+struct AttnLoopBwdLongParams {
+  AttnLoopBwdParams b;
+  float* dq32;
+  long long lddq32;
+};
+
+template <int HDP>
+__global__ void __launch_bounds__(AL_THREADS, 1)
+    attn_loop_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                              const __grid_constant__ AttnLoopBwdLongParams pl) {
+  const AttnLoopBwdParams& p = pl.b;
+  constexpr uint32_t SWZ = HDP == 64 ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t ROW_BYTES = HDP * 2;
+  constexpr uint32_t SBO_QKV = 8 * ROW_BYTES;
+  constexpr int TILE_BYTES = AL_ROWS * HDP * 2;
+  constexpr int QDO_OFF = 0;                      // 2 stages of (Q_i, dO_i)
+  constexpr int KV_OFF = 4 * TILE_BYTES;          // 2 stages of (K_j, V_j)
+  constexpr int P_OFF = KV_OFF + 4 * TILE_BYTES;
+  constexpr int DS_OFF = P_OFF + AL_ROWS * 128 * 2;
+  constexpr int CTRL_OFF = DS_OFF + AL_ROWS * 128 * 2;
+  constexpr int ROWV_OFF = CTRL_OFF + 256;        // delta[nt * 128], lse[nt * 128]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, nt = p.nt;
+  uint64_t* qdo_full = reinterpret_cast<uint64_t*>(smem + CTRL_OFF);  // [2]
+  uint64_t* qdo_empty = qdo_full + 2;  // [2]
+  uint64_t* kv_full = qdo_empty + 2;   // [2]
+  uint64_t* kv_empty = kv_full + 2;    // [2]
+  uint64_t* sdp_full = kv_empty + 2;
+  uint64_t* sdp_empty = sdp_full + 1;
+  uint64_t* pds_full = sdp_empty + 1;
+  uint64_t* pds_empty = pds_full + 1;
+  uint64_t* dkv_full = pds_empty + 1;
+  uint64_t* dkv_empty = dkv_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_empty + 1);
+  float* s_delta = reinterpret_cast<float*>(smem + ROWV_OFF);
+  float* s_lse = s_delta + nt * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
+      mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4);
+    mbar_init(pds_full, 4), mbar_init(pds_empty, 1);
+    mbar_init(dkv_full, 1), mbar_init(dkv_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+
+  const int items = p.groups * p.heads;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kv_cnt = 0, pair = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int grp = w % p.groups, head = w / p.groups;
+        const int row0 = grp * S;
+        for (int j = 0; j < nt; ++j, ++kv_cnt) {
+          const int st = kv_cnt & 1;
+          mbar_wait(&kv_empty[st], ((kv_cnt >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          tma_load_2d(smem + KV_OFF + (2 * st) * TILE_BYTES, &tmap_qkv, &kv_full[st], (p.heads + head) * HDP, row0 + j * 128);
+          tma_load_2d(smem + KV_OFF + (2 * st + 1) * TILE_BYTES, &tmap_qkv, &kv_full[st], (2 * p.heads + head) * HDP,
+                      row0 + j * 128);
+          for (int i = 0; i < nt; ++i, ++pair) {
+            const int qs = pair & 1;
+            mbar_wait(&qdo_empty[qs], ((pair >> 1) & 1) ^ 1);
+            mbar_expect_tx(&qdo_full[qs], 2 * TILE_BYTES);
+            tma_load_2d(smem + QDO_OFF + (2 * qs) * TILE_BYTES, &tmap_qkv, &qdo_full[qs], head * HDP, row0 + i * 128);
+            tma_load_2d(smem + QDO_OFF + (2 * qs + 1) * TILE_BYTES, &tmap_do, &qdo_full[qs], head * HDP, row0 + i * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_ss = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t id_tn = make_idesc_f16(128, HDP, 1, 1);  // A = P / dS read MN-major (M = keys), B MN-major
+      const uint32_t id_dq = make_idesc_f16(128, HDP, 0, 1);
+      const uint32_t sP = smem_u32(smem + P_OFF), sDS = smem_u32(smem + DS_OFF);
+      uint32_t kv_cnt = 0, pair = 0, jcnt = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        for (int j = 0; j < nt; ++j, ++kv_cnt, ++jcnt) {
+          const int st = kv_cnt & 1;
+          mbar_wait(&kv_full[st], (kv_cnt >> 1) & 1);
+          const uint32_t sK = smem_u32(smem + KV_OFF + (2 * st) * TILE_BYTES), sV = sK + TILE_BYTES;
+          for (int i = 0; i < nt; ++i, ++pair) {
+            const int qs = pair & 1;
+            const uint32_t sQ = smem_u32(smem + QDO_OFF + (2 * qs) * TILE_BYTES), sDO = sQ + TILE_BYTES;
+            mbar_wait(&qdo_full[qs], (pair >> 1) & 1);
+            mbar_wait(sdp_empty, (pair & 1) ^ 1);  // the softmax warps have read the previous pair's S / dP
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < HDP / 16; ++k)
+              umma_f16_ss(tS, make_smem_desc(sQ + k * 32, 16, SBO_QKV, SWZ), make_smem_desc(sK + k * 32, 16, SBO_QKV, SWZ), id_ss,
+                          k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < HDP / 16; ++k)
+              umma_f16_ss(tDP, make_smem_desc(sDO + k * 32, 16, SBO_QKV, SWZ), make_smem_desc(sV + k * 32, 16, SBO_QKV, SWZ), id_ss,
+                          k > 0 ? 1u : 0u);
+            umma_commit(sdp_full);
+            // pds_full also says: the previous pair's dQ partial has been read out of tDQ
+            mbar_wait(pds_full, pair & 1);
+            if (i == 0) mbar_wait(dkv_empty, (jcnt & 1) ^ 1);  // previous key tile's dV / dK have been read out
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows in steps of 16
+              const uint64_t aP = make_smem_desc(sP + ks * 2048, AL_ROWS * 128, 1024, SWZ_128B);
+              const uint64_t aDS = make_smem_desc(sDS + ks * 2048, AL_ROWS * 128, 1024, SWZ_128B);
+              const uint64_t bDO = make_smem_desc(sDO + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
+              const uint64_t bQ = make_smem_desc(sQ + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
+              umma_f16_ss(tDV, aP, bDO, id_tn, (i > 0 || ks > 0) ? 1u : 0u);
+              umma_f16_ss(tDK, aDS, bQ, id_tn, (i > 0 || ks > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // K = 128 keys
+              const uint64_t aDS = make_smem_desc(sDS + (ks >> 2) * (AL_ROWS * 128) + (ks & 3) * 32, 16, 1024, SWZ_128B);
+              const uint64_t bK = make_smem_desc(sK + ks * 16 * ROW_BYTES, 0, SBO_QKV, SWZ);
+              umma_f16_ss(tDQ, aDS, bK, id_dq, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(pds_empty);
+            umma_commit(&qdo_empty[qs]);
+          }
+          umma_commit(dkv_full);
+          umma_commit(&kv_empty[st]);
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    uint8_t* sP = smem + P_OFF;
+    uint8_t* sDS = smem + DS_OFF;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    uint32_t pair = 0, jcnt = 0;
+    const int Cp = p.heads * HDP;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int grp = w % p.groups, head = w / p.groups;
+      const long long row0 = (long long)grp * S;
+      // per query row this thread owns (row r of every tile): delta = sum_c dO * O and the forward's log-sum-exp
+      for (int i = 0; i < nt; ++i) {
+        const int q = i * 128 + r;
+        float acc = 0.f, l = 0.f;
+        if (q < S) {
+          const uint4* a = reinterpret_cast<const uint4*>(p.dout + (row0 + q) * p.lddo + head * HDP);
+          const uint4* b = reinterpret_cast<const uint4*>(p.out + (row0 + q) * p.ldo + head * HDP);
+#pragma unroll
+          for (int v = 0; v < HDP / 8; ++v) {
+            const uint4 x = __ldg(a + v), y = __ldg(b + v);
+            const __half2* hx = reinterpret_cast<const __half2*>(&x);
+            const __half2* hy = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fx = __half22float2(hx[e]), fy = __half22float2(hy[e]);
+              acc = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, acc));
+            }
+          }
+          l = p.lse[(row0 + q) * p.heads + head];
+        }
+        s_delta[q] = acc, s_lse[q] = l;   // (read back by this thread only)
+      }
+      // partial dQ of the pair (j, i): TMEM -> * scale -> this thread's fp32 scratch row
+      auto flush_dq = [&](int j, int i) {
+        const int q = i * 128 + r;
+        float* drow = pl.dq32 + (row0 + q) * pl.lddq32 + head * HDP;
+#pragma unroll
+        for (int c0 = 0; c0 < HDP; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tDQ + lane_off + c0, raw);
+          tmem_ld_wait();
+          if (q < S) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float v0 = __uint_as_float(raw[q4 * 4]) * p.scale, v1 = __uint_as_float(raw[q4 * 4 + 1]) * p.scale;
+              const float v2 = __uint_as_float(raw[q4 * 4 + 2]) * p.scale, v3 = __uint_as_float(raw[q4 * 4 + 3]) * p.scale;
+              if (j == 0)
+                *reinterpret_cast<float4*>(drow + c0 + q4 * 4) = make_float4(v0, v1, v2, v3);
+              else
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + q4 * 4), "f"(v0), "f"(v1),
+                             "f"(v2), "f"(v3)
+                             : "memory");
+            }
+          }
+        }
+      };
+      for (int j = 0; j < nt; ++j, ++jcnt) {
+        const int ncols = min(128, S - j * 128);
+        for (int i = 0; i < nt; ++i, ++pair) {
+          const int q = i * 128 + r;
+          const bool row_ok = q < S;
+          const float my_lse = s_lse[q], my_delta = s_delta[q];
+          mbar_wait(sdp_full, pair & 1);
+          mbar_wait(pds_empty, (pair & 1) ^ 1);  // the previous pair's gradient MMAs are complete: P / dS free, dQ final
+          tc_fence_after();
+          if (i > 0) flush_dq(j, i - 1);
+          const float* brow = (p.bias && row_ok) ? p.bias + ((long long)head * S + q) * S + j * 128 : nullptr;
+          float* dbrow = (p.dbias && row_ok) ? p.dbias + ((long long)head * S + q) * S + j * 128 : nullptr;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t pkp[16], pkd[16];
+            if (c0 < ncols) {
+              uint32_t rs[32], rd[32];
+              tmem_ld32(tS + lane_off + c0, rs);
+              tmem_ld32(tDP + lane_off + c0, rd);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const int c = c0 + q4 * 4;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (brow && c < ncols) b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                float pv[4], ds[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const bool in = row_ok && (c + e < ncols);
+                  const float sc = fmaf(__uint_as_float(rs[q4 * 4 + e]), p.scale_log2e, fmaf(bb[e], 1.4426950408889634f, -my_lse));
+                  pv[e] = in ? exp2f(sc) : 0.f;
+                  ds[e] = in ? pv[e] * (__uint_as_float(rd[q4 * 4 + e]) - my_delta) : 0.f;
+                }
+                if (dbrow && c < ncols)  // (S % 4 == 0: a 4-column group is entirely inside or outside the window)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbrow + c), "f"(ds[0]), "f"(ds[1]),
+                               "f"(ds[2]), "f"(ds[3])
+                               : "memory");
+                const __half2 p0 = __floats2half2_rn(pv[0], pv[1]), p1 = __floats2half2_rn(pv[2], pv[3]);
+                const __half2 d0 = __floats2half2_rn(ds[0], ds[1]), d1 = __floats2half2_rn(ds[2], ds[3]);
+                pkp[q4 * 2] = *reinterpret_cast<const uint32_t*>(&p0), pkp[q4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+                pkd[q4 * 2] = *reinterpret_cast<const uint32_t*>(&d0), pkd[q4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&d1);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pkp[e] = 0u, pkd[e] = 0u;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int c = c0 + qq * 8;
+              const uint32_t off = (c >> 6) * (AL_ROWS * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(sP + off) = make_uint4(pkp[4 * qq], pkp[4 * qq + 1], pkp[4 * qq + 2], pkp[4 * qq + 3]);
+              *reinterpret_cast<uint4*>(sDS + off) = make_uint4(pkd[4 * qq], pkd[4 * qq + 1], pkd[4 * qq + 2], pkd[4 * qq + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(sdp_empty);
+            mbar_arrive(pds_full);
+          }
+        }
+        // every MMA of this key tile is complete: the last pair's dQ partial, then dV_j / dK_j (row r = key j*128 + r)
+        mbar_wait(dkv_full, jcnt & 1);
+        tc_fence_after();
+        flush_dq(j, nt - 1);
+        {
+          const int key = j * 128 + r;
+          const bool ok = key < S;
+          __half* orow = p.dqkv + (row0 + key) * p.lddq + head * HDP;
+#pragma unroll
+          for (int which = 1; which < 3; ++which) {
+            const uint32_t tsrc = (which == 1 ? tDK : tDV) + lane_off;
+            const float mul = which == 1 ? p.scale : 1.f;
+#pragma unroll
+            for (int c0 = 0; c0 < HDP; c0 += 32) {
+              uint32_t raw[32];
+              tmem_ld32(tsrc + c0, raw);
+              tmem_ld_wait();
+              if (ok) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                  uint32_t o4[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const __half2 hh = __floats2half2_rn(__uint_as_float(raw[qq * 8 + 2 * u]) * mul,
+                                                         __uint_as_float(raw[qq * 8 + 2 * u + 1]) * mul);
+                    o4[u] = *reinterpret_cast<const uint32_t*>(&hh);
+                  }
+                  *reinterpret_cast<uint4*>(orow + which * Cp + c0 + qq * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_empty);
+      }
+      // dQ rows of this (window, head): fp32 scratch (written by this thread only) -> fp16
+      __threadfence();
+      for (int i = 0; i < nt; ++i) {
+        const int q = i * 128 + r;
+        if (q < S) {
+          const float* drow = pl.dq32 + (row0 + q) * pl.lddq32 + head * HDP;
+          __half* orow = p.dqkv + (row0 + q) * p.lddq + head * HDP;
+#pragma unroll
+          for (int c = 0; c < HDP; c += 8) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(drow + c));
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(drow + c + 4));
+            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+            const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+            *reinterpret_cast<uint4*>(orow + c) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                           *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HDP>
+static int launch_attn_loop_bwd_long(const CUtensorMap& tq, const CUtensorMap& td, const AttnLoopBwdLongParams& p,
+                                     cudaStream_t st) {
+  const size_t smem = 1024 + (size_t)8 * AL_ROWS * HDP * 2 + 2 * AL_ROWS * 128 * 2 + 256 + (size_t)p.b.nt * 128 * 8;
+  FVIT_CHECK(smem <= 227 * 1024, "fvit_attn_loop_bwd_long: S=%d needs %zu bytes of shared memory", p.b.S, smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    FVIT_CUDA(cudaFuncSetAttribute(attn_loop_bwd_long_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int items = p.b.groups * p.b.heads;
+  const int sms = num_sms();
+  attn_loop_bwd_long_kernel<HDP><<<items < sms ? items : sms, AL_THREADS, smem, st>>>(tq, td, p);
+  return post_launch("attn_loop_bwd_long_kernel");
+}
+
 }  // namespace fvit
 
 extern "C" int fvit_attn_loop_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, const void* out, int64_t ldo,
@@ -800,4 +1150,41 @@ extern "C" int fvit_attn_loop_bwd(const void* qkv, int64_t ldq, const void* dout
   }
   if (hdp == 64) return launch_attn_loop_bwd<64>(tq, td, p, (cudaStream_t)stream);
   return launch_attn_loop_bwd<32>(tq, td, p, (cudaStream_t)stream);
+}
+
+extern "C" int fvit_attn_loop_bwd_long(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, const void* out,
+                                       int64_t ldo, const float* lse, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
+                                       const float* bias, float scale, void* dqkv, int64_t lddq, float* dbias,
+                                       float* dq_scratch, int64_t ld_scratch, void* stream) {
+  using namespace fvit;
+  FVIT_CHECK(qkv && dout && out && lse && dqkv && dq_scratch && groups > 0 && heads > 0, "fvit_attn_loop_bwd_long: bad arguments");
+  FVIT_CHECK(S > 128, "fvit_attn_loop_bwd_long: S=%d unsupported (windows of more than one 128-row tile)", S);
+  FVIT_CHECK(S % 4 == 0, "fvit_attn_loop_bwd_long: S=%d must be a multiple of 4 (16-byte bias / dbias accesses)", S);
+  FVIT_CHECK(hdp == 32 || hdp == 64, "fvit_attn_loop_bwd_long: padded head dim %d unsupported", hdp);
+  FVIT_CHECK(ldq % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 && ld_scratch % 4 == 0 &&
+                 ld_scratch >= (int64_t)heads * hdp && (reinterpret_cast<uintptr_t>(dq_scratch) & 15) == 0,
+             "fvit_attn_loop_bwd_long: bad leading dimensions");
+  AttnLoopBwdLongParams pl;
+  AttnLoopBwdParams& p = pl.b;
+  p.groups = groups, p.S = S, p.heads = heads, p.nt = (S + 127) / 128;
+  p.scale = scale, p.scale_log2e = scale * 1.4426950408889634f;
+  p.bias = bias, p.dbias = dbias, p.lse = lse;
+  p.dout = (const __half*)dout, p.lddo = lddo, p.out = (const __half*)out, p.ldo = ldo;
+  p.dqkv = (__half*)dqkv, p.lddq = lddq;
+  pl.dq32 = dq_scratch, pl.lddq32 = ld_scratch;
+  CUtensorMap tq, td;
+  const CUtensorMapSwizzle swz = hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  uint32_t box[2] = {(uint32_t)hdp, (uint32_t)AL_ROWS};
+  {
+    uint64_t dims[2] = {(uint64_t)(3 * heads * hdp), (uint64_t)groups * S};
+    uint64_t strides[1] = {(uint64_t)ldq * 2};
+    int rc = cached_tmap_16bit(&tq, qkv, 2, dims, strides, box, swz);
+    if (rc) return rc;
+    uint64_t dims2[2] = {(uint64_t)(heads * hdp), (uint64_t)groups * S};
+    uint64_t strides2[1] = {(uint64_t)lddo * 2};
+    rc = cached_tmap_16bit(&td, dout, 2, dims2, strides2, box, swz);
+    if (rc) return rc;
+  }
+  if (hdp == 64) return launch_attn_loop_bwd_long<64>(tq, td, pl, (cudaStream_t)stream);
+  return launch_attn_loop_bwd_long<32>(tq, td, pl, (cudaStream_t)stream);
 }

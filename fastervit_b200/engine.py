@@ -119,6 +119,10 @@ class Plan:
         sb = os.environ.get("FVIT_SIDE_BRANCHES", "1") if self.use_graphs else "0"
         self.side_branches = sb in ("1", "3")
         self.prep_branches = sb in ("1", "2")
+        # weight-gradient GEMMs as side-branch launches too (engine_train.py: _side_from / _before_write): their CTAs fill
+        # the tails of the data-gradient chain's persistent grids. FVIT_WGRAD_SIDE=0/1 (A/B switch)
+        # (decided at plan build: the markers are emitted either way and are inert when side branches are off)
+        self.wgrad_side = os.environ.get("FVIT_WGRAD_SIDE", "0") == "1"
         self._graphs: dict = {}
         self._x_static = None
         self._deploy_mods: list = []
@@ -722,6 +726,8 @@ class Plan:
         base = getattr(self, "_op_base", 0)
         cur = side_stream = None
         forked = False
+        side_reads = getattr(self, "_side_reads", None) or {}
+        side_events: dict = {}   # buffer pointer -> event behind the last side launch that reads it (this call only)
         if side:
             cur = torch.cuda.current_stream()
             side_stream = self._side_streams(1)[0]
@@ -741,6 +747,12 @@ class Plan:
                 if mod.deploy:
                     continue
                 rc = fn2(*args2, st)
+            elif fn == "wait_side":   # the next launch overwrites buffers a side-branch launch may still be reading
+                for k in args:
+                    ev = side_events.pop(k, None)
+                    if ev is not None:
+                        cur.wait_event(ev)
+                continue
             elif fn == "bucket":   # gradient slice [lo, hi) of the flat buffer is final (engine_train.py)
                 if forked:
                     cur.wait_stream(side_stream)
@@ -753,6 +765,12 @@ class Plan:
                 side_stream.wait_stream(cur)
                 forked = True
                 rc = fn(*args, side_stream.cuda_stream)
+                keys = side_reads.get(base + idx)
+                if keys:
+                    ev = torch.cuda.Event()
+                    ev.record(side_stream)
+                    for k in keys:
+                        side_events[k] = ev
             else:
                 rc = fn(*args, st)
             if rc != 0:

@@ -42,6 +42,7 @@ class TrainPlan(Plan):
         self.scratch_n = 0
         self._scratch_req: list[tuple[str, int]] = []
         self._bwd_side: set[int] = set()     # backward launches that run as a side branch (engine_train_levels.py)
+        self._side_reads: dict[int, tuple] = {}   # side launch -> shared gradient buffers it reads (WAR hazards)
         # device scalars: [0] S, [1] 1/S, [2] 1.0, then per-branch (s_b, 1/s_b, 1/(S s_b))
         self._nscal = 3
         self._branch_slots: list[tuple[int, object]] = []
@@ -142,6 +143,25 @@ class TrainPlan(Plan):
         if lst is self.bwd_ops:
             self.bwd_flops[len(lst) - 1] = flops if flops is not None else 2.0 * m * n * kc * len(taps)
 
+    # ------------------------------------------------------------------------------ weight gradients as a side branch
+    # A weight-gradient GEMM reads an activation gradient (a per-level buffer every block reuses) and a saved
+    # activation, and adds into parameter-gradient memory nobody reads before the next bucket point: a leaf. As a
+    # side-branch launch it runs beside the data-gradient chain -- two persistent grids share the SMs, each filling
+    # the other's tail waves. The one hazard is write-after-read on the reused gradient buffers: the launch that next
+    # overwrites such a buffer first waits for the event behind its last side-branch reader (`wait_side`).
+    def _side_from(self, first: int, *reads: int) -> None:
+        """make backward launches [first, now) side-branch launches that read the reusable buffers `reads`"""
+        if not self.wgrad_side:
+            return
+        for i in range(first, len(self.bwd_ops)):
+            self._bwd_side.add(i)
+            self._side_reads[i] = tuple(reads)
+
+    def _before_write(self, *ptrs: int) -> None:
+        """the next backward launch overwrites `ptrs`: order it behind their side-branch readers"""
+        if self.wgrad_side:
+            self.bwd_ops.append(("wait_side", tuple(ptrs), "wait_side"))
+
     def _split_k(self, m: int, n: int, k_rows: int, ntaps: int = 1) -> int:
         tiles = ((m + 127) // 128) * ((n + 255) // 256) * ntaps
         kb = (k_rows + 63) // 64
@@ -162,13 +182,16 @@ class TrainPlan(Plan):
         gW = self.G(lin.weight) if gW is None else gW
         gW_ld = k_in if gW_ld is None else gW_ld
         fk = k_in if flops_k is None else flops_k
+        n0 = len(self.bwd_ops)
         self._bgemm(a=dz16, a_rows=rows, lda=lddz, a_mn=True, b=x16, b_rows=rows, ldb=ldx, b_mn=True, m=n_out, n=k_in,
                     kc=rows, split_k=self._split_k(n_out, k_in, rows), alpha_ptr=br["w_alpha"], out_f32=gW,
                     ld_o32=gW_ld, row_map=gW_row_map, flops=2.0 * rows * n_out * fk)
+        self._side_from(n0, dz16)
         if (lin.bias is not None or bias_to is not None) and not bias_done:
             dst = bias_to if bias_to is not None else self.G(lin.bias)
             self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst, None)
         if want_dgrad:
+            self._before_write(dx16)
             self._bgemm(a=dz16, a_rows=rows, lda=lddz, b=w16, b_rows=n_out, ldb=ldw, b_mn=True, m=rows, n=k_in, kc=n_out,
                         alpha_ptr=dx_alpha if dx_alpha is not None else br["inv_s"], act=dx_act, aux=dx_aux,
                         ld_aux=ld_aux, out_f16=dx16, ld_o16=lddx, flops=2.0 * rows * n_out * fk,

@@ -232,10 +232,12 @@ def _conv_wgrad(self, *, dz, lddz, x, ldx, x_rows, rows, cout, cin, shifts, conv
     nt = len(shifts)
     scr = ("scr", self._scratch(name + ".dWtaps", nt * cout * cin))
     sk = self._split_k(cout, cin, rows, nt)
+    n0 = len(self.bwd_ops)
     self._bgemm(a=dz, a_rows=rows, lda=lddz, a_mn=True, b=x, b_rows=x_rows, ldb=ldx, b_mn=True, b_taps=list(shifts), m=cout,
                 n=cin, kc=rows, split_k=sk, alpha_ptr=("scal", 1), out_f32=scr, ld_o32=nt * cin,
                 flops=2.0 * rows * cout * cin * nt)
     self._op(self.bwd_ops, "fvit_unpack_conv_grad", scr, nt * cin, self.G(conv_weight), cout, cin)
+    self._side_from(n0, dz)   # (its own zeroed scratch slice in, a parameter gradient out: a leaf pair)
 
 
 def _emit_downsample_bwd(self, ds: dict, src: dict, dst: dict) -> None:
@@ -269,6 +271,7 @@ def _emit_conv_blocks_bwd(self, lv: dict) -> None:
     for sv in reversed(lv["blocks_sv"]):
         blk, bnA, bnB = sv["blk"], sv["bnA"], sv["bnB"]
         # x_out = x_in + BN2(conv2(h)); h = GELU(BN1(conv1(x_in)))
+        self._before_write(lv["dzB"].data_ptr())
         self._op(ops, "fvit_bn_bwd", g, 0, Cc, pix, sv["rawB"].data_ptr(), ld, pix, npix, Cc, bnB["mu"].data_ptr(),
                  bnB["rs"].data_ptr(), blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr(), L.ACT_NONE, None,
                  bnB["s12"][0].data_ptr(), bnB["s12"][1].data_ptr(), inv, lv["dzB"].data_ptr(), ld, pix,
@@ -283,6 +286,7 @@ def _emit_conv_blocks_bwd(self, lv: dict) -> None:
                     m=rows, n=Cc, kc=Cc, taps=lv["taps"], act=L.ACT_GELU_BWD, aux=sv["rawA"].data_ptr(), ld_aux=ld,
                     aux_scale=bnA["sc"].data_ptr(), aux_shift=bnA["sh"].data_ptr(),
                     row_map=interior, out_f16=lv["dyA"].data_ptr(), ld_o16=ld, flops=2.0 * npix * Cc * Cc * 9)
+        self._before_write(lv["dzA"].data_ptr())
         self._op(ops, "fvit_bn_bwd", lv["dyA"].data_ptr(), 1, ld, pix, sv["rawA"].data_ptr(), ld, pix, npix, Cc,
                  bnA["mu"].data_ptr(), bnA["rs"].data_ptr(), blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr(), L.ACT_NONE,
                  None, bnA["s12"][0].data_ptr(), bnA["s12"][1].data_ptr(), inv, lv["dzA"].data_ptr(), ld, pix,

@@ -412,15 +412,28 @@ def _emit_head_bwd(self, feat: dict) -> None:
 
 
 def _emit_attn_core_bwd(self, at: dict, dao, dqkv, groups: int, S: int) -> None:
-    """backward of the attention core: the tcgen05 tile kernel (S <= 64), the tcgen05 key-loop kernel (128 < S <= 256,
-    needs the forward's output and log-sum-exp) or the generic SIMT kernel"""
+    """backward of the attention core: the tcgen05 tile kernel (S <= 64), the tcgen05 key-loop kernels (S > 128, need
+    the forward's output and log-sum-exp: all of dQ in TMEM for S <= 256, per-pair partial dQ reduced into an fp32
+    scratch matrix beyond -- the 24 x 24 / 32 x 32 / 48 x 48 windows of the 21k models) or the generic SIMT kernel"""
     attn = at["attn"]
     h, hd, hdp, Cp = attn.num_heads, at["hd"], at["hdp"], at["Cp"]
     ops = self.bwd_ops
+    self._before_write(dqkv.data_ptr())
     if at.get("kind") == "loop" and S <= 256:
         self._op(ops, "fvit_attn_loop_bwd", at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, at["ao"].data_ptr(), Cp,
                  at["lse"].data_ptr(), groups, S, h, hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp,
                  at["bias"]["dbias"])
+    elif at.get("kind") == "loop":
+        # one scratch matrix per plan, sized for the largest attention of the model (the blocks' backward passes run
+        # one after the other on the main stream; the kernel leaves nothing in it)
+        need = groups * S * Cp
+        scr = getattr(self, "_dq_scratch", None)
+        if scr is None or scr.numel() < need:
+            scr = self.bufs.new(f"grad.attn_dq32.{need}", (need,), torch.float32)   # (a smaller one stays alive: its
+            self._dq_scratch = scr                                                  # launches keep their pointer)
+        self._op(ops, "fvit_attn_loop_bwd_long", at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, at["ao"].data_ptr(), Cp,
+                 at["lse"].data_ptr(), groups, S, h, hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp,
+                 at["bias"]["dbias"], scr.data_ptr(), Cp)
     else:
         self._op(ops, _attn_bwd_entry(S, hdp, at["use_tc"]), at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, groups, S, h, hd,
                  hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp, at["bias"]["dbias"])
@@ -467,6 +480,7 @@ def _mlp_bwd(self, tl: dict, ms: dict, gamma, g_ptr: int, rows: int, ln: nn.Laye
     br = self._branch(gamma)
     dz, dp, dy = tl["dz"], tl["dp"], tl["dy"]
     fused = Cc % 8 == 0 and mlp.fc2.bias is not None
+    self._before_write(dz.data_ptr())
     if fused:   # operand cast + fc2 bias gradient + layer-scale gradient in one pass over g
         has_g = br["gamma"] is not None
         self._op(ops, "fvit_branch_grad", g_ptr, Cc, rows, Cc, P(br["gamma"]), br["s"], ms["rs"], dz.data_ptr(), Cc,
@@ -502,6 +516,7 @@ def _attn_bwd(self, tl: dict, at: dict, gamma, g_ptr: int, ln: nn.LayerNorm, xh,
     dz, dy, dao, dqkv = tl["dz"], tl["dy"], tl["dao"], tl["dqkv"]
     padded = hdp != hd
     fused = Cc % 8 == 0 and attn.proj.bias is not None
+    self._before_write(dz.data_ptr())
     if fused:   # operand cast + proj bias gradient + layer-scale gradient in one pass over g
         has_g = br["gamma"] is not None
         self._op(ops, "fvit_branch_grad", g_ptr, Cc, rows, Cc, P(br["gamma"]), br["s"], at["rs"], dz.data_ptr(), Cc,
@@ -612,6 +627,7 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
     dz, dy, dao, dqkv = tl["dz"], tl["dy"], tl["dao"], tl["dqkv"]
     padded = hdp != hd
     fused = Cc % 8 == 0 and attn.proj.bias is not None
+    self._before_write(dz.data_ptr())
     if fused:
         has_g = br["gamma"] is not None
         self._op(ops, "fvit_branch_grad", gc_ptr, Cc, rows_c, Cc, P(br["gamma"]), br["s"], at["rs"], dz.data_ptr(), Cc,

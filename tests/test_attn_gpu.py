@@ -176,6 +176,57 @@ def test_attn_loop_backward_matches_autograd(S, heads, hd, groups):
     assert err < 4e-3, ("dbias", err)
 
 
+@pytest.mark.parametrize("S,heads,hd,groups", [(576, 4, 24, 3), (260, 2, 32, 5), (384, 3, 49, 2), (1024, 2, 64, 2),
+                                               (148, 8, 32, 9), (576, 16, 49, 150), (2304, 1, 32, 1)])
+def test_attn_loop_long_backward_matches_autograd(S, heads, hd, groups):
+    """fvit_attn_loop_bwd_long (any number of 128-row tiles: the 21k models' 576 / 1024 / 2304-token windows): dq, dk,
+    dv and dbias vs torch autograd in fp32. dq goes through the fp32 scratch matrix (NaN-filled here: the kernel must
+    not depend on its contents)."""
+    from fastervit_b200 import lib
+    lib.load()
+    hdp = 32 if hd <= 32 else 64
+    g = torch.Generator(device="cuda").manual_seed(S * 19 + heads + hd)
+    qkv = torch.zeros(groups * S, 3, heads, hdp, device="cuda")
+    qkv[..., :hd] = torch.randn(groups * S, 3, heads, hd, device="cuda", generator=g)
+    qkv16 = qkv.reshape(groups * S, 3 * heads * hdp).half()
+    bias = (torch.randn(heads, S, S, device="cuda", generator=g) * 2 + 4).requires_grad_(True)
+    do = torch.zeros(groups * S, heads, hdp, device="cuda")
+    do[..., :hd] = torch.randn(groups * S, heads, hd, device="cuda", generator=g)
+    do16 = do.reshape(groups * S, heads * hdp).half()
+    scale = hd ** -0.5
+    ref = torch.zeros(groups, S, 3, heads, hdp, device="cuda")
+    dbias_ref = torch.zeros(heads, S, S, device="cuda")
+    step = max(1, min(groups, (1 << 27) // (heads * S * S)))   # windows per autograd chunk (bounded score memory)
+    for g0 in range(0, groups, step):
+        x = qkv16.float().view(groups, S, 3, heads, hdp)[g0:g0 + step, ..., :hd].clone().requires_grad_(True)
+        q, k, v = x.permute(2, 0, 3, 1, 4)
+        p = ((q @ k.transpose(-2, -1)) * scale + bias[None]).softmax(-1)
+        o = (p @ v).permute(0, 2, 1, 3)
+        o.backward(do16.float().view(groups, S, heads, hdp)[g0:g0 + step, ..., :hd])
+        ref[g0:g0 + step, ..., :hd] = x.grad
+        dbias_ref += bias.grad
+        bias.grad = None
+    ref = ref.reshape(groups * S, 3 * heads * hdp)
+    out16 = torch.zeros(groups * S, heads * hdp, device="cuda", dtype=torch.half)
+    lse = torch.zeros(groups * S, heads, device="cuda")
+    lib.call("fvit_attn_loop_fwd", qkv16.data_ptr(), qkv16.stride(0), groups, S, heads, hdp, bias.data_ptr(), scale,
+             out16.data_ptr(), out16.stride(0), lse.data_ptr())
+    dqkv = torch.full((groups * S, 3 * heads * hdp), float("nan"), device="cuda", dtype=torch.half)
+    dbias = torch.zeros(heads, S, S, device="cuda")
+    scratch = torch.full((groups * S, heads * hdp), float("nan"), device="cuda")
+    lib.call("fvit_attn_loop_bwd_long", qkv16.data_ptr(), qkv16.stride(0), do16.data_ptr(), do16.stride(0),
+             out16.data_ptr(), out16.stride(0), lse.data_ptr(), groups, S, heads, hdp, bias.data_ptr(), scale,
+             dqkv.data_ptr(), dqkv.stride(0), dbias.data_ptr(), scratch.data_ptr(), scratch.stride(0))
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    for w, nm in enumerate("qkv"):
+        sl = slice(w * heads * hdp, (w + 1) * heads * hdp)
+        err = ((dqkv[:, sl].float() - ref[:, sl]).abs().max() / ref[:, sl].abs().max()).item()
+        assert err < 4e-3, (nm, err)
+    err = ((dbias - dbias_ref).abs().max() / dbias_ref.abs().max()).item()
+    assert err < 4e-3, ("dbias", err)
+
+
 @pytest.mark.parametrize("S,heads,hd,groups,C", [(53, 8, 32, 37, 256), (49, 16, 32, 20, 512), (16, 8, 32, 11, 256),
                                                  (53, 16, 49, 9, 784), (49, 32, 49, 6, 1568), (60, 8, 32, 5, 256),
                                                  (36, 16, 32, 31, 512), (128, 2, 64, 3, 128), (64, 4, 24, 6, 96),
