@@ -785,8 +785,11 @@ struct AttnLoopBwdLongParams {
   long long lddq32;
 };
 
+constexpr int ALL_SOFTMAX_WARPS = 8;                      // two per TMEM lane quarter (64 score columns each)
+constexpr int ALL_THREADS = (2 + ALL_SOFTMAX_WARPS) * 32;  // + TMA producer, MMA issuer
+
 template <int HDP>
-__global__ void __launch_bounds__(AL_THREADS, 1)
+__global__ void __launch_bounds__(ALL_THREADS, 1)
     attn_loop_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                               const __grid_constant__ AttnLoopBwdLongParams pl) {
   const AttnLoopBwdParams& p = pl.b;
@@ -825,9 +828,9 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
       mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
       mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(sdp_full, 1), mbar_init(sdp_empty, 4);
-    mbar_init(pds_full, 4), mbar_init(pds_empty, 1);
-    mbar_init(dkv_full, 1), mbar_init(dkv_empty, 4);
+    mbar_init(sdp_full, 1), mbar_init(sdp_empty, ALL_SOFTMAX_WARPS);
+    mbar_init(pds_full, ALL_SOFTMAX_WARPS), mbar_init(pds_empty, 1);
+    mbar_init(dkv_full, 1), mbar_init(dkv_empty, ALL_SOFTMAX_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -917,44 +920,52 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
       }
     }
   } else {
-    const int quad = warp & 3;
+    // eight softmax warps: TMEM lane quarter (warp & 3) = query rows 32 * quad .. + 31 of the tile, `half` = which 64 of
+    // the 128 key columns of a pair (and which half of the head columns in the epilogues). Two warps per scheduler
+    // hide each other's tcgen05.ld / bias latencies; the bias values of a pair are requested before the wait for its
+    // score MMAs (the addresses do not depend on them).
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     uint8_t* sP = smem + P_OFF;
     uint8_t* sDS = smem + DS_OFF;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     uint32_t pair = 0, jcnt = 0;
     const int Cp = p.heads * HDP;
+    const int cbeg = half * 64;              // score columns [cbeg, cbeg + 64) of every pair
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int grp = w % p.groups, head = w / p.groups;
       const long long row0 = (long long)grp * S;
-      // per query row this thread owns (row r of every tile): delta = sum_c dO * O and the forward's log-sum-exp
-      for (int i = 0; i < nt; ++i) {
-        const int q = i * 128 + r;
-        float acc = 0.f, l = 0.f;
-        if (q < S) {
-          const uint4* a = reinterpret_cast<const uint4*>(p.dout + (row0 + q) * p.lddo + head * HDP);
-          const uint4* b = reinterpret_cast<const uint4*>(p.out + (row0 + q) * p.ldo + head * HDP);
+      // per query row: delta = sum_c dO * O and the forward's log-sum-exp (half 0 computes, both halves read)
+      if (half == 0) {
+        for (int i = 0; i < nt; ++i) {
+          const int q = i * 128 + r;
+          float acc = 0.f, l = 0.f;
+          if (q < S) {
+            const uint4* a = reinterpret_cast<const uint4*>(p.dout + (row0 + q) * p.lddo + head * HDP);
+            const uint4* b = reinterpret_cast<const uint4*>(p.out + (row0 + q) * p.ldo + head * HDP);
 #pragma unroll
-          for (int v = 0; v < HDP / 8; ++v) {
-            const uint4 x = __ldg(a + v), y = __ldg(b + v);
-            const __half2* hx = reinterpret_cast<const __half2*>(&x);
-            const __half2* hy = reinterpret_cast<const __half2*>(&y);
+            for (int v = 0; v < HDP / 8; ++v) {
+              const uint4 x = __ldg(a + v), y = __ldg(b + v);
+              const __half2* hx = reinterpret_cast<const __half2*>(&x);
+              const __half2* hy = reinterpret_cast<const __half2*>(&y);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 fx = __half22float2(hx[e]), fy = __half22float2(hy[e]);
-              acc = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, acc));
+              for (int e = 0; e < 4; ++e) {
+                const float2 fx = __half22float2(hx[e]), fy = __half22float2(hy[e]);
+                acc = fmaf(fx.x, fy.x, fmaf(fx.y, fy.y, acc));
+              }
             }
+            l = p.lse[(row0 + q) * p.heads + head];
           }
-          l = p.lse[(row0 + q) * p.heads + head];
+          s_delta[q] = acc, s_lse[q] = l;
         }
-        s_delta[q] = acc, s_lse[q] = l;   // (read back by this thread only)
       }
-      // partial dQ of the pair (j, i): TMEM -> * scale -> this thread's fp32 scratch row
+      asm volatile("bar.sync 1, %0;" ::"n"(ALL_SOFTMAX_WARPS * 32) : "memory");   // (the softmax warps only)
+      // partial dQ of the pair (j, i): TMEM -> * scale -> this thread's share of the fp32 scratch row
       auto flush_dq = [&](int j, int i) {
         const int q = i * 128 + r;
         float* drow = pl.dq32 + (row0 + q) * pl.lddq32 + head * HDP;
 #pragma unroll
-        for (int c0 = 0; c0 < HDP; c0 += 32) {
+        for (int c0 = half * 32; c0 < HDP; c0 += 64) {
           uint32_t raw[32];
           tmem_ld32(tDQ + lane_off + c0, raw);
           tmem_ld_wait();
@@ -979,25 +990,32 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
           const int q = i * 128 + r;
           const bool row_ok = q < S;
           const float my_lse = s_lse[q], my_delta = s_delta[q];
+          const float* brow = (p.bias && row_ok) ? p.bias + ((long long)head * S + q) * S + j * 128 : nullptr;
+          float* dbrow = (p.dbias && row_ok) ? p.dbias + ((long long)head * S + q) * S + j * 128 : nullptr;
+          // this pair's 64 bias values, in flight while the score MMAs run
+          float4 bq[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int c = cbeg + u * 4;
+            bq[u] = (brow && c < ncols) ? __ldg(reinterpret_cast<const float4*>(brow + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           mbar_wait(sdp_full, pair & 1);
           mbar_wait(pds_empty, (pair & 1) ^ 1);  // the previous pair's gradient MMAs are complete: P / dS free, dQ final
           tc_fence_after();
           if (i > 0) flush_dq(j, i - 1);
-          const float* brow = (p.bias && row_ok) ? p.bias + ((long long)head * S + q) * S + j * 128 : nullptr;
-          float* dbrow = (p.dbias && row_ok) ? p.dbias + ((long long)head * S + q) * S + j * 128 : nullptr;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t pkp[16], pkd[16];
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 16) {
+            const int c0 = cbeg + cc;
+            uint32_t pkp[8], pkd[8];
             if (c0 < ncols) {
-              uint32_t rs[32], rd[32];
-              tmem_ld32(tS + lane_off + c0, rs);
-              tmem_ld32(tDP + lane_off + c0, rd);
+              uint32_t rs[16], rd[16];
+              tmem_ld16(tS + lane_off + c0, rs);
+              tmem_ld16(tDP + lane_off + c0, rd);
               tmem_ld_wait();
 #pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
+              for (int q4 = 0; q4 < 4; ++q4) {
                 const int c = c0 + q4 * 4;
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (brow && c < ncols) b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
+                const float4 b4 = bq[cc / 4 + q4];
                 const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                 float pv[4], ds[4];
 #pragma unroll
@@ -1018,10 +1036,10 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
               }
             } else {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) pkp[e] = 0u, pkd[e] = 0u;
+              for (int e = 0; e < 8; ++e) pkp[e] = 0u, pkd[e] = 0u;
             }
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < 2; ++qq) {
               const int c = c0 + qq * 8;
               const uint32_t off = (c >> 6) * (AL_ROWS * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4);
               *reinterpret_cast<uint4*>(sP + off) = make_uint4(pkp[4 * qq], pkp[4 * qq + 1], pkp[4 * qq + 2], pkp[4 * qq + 3]);
@@ -1049,7 +1067,7 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
             const uint32_t tsrc = (which == 1 ? tDK : tDV) + lane_off;
             const float mul = which == 1 ? p.scale : 1.f;
 #pragma unroll
-            for (int c0 = 0; c0 < HDP; c0 += 32) {
+            for (int c0 = half * 32; c0 < HDP; c0 += 64) {
               uint32_t raw[32];
               tmem_ld32(tsrc + c0, raw);
               tmem_ld_wait();
@@ -1073,7 +1091,7 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(dkv_empty);
       }
-      // dQ rows of this (window, head): fp32 scratch (written by this thread only) -> fp16
+      // dQ rows of this (window, head): fp32 scratch (each column range written by this thread only) -> fp16
       __threadfence();
       for (int i = 0; i < nt; ++i) {
         const int q = i * 128 + r;
@@ -1081,14 +1099,17 @@ __global__ void __launch_bounds__(AL_THREADS, 1)
           const float* drow = pl.dq32 + (row0 + q) * pl.lddq32 + head * HDP;
           __half* orow = p.dqkv + (row0 + q) * p.lddq + head * HDP;
 #pragma unroll
-          for (int c = 0; c < HDP; c += 8) {
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(drow + c));
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(drow + c + 4));
-            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-            const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
-            *reinterpret_cast<uint4*>(orow + c) =
-                make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                           *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          for (int c0 = half * 32; c0 < HDP; c0 += 64) {
+#pragma unroll
+            for (int c = c0; c < c0 + 32; c += 8) {
+              const float4 a = __ldcg(reinterpret_cast<const float4*>(drow + c));
+              const float4 b = __ldcg(reinterpret_cast<const float4*>(drow + c + 4));
+              const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+              const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+              *reinterpret_cast<uint4*>(orow + c) =
+                  make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                             *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+            }
           }
         }
       }
@@ -1114,7 +1135,7 @@ static int launch_attn_loop_bwd_long(const CUtensorMap& tq, const CUtensorMap& t
   }
   const int items = p.b.groups * p.b.heads;
   const int sms = num_sms();
-  attn_loop_bwd_long_kernel<HDP><<<items < sms ? items : sms, AL_THREADS, smem, st>>>(tq, td, p);
+  attn_loop_bwd_long_kernel<HDP><<<items < sms ? items : sms, ALL_THREADS, smem, st>>>(tq, td, p);
   return post_launch("attn_loop_bwd_long_kernel");
 }
 

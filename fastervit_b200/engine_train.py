@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import lib as L
@@ -42,6 +44,7 @@ class TrainPlan(Plan):
         self.scratch_n = 0
         self._scratch_req: list[tuple[str, int]] = []
         self._bwd_side: set[int] = set()     # backward launches that run as a side branch (engine_train_levels.py)
+        self._bwd_side_wgrad: set[int] = set()    # weight-gradient launches: side branch on a single GPU only (below)
         self._side_reads: dict[int, tuple] = {}   # side launch -> shared gradient buffers it reads (WAR hazards)
         # device scalars: [0] S, [1] 1/S, [2] 1.0, then per-branch (s_b, 1/s_b, 1/(S s_b))
         self._nscal = 3
@@ -154,8 +157,17 @@ class TrainPlan(Plan):
         if not self.wgrad_side:
             return
         for i in range(first, len(self.bwd_ops)):
-            self._bwd_side.add(i)
+            self._bwd_side_wgrad.add(i)
             self._side_reads[i] = tuple(reads)
+
+    def _side_set(self, data_parallel: bool):
+        """Launches that go to the side branch. With a gradient all-reduce in flight the weight-gradient GEMMs stay on
+        the main branch: a second persistent grid would take the SMs the capped launches leave to NCCL (§7)."""
+        if not self.side_branches:
+            return None
+        if data_parallel and os.environ.get("FVIT_WGRAD_SIDE_DDP", "0") != "1":
+            return self._bwd_side
+        return self._bwd_side | self._bwd_side_wgrad
 
     def _before_write(self, *ptrs: int) -> None:
         """the next backward launch overwrites `ptrs`: order it behind their side-branch readers"""
@@ -186,10 +198,10 @@ class TrainPlan(Plan):
         self._bgemm(a=dz16, a_rows=rows, lda=lddz, a_mn=True, b=x16, b_rows=rows, ldb=ldx, b_mn=True, m=n_out, n=k_in,
                     kc=rows, split_k=self._split_k(n_out, k_in, rows), alpha_ptr=br["w_alpha"], out_f32=gW,
                     ld_o32=gW_ld, row_map=gW_row_map, flops=2.0 * rows * n_out * fk)
-        self._side_from(n0, dz16)
         if (lin.bias is not None or bias_to is not None) and not bias_done:
             dst = bias_to if bias_to is not None else self.G(lin.bias)
             self._op(self.bwd_ops, "fvit_colsum", dz16, 1, lddz, None, None, 0, rows, n_out, None, br["w_alpha"], dst, None)
+        self._side_from(n0, dz16)   # (weight gradient + bias column sums: both only read dz16)
         if want_dgrad:
             self._before_write(dx16)
             self._bgemm(a=dz16, a_rows=rows, lda=lddz, b=w16, b_rows=n_out, ldb=ldw, b_mn=True, m=rows, n=k_in, kc=n_out,
@@ -251,7 +263,7 @@ class TrainPlan(Plan):
 
             def body():
                 self._bwd_start(None)
-                self.run_ops(self.bwd_ops, None, side=self._bwd_side if self.side_branches else None)
+                self.run_ops(self.bwd_ops, None, side=self._side_set(False))
             self.run_captured("backward", body)
             return
         # data parallel: each bucket's all-reduce is issued the moment the launches that finish its gradients are
@@ -279,7 +291,7 @@ class TrainPlan(Plan):
                         self._bwd_start(None)
                     self._op_base = lo
                     try:
-                        self.run_ops(self.bwd_ops[lo:hi], None, side=self._bwd_side if self.side_branches else None)
+                        self.run_ops(self.bwd_ops[lo:hi], None, side=self._side_set(True))
                     finally:
                         self._op_base = 0
                 if hi > lo or n == 0:   # (the list ends with a bucket point: nothing to capture after it)

@@ -412,18 +412,15 @@ def _emit_head_bwd(self, feat: dict) -> None:
 
 
 def _emit_attn_core_bwd(self, at: dict, dao, dqkv, groups: int, S: int) -> None:
-    """backward of the attention core: the tcgen05 tile kernel (S <= 64), the tcgen05 key-loop kernels (S > 128, need
-    the forward's output and log-sum-exp: all of dQ in TMEM for S <= 256, per-pair partial dQ reduced into an fp32
-    scratch matrix beyond -- the 24 x 24 / 32 x 32 / 48 x 48 windows of the 21k models) or the generic SIMT kernel"""
+    """backward of the attention core: the tcgen05 tile kernel (S <= 64), the tcgen05 key-loop kernel (S > 128: needs the
+    forward's output and log-sum-exp; per-pair partial dQ reduced into an fp32 scratch matrix -- any-res S = 148, the
+    14 x 14 ... 48 x 48 windows of the 21k models) or the generic SIMT kernel. (fvit_attn_loop_bwd, the two-tile variant
+    that keeps all of dQ in TMEM, measured 25 % slower on S = 148 / 196 than the eight-softmax-warp kernel: r02t.)"""
     attn = at["attn"]
     h, hd, hdp, Cp = attn.num_heads, at["hd"], at["hdp"], at["Cp"]
     ops = self.bwd_ops
     self._before_write(dqkv.data_ptr())
-    if at.get("kind") == "loop" and S <= 256:
-        self._op(ops, "fvit_attn_loop_bwd", at["qkv"].data_ptr(), 3 * Cp, dao.data_ptr(), Cp, at["ao"].data_ptr(), Cp,
-                 at["lse"].data_ptr(), groups, S, h, hdp, at["bias"]["out"].data_ptr(), at["scale"], dqkv.data_ptr(), 3 * Cp,
-                 at["bias"]["dbias"])
-    elif at.get("kind") == "loop":
+    if at.get("kind") == "loop":
         # one scratch matrix per plan, sized for the largest attention of the model (the blocks' backward passes run
         # one after the other on the main stream; the kernel leaves nothing in it)
         need = groups * S * Cp

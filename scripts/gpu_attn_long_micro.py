@@ -47,7 +47,17 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n * 1e3
 
 
+def bwd2(b, db):   # the two-tile kernel (128 < S <= 256: every dQ tile in TMEM)
+    lib.call("fvit_attn_loop_bwd", qkv16.data_ptr(), qkv16.stride(0), do16.data_ptr(), do16.stride(0), out16.data_ptr(),
+             out16.stride(0), lse.data_ptr(), groups, S, heads, hdp, b.data_ptr() if b is not None else None, scale,
+             dqkv.data_ptr(), dqkv.stride(0), db.data_ptr() if db is not None else None)
+
+
 flops = 10.0 * groups * heads * S * S * hd
+if S <= 256:
+    fwd(bias)
+    print(f"S={S} heads={heads} hd={hd} groups={groups} two-tile kernel [bias + dbias]: bwd {timed(lambda: bwd2(bias, dbias)):.0f} us",
+          flush=True)
 for tag, b, db in (("bias + dbias", bias, dbias), ("bias, no dbias", bias, None), ("no bias, no dbias", None, None)):
     fwd(b)
     t_f = timed(lambda: fwd(b))
