@@ -161,11 +161,13 @@ class TrainPlan(Plan):
             self._side_reads[i] = tuple(reads)
 
     def _side_set(self, data_parallel: bool):
-        """Launches that go to the side branch. With a gradient all-reduce in flight the weight-gradient GEMMs stay on
-        the main branch: a second persistent grid would take the SMs the capped launches leave to NCCL (§7)."""
+        """Launches that go to the side branch. Under a gradient all-reduce the weight-gradient GEMMs stay there too: a
+        second persistent grid does compete with NCCL's CTAs for the SMs the capped launches leave free, but measured on
+        2 x B200 (profiles/r02v_ddp_n2.txt) the step is 75.1 ms with them against 76.8 ms without (73.0 ms on one GPU of
+        the same box). FVIT_WGRAD_SIDE_DDP=0 keeps them on the main branch (A/B switch)."""
         if not self.side_branches:
             return None
-        if data_parallel and os.environ.get("FVIT_WGRAD_SIDE_DDP", "0") != "1":
+        if data_parallel and os.environ.get("FVIT_WGRAD_SIDE_DDP", "1") != "1":
             return self._bwd_side
         return self._bwd_side | self._bwd_side_wgrad
 
