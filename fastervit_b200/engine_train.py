@@ -22,9 +22,11 @@ import torch
 
 from . import lib as L
 from .engine import Plan, _ru
+from .engine_train_conv import ConvPartEmitters
+from .engine_train_levels import TokenLevelEmitters
 
 
-class TrainPlan(Plan):
+class TrainPlan(Plan, ConvPartEmitters, TokenLevelEmitters):
     def __init__(self, model, B: int, H: int, W: int, device):
         self.bwd_ops: list[tuple] = []
         self.fwd_zero: list[torch.Tensor] = []   # accumulators zeroed before every forward (BN statistics)
@@ -221,7 +223,7 @@ class TrainPlan(Plan):
         self._build_backward()
         self._finish_train()
 
-    # forward / backward emitters are attached below from engine_train_levels.py / engine_train_conv.py
+    # forward / backward emitters: the ConvPartEmitters / TokenLevelEmitters mixins (engine_train_conv.py, engine_train_levels.py)
 
     # ------------------------------------------------------------------------------ execution
     def run_forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -466,16 +468,3 @@ class _FasterViTFunction(torch.autograd.Function):
                 "next forward, or use different plans / model copies for multi-view losses)")
         plan.run_backward(dlogits.contiguous().float())
         return (None, None, *plan.grad_views())
-
-
-def _attach() -> None:
-    import types
-    from . import engine_train_conv as ec
-    from . import engine_train_levels as el
-    for mod in (el, ec):
-        for name, fn in vars(mod).items():
-            if isinstance(fn, types.FunctionType) and name.startswith("_") and fn.__module__ == mod.__name__:
-                setattr(TrainPlan, name, fn)
-
-
-_attach()

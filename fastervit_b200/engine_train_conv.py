@@ -346,3 +346,18 @@ def _emit_conv_part_bwd(self) -> None:
     self._bgemm(a=dz1.data_ptr(), a_rows=npix1, lda=ld_in, a_mn=True, b=st["col16"].data_ptr(), b_rows=npix1, ldb=self.STEM_LD,
                 b_mn=True, m=in_dim, n=27, kc=npix1, split_k=self._split_k(in_dim, 27, npix1), alpha_ptr=inv,
                 out_f32=self.G(pe[0].weight), ld_o32=27, flops=2.0 * npix1 * in_dim * 27)
+
+
+class ConvPartEmitters:
+    """TrainPlan mixin: launch-list emitters of PatchEmbed, the conv levels and the Downsamples (the functions above take the
+    plan as `self`)."""
+    _bn_train = _bn_train
+    _bn_finalize = _bn_finalize
+    _emit_conv_part_train = _emit_conv_part_train
+    _conv_level_train_buffers = _conv_level_train_buffers
+    _emit_conv_blocks_train = _emit_conv_blocks_train
+    _emit_downsample_train = _emit_downsample_train
+    _conv_wgrad = _conv_wgrad
+    _emit_downsample_bwd = _emit_downsample_bwd
+    _emit_conv_blocks_bwd = _emit_conv_blocks_bwd
+    _emit_conv_part_bwd = _emit_conv_part_bwd

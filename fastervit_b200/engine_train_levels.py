@@ -667,3 +667,28 @@ def _attn_bwd_carrier(self, tl: dict, sv: dict, blk, gc_ptr: int, g_ptr: int) ->
         self._op(ops, "fvit_group_sum", gc_ptr, Cc, B, n_ct, 0, Cc, ("scal", 1), sv["hat_pe"]["dout"])
         _posemb_bwd(self, sv["hat_pe"])
     self._op(ops, "fvit_scatter_add_rows", gc_ptr, Cc, g_ptr, Cc, tl["ct_gather"].data_ptr(), rows_c, Cc)
+
+
+class TokenLevelEmitters:
+    """TrainPlan mixin: launch-list emitters of the transformer levels, the head and the build drivers (the functions
+    above take the plan as `self`; `_attn_bwd_entry` is a plain helper)."""
+    _drop_buf = _drop_buf
+    _gen_drop_masks = _gen_drop_masks
+    _build_forward = _build_forward
+    _posemb_train = _posemb_train
+    _bias_train = _bias_train
+    _attn_fwd_train = _attn_fwd_train
+    _gemm_train_branch = _gemm_train_branch
+    _emit_token_level_train = _emit_token_level_train
+    _mlp_fwd_train = _mlp_fwd_train
+    _emit_head_train = _emit_head_train
+    _build_backward = _build_backward
+    _emit_head_bwd = _emit_head_bwd
+    _emit_attn_core_bwd = _emit_attn_core_bwd
+    _posemb_bwd = _posemb_bwd
+    _bias_bwd = _bias_bwd
+    _mlp_bwd = _mlp_bwd
+    _attn_bwd = _attn_bwd
+    _unpad_row_map = _unpad_row_map
+    _emit_token_level_bwd = _emit_token_level_bwd
+    _attn_bwd_carrier = _attn_bwd_carrier
