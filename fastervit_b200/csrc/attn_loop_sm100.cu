@@ -382,7 +382,9 @@ using namespace fvit;
 extern "C" int fvit_attn_loop_fwd(const void* qkv, int64_t ldq, int32_t groups, int32_t S, int32_t heads, int32_t hdp,
                                   const float* bias, float scale, void* out, int64_t ldo, float* lse, void* stream) {
   FVIT_CHECK(qkv && out && groups > 0 && heads > 0, "fvit_attn_loop_fwd: bad arguments");
-  FVIT_CHECK(S > 128, "fvit_attn_loop_fwd: S=%d (windows of up to 128 tokens use fvit_attn_tc_fwd)", S);
+  // (any S: one tile is the case nqt = nkt = 1. Inference plans give windows of up to 128 tokens to fvit_attn_tc_fwd / the fused
+  // kernel, which pack several windows into a tile; training plans come here from 65 tokens on for the log-sum-exp rows)
+  FVIT_CHECK(S > 0, "fvit_attn_loop_fwd: S=%d", S);
   FVIT_CHECK(hdp == 32 || hdp == 64, "fvit_attn_loop_fwd: padded head dim %d unsupported (32 or 64)", hdp);
   FVIT_CHECK(ldq % 8 == 0 && ldo % 8 == 0 && ldq >= 3 * heads * hdp && ldo >= heads * hdp,
              "fvit_attn_loop_fwd: bad leading dimensions");
@@ -1179,7 +1181,7 @@ extern "C" int fvit_attn_loop_bwd_long(const void* qkv, int64_t ldq, const void*
                                        float* dq_scratch, int64_t ld_scratch, void* stream) {
   using namespace fvit;
   FVIT_CHECK(qkv && dout && out && lse && dqkv && dq_scratch && groups > 0 && heads > 0, "fvit_attn_loop_bwd_long: bad arguments");
-  FVIT_CHECK(S > 128, "fvit_attn_loop_bwd_long: S=%d unsupported (windows of more than one 128-row tile)", S);
+  FVIT_CHECK(S > 0, "fvit_attn_loop_bwd_long: S=%d", S);
   FVIT_CHECK(S % 4 == 0, "fvit_attn_loop_bwd_long: S=%d must be a multiple of 4 (16-byte bias / dbias accesses)", S);
   FVIT_CHECK(hdp == 32 || hdp == 64, "fvit_attn_loop_bwd_long: padded head dim %d unsupported", hdp);
   FVIT_CHECK(ldq % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 && ld_scratch % 4 == 0 &&

@@ -110,6 +110,11 @@ def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, 
     Cc, h, hd = attn.qkv.in_features, attn.num_heads, attn.head_dim
     hdp = self._head_pad(hd)
     kind = self._attn_kind(S, hdp)
+    if kind == "tile" and S > 64 and S % 4 == 0:
+        # one window per 128-row tile either way; the key-loop forward also writes the log-sum-exp rows its tensor-core
+        # backward needs (fvit_attn_tc_bwd stops at 64-row window slots: without this, 65..128-token windows -- any-res
+        # models with 8 x 8 ... 11 x 11 windows -- would train through the SIMT backward)
+        kind = "loop"
     use_tc = kind != "simt"
     if not use_tc:
         hdp = hd

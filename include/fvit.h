@@ -337,7 +337,7 @@ int fvit_attn_tc_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t ldd
 int fvit_attn_loop_bwd(const void* qkv, int64_t ldq, const void* dout, int64_t lddo, const void* out, int64_t ldo,
                        const float* lse, int32_t groups, int32_t S, int32_t heads, int32_t hdp, const float* bias,
                        float scale, void* dqkv, int64_t lddq, float* dbias, void* stream);
-/* The same backward for any S > 128 (S % 4 == 0): the 24 x 24 / 32 x 32 / 48 x 48 windows of the 21k models
+/* The same backward for any S (S % 4 == 0; the training plans use it from 65 tokens on): the 24 x 24 / 32 x 32 / 48 x 48 windows of the 21k models
  * (fv.py:1253-1418, WindowAttention.forward fv.py:557-568 differentiated). Key tiles outside, query tiles inside; dV_j /
  * dK_j accumulate in TMEM over the query loop, the per-pair partial dQ_i = dS K_j is added to the row of the fp32
  * scratch matrix dq_scratch[groups * S, ld_scratch >= heads * hdp] its owning thread keeps (16-byte stores for the

@@ -41,6 +41,13 @@ CASES = {
         dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 9, 5],
         ct_size=2, mlp_ratio=4, resolution=[144, 288], hat=[False, False, True, False],
         do_propagation=False, any_res=True)),
+    # S = 64 + 4 = 68: one 128-row tile, more than the 64-row window slots of the tile backward -- training takes the
+    # key-loop kernels with a single key / query tile (window 8 at level 2, 4 at level 3; level-2 map 16 x 24)
+    "tiny_ar68": ("faster_vit_0_any_res", dict(resolution=[256, 384], window_size=[7, 7, 8, 4], ct_size=2, dim=16,
+                                               in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
+        dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 8, 4],
+        ct_size=2, mlp_ratio=4, resolution=[256, 384], hat=[False, False, True, False],
+        do_propagation=False, any_res=True)),
     "tiny_ar148": ("faster_vit_0_any_res", dict(resolution=[384, 576], window_size=[7, 7, 12, 6], ct_size=2, dim=16,
                                                 in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8]), dict(
         dim=16, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 12, 6],

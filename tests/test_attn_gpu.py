@@ -44,11 +44,12 @@ def test_attn_tc_matches_torch(S, heads, hd, groups, with_bias):
 
 @pytest.mark.parametrize("S,heads,hd,groups", [(148, 8, 32, 30), (148, 8, 32, 480), (196, 16, 49, 8), (144, 4, 24, 5),
                                                (256, 2, 64, 3), (576, 4, 49, 2), (1024, 2, 49, 1), (2304, 1, 49, 1),
-                                               (132, 3, 32, 7)])
+                                               (132, 3, 32, 7), (68, 4, 16, 12), (104, 8, 32, 300), (128, 2, 64, 5)])
 @pytest.mark.parametrize("with_bias", [True, False])
 def test_attn_loop_matches_torch(S, heads, hd, groups, with_bias):
-    """Key-loop tensor-core attention (S > 128): the any-res level-2 geometry (S = 148, BASELINE config 4) and the
-    21k windows, against fp32 torch on the same fp16 operands; also the saved log-sum-exp vector."""
+    """Key-loop tensor-core attention: the any-res level-2 geometry (S = 148, BASELINE config 4), the 21k windows and
+    the single-tile case training plans use for 65..128-token windows, against fp32 torch on the same fp16 operands;
+    also the saved log-sum-exp vector."""
     from fastervit_b200 import lib
     lib.load()
     hdp = 32 if hd <= 32 else 64
@@ -177,7 +178,8 @@ def test_attn_loop_backward_matches_autograd(S, heads, hd, groups):
 
 
 @pytest.mark.parametrize("S,heads,hd,groups", [(576, 4, 24, 3), (260, 2, 32, 5), (384, 3, 49, 2), (1024, 2, 64, 2),
-                                               (148, 8, 32, 9), (576, 16, 49, 150), (2304, 1, 32, 1)])
+                                               (148, 8, 32, 9), (576, 16, 49, 150), (2304, 1, 32, 1),
+                                               (68, 4, 16, 12), (104, 8, 32, 7), (128, 2, 64, 5), (100, 3, 49, 200)])
 def test_attn_loop_long_backward_matches_autograd(S, heads, hd, groups):
     """fvit_attn_loop_bwd_long (any number of 128-row tiles: the 21k models' 576 / 1024 / 2304-token windows): dq, dk,
     dv and dbias vs torch autograd in fp32. dq goes through the fp32 scratch matrix (NaN-filled here: the kernel must
