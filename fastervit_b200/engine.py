@@ -509,7 +509,7 @@ class Plan:
                 qbp = self.bufs.new(nm + ".qkv.bias_pad", (3 * Cp,), torch.float32)
                 self._op(self.prep_ops, "fvit_vec_headpad_f32", qb.data_ptr(), qbp.data_ptr(), 3 * Cp, hd, hdp)
                 qb_ptr = qbp.data_ptr()
-        scale = float(hd ** -0.5)
+        scale = float(getattr(attn, "scale", hd ** -0.5))   # qk_scale or head_dim ** -0.5 (fv.py:544)
         fused = (self._attn_kind(S, hdp) == "tile" and self.fused_hat != "0"
                  and (self.fused_hat == "1" or hdp == 64))
         if fused:

@@ -136,7 +136,7 @@ def _attn_fwd_train(self, nm: str, attn, gamma, rows: int, groups: int, S: int, 
     self._gemm(a=y16.data_ptr(), a_rows=rows, lda=Cc, b=wq.data_ptr(), ldb=ldq, m=rows, n=3 * Cp, kc=Cc,
                col_shift=qb_ptr, out_f16=qkv.data_ptr(), ld_o16=3 * Cp)
     self.op_flops[len(self.ops) - 1] = 2.0 * rows * 3 * Cc * Cc
-    scale = float(hd ** -0.5)
+    scale = float(getattr(attn, "scale", hd ** -0.5))   # qk_scale or head_dim ** -0.5 (fv.py:544)
     lse = None
     if kind == "loop":
         lse = self.bufs.new(nm + ".lse", (rows, h), torch.float32)   # log-sum-exp rows, read by the backward kernel

@@ -77,9 +77,10 @@ class RelPosBias(_Holder):
 class WindowAttention(_Holder):
     """fv.py:515-568: qkv / proj linears + relative position bias."""
 
-    def __init__(self, dim: int, num_heads: int, qkv_bias: bool, resolution: int, seq_length: int):
+    def __init__(self, dim: int, num_heads: int, qkv_bias: bool, resolution: int, seq_length: int, qk_scale=None):
         super().__init__()
         self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.scale = qk_scale or self.head_dim ** -0.5     # fv.py:544
         self.resolution = resolution
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.proj = nn.Linear(dim, dim)
@@ -97,7 +98,7 @@ class HAT(_Holder):
     """Hierarchical attention block (fv.py:571-701; fvar.py:572-707)."""
 
     def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, sr_ratio: Sequence[int], window_size, last,
-                 layer_scale, ct_size, do_propagation, any_res: bool):
+                 layer_scale, ct_size, do_propagation, any_res: bool, qk_scale=None):
         super().__init__()
         self.window_size, self.ct_size, self.last = window_size, ct_size, last
         self.sr_ratio = list(sr_ratio)
@@ -113,14 +114,14 @@ class HAT(_Holder):
 
         self.pos_embed = TokenPosEmbed(dim, window_size ** 2)
         self.norm1 = nn.LayerNorm(dim)
-        self.attn = WindowAttention(dim, num_heads, qkv_bias, window_size, window_size ** 2 + n_ct_win)
+        self.attn = WindowAttention(dim, num_heads, qkv_bias, window_size, window_size ** 2 + n_ct_win, qk_scale)
         self.norm2 = nn.LayerNorm(dim)
         self.mlp = Mlp(dim, hidden)
         self.gamma3, self.gamma4 = ls(), ls()
         if self.has_carriers:
             self.hat_norm1 = nn.LayerNorm(dim)
             self.hat_norm2 = nn.LayerNorm(dim)
-            self.hat_attn = WindowAttention(dim, num_heads, qkv_bias, int(n_ct ** 0.5), n_ct)
+            self.hat_attn = WindowAttention(dim, num_heads, qkv_bias, int(n_ct ** 0.5), n_ct, qk_scale)
             self.hat_mlp = Mlp(dim, hidden)
             # the any-res variant only has a carrier positional embedding on square grids (fvar.py:658)
             if (not any_res) or sr_ratio[0] == sr_ratio[1]:
@@ -182,7 +183,7 @@ class FasterViTLayer(_Holder):
 
     def __init__(self, dim, depth, input_resolution: Sequence[int], num_heads, window_size, ct_size, conv,
                  downsample, mlp_ratio, qkv_bias, layer_scale, layer_scale_conv, only_local,
-                 do_propagation, any_res: bool):
+                 do_propagation, any_res: bool, qk_scale=None):
         super().__init__()
         self.conv, self.window_size, self.dim = conv, window_size, dim
         res = list(input_resolution)
@@ -196,7 +197,7 @@ class FasterViTLayer(_Holder):
             self.sr_ratio = [1, 1] if only_local else [res[0] // window_size, res[1] // window_size]
             self.blocks = nn.ModuleList([
                 HAT(dim, num_heads, mlp_ratio, qkv_bias, self.sr_ratio, window_size, i == depth - 1,
-                    layer_scale, ct_size, do_propagation, any_res) for i in range(depth)])
+                    layer_scale, ct_size, do_propagation, any_res, qk_scale) for i in range(depth)])
         self.downsample = Downsample(dim) if downsample else None
         want_gt = (len(self.blocks) > 0 and not only_local and not conv and
                    (any_res or res[0] // window_size > 1))
@@ -218,8 +219,8 @@ class FasterViT(nn.Module):
         super().__init__()
         if layer_norm_last:
             raise NotImplementedError("layer_norm_last=True is not used by any shipped FasterViT config")
-        if qk_scale is not None or drop_rate or attn_drop_rate:
-            raise NotImplementedError("qk_scale / dropout are unused (0) in every FasterViT config")
+        if drop_rate or attn_drop_rate:
+            raise NotImplementedError("dropout is unused (0) in every FasterViT config")
         hat = [True] * len(depths) if hat is None else list(hat)
         self.any_res = bool(any_res)
         self.resolution = _pair(resolution)
@@ -231,6 +232,8 @@ class FasterViT(nn.Module):
                         resolution=self.resolution if self.any_res else self.resolution[0],
                         hat=hat, do_propagation=bool(do_propagation), any_res=self.any_res,
                         in_chans=in_chans)
+        if qk_scale is not None:
+            self.cfg["qk_scale"] = float(qk_scale)
         # stochastic-depth schedule over all blocks (fv.py:901)
         self.drop_path_rates = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
         self.patch_embed = PatchEmbed(in_chans, in_dim, dim)
@@ -242,7 +245,7 @@ class FasterViT(nn.Module):
                 num_heads=num_heads[i], window_size=window_size[i], ct_size=ct_size, conv=(i < 2),
                 downsample=(i < 3), mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, layer_scale=layer_scale,
                 layer_scale_conv=layer_scale_conv, only_local=not hat[i], do_propagation=do_propagation,
-                any_res=self.any_res))
+                any_res=self.any_res, qk_scale=qk_scale))
         self.norm = nn.BatchNorm2d(self.num_features)
         self.avgpool = nn.AdaptiveAvgPool2d(1)
         self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()

@@ -26,6 +26,10 @@ CASES = {
     "tiny_b": ("faster_vit_4_224", dict(dim=24, in_dim=16, depths=[1, 2, 2, 2], num_heads=[1, 2, 8, 16]), dict(
         dim=24, in_dim=16, depths=[1, 2, 2, 2], num_heads=[1, 2, 8, 16], window_size=[7, 7, 7, 7],
         ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, True, False], do_propagation=True)),
+    # tiny_a with an explicit qk_scale (fv.py:544: scale = qk_scale or head_dim ** -0.5)
+    "tiny_qk": ("faster_vit_0_224", dict(dim=32, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], qk_scale=0.3), dict(
+        dim=32, in_dim=16, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=[7, 7, 7, 7],
+        ct_size=2, mlp_ratio=4, resolution=224, hat=[False, False, True, False], do_propagation=False, qk_scale=0.3)),
     # any-res reduced: non-square carrier grid (sr = [2, 3]) and padding to the window (30x42 -> 30x42,
     # level 3: 15x21 -> 18x24 with window 6)
     "tiny_ar": ("faster_vit_0_any_res", dict(resolution=[240, 336], window_size=[7, 7, 5, 6], ct_size=2, dim=16,

@@ -131,14 +131,14 @@ def pos_embed_1d(sd, prefix, seq_len, dtype):
     return F.linear(h, sd[prefix + ".cpb_mlp.2.weight"])
 
 
-def window_attention(sd, prefix, x, num_heads, resolution, quant):
-    """WindowAttention.forward (fv.py:557-568)."""
+def window_attention(sd, prefix, x, num_heads, resolution, quant, qk_scale=None):
+    """WindowAttention.forward (fv.py:557-568); scale = qk_scale or head_dim ** -0.5 (fv.py:544)."""
     B, N, C = x.shape
     hd = C // num_heads
     qkv = _linear(x, sd[prefix + ".qkv.weight"], sd.get(prefix + ".qkv.bias"), quant)
     qkv = qkv.reshape(B, -1, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
-    attn = (_q(q, quant) @ _q(k, quant).transpose(-2, -1)) * (hd ** -0.5)
+    attn = (_q(q, quant) @ _q(k, quant).transpose(-2, -1)) * (qk_scale or hd ** -0.5)
     attn = attn + attn_bias(sd, prefix + ".pos_emb_funct", resolution, num_heads, N, x.dtype).unsqueeze(0)
     attn = attn.softmax(dim=-1)
     out = (_q(attn, quant) @ _q(v, quant)).transpose(1, 2).reshape(B, -1, C)
@@ -164,7 +164,8 @@ def _dp(t, masks, key):
     return t * m.view(-1, *([1] * (t.dim() - 1)))
 
 
-def hat_block(sd, prefix, x, ct, *, num_heads, ws, sr, ct_size, last, do_propagation, square, quant, masks=None):
+def hat_block(sd, prefix, x, ct, *, num_heads, ws, sr, ct_size, last, do_propagation, square, quant, masks=None,
+              qk_scale=None):
     """HAT.forward (fv.py:662-701; fvar.py:668-707). sr = (sr_h, sr_w). `masks` (optional) holds explicit
     stochastic-depth factors per drop_path call site: prefix + .attn/.mlp (per window), .hat_attn/.hat_mlp
     (per image) — the reference draws them with torch RNG (fv.py:679-680, 690-691)."""
@@ -179,14 +180,14 @@ def hat_block(sd, prefix, x, ct, *, num_heads, ws, sr, ct_size, last, do_propaga
         n_ct = ct.shape[1]
         ct = ct + _dp(_gamma(sd, prefix + ".gamma1") * window_attention(
             sd, prefix + ".hat_attn", _ln(ct, sd, prefix + ".hat_norm1", 1e-5), num_heads,
-            int(n_ct ** 0.5), quant), masks, prefix + ".hat_attn")
+            int(n_ct ** 0.5), quant, qk_scale), masks, prefix + ".hat_attn")
         ct = ct + _dp(_gamma(sd, prefix + ".gamma2") * mlp(
             sd, prefix + ".hat_mlp", _ln(ct, sd, prefix + ".hat_norm2", 1e-5), quant), masks, prefix + ".hat_mlp")
         ct = ct_window(ct, ct_size * sr[0], ct_size * sr[1], ct_size)
         ct = ct.reshape(x.shape[0], -1, N)
         x = torch.cat((ct, x), dim=1)
     x = x + _dp(_gamma(sd, prefix + ".gamma3") * window_attention(
-        sd, prefix + ".attn", _ln(x, sd, prefix + ".norm1", 1e-5), num_heads, ws, quant), masks, prefix + ".attn")
+        sd, prefix + ".attn", _ln(x, sd, prefix + ".norm1", 1e-5), num_heads, ws, quant, qk_scale), masks, prefix + ".attn")
     x = x + _dp(_gamma(sd, prefix + ".gamma4") * mlp(sd, prefix + ".mlp", _ln(x, sd, prefix + ".norm2", 1e-5), quant),
                 masks, prefix + ".mlp")
     if do_sr:
@@ -279,7 +280,8 @@ def forward(sd: dict, cfg: dict, x: torch.Tensor, *, training: bool = False,
                 xw, ct = hat_block(sd, f"{lp}.blocks.{j}", xw, ct, num_heads=heads[i], ws=ws, sr=sr,
                                    ct_size=ct_size, last=(j == depths[i] - 1),
                                    do_propagation=cfg.get("do_propagation", False),
-                                   square=(sr[0] == sr[1]), quant=quant, masks=drop_masks)
+                                   square=(sr[0] == sr[1]), quant=quant, masks=drop_masks,
+                                   qk_scale=cfg.get("qk_scale"))
                 cap(f"{lp}.blocks.{j}", xw)
             x = window_reverse(xw, ws, Hp, Wp, B)
             if Hp != H or Wp != W:

@@ -46,7 +46,7 @@ def summarize(t: torch.Tensor) -> dict:
 
 def batch_for(case: str) -> tuple[int, int]:
     """(eval batch, train batch)"""
-    return {"fv0": (2, 2), "fv4": (1, 2), "ar0": (1, 0), "tiny_a": (2, 3), "tiny_b": (2, 3),
+    return {"fv0": (2, 2), "fv4": (1, 2), "ar0": (1, 0), "tiny_a": (2, 3), "tiny_qk": (2, 3), "tiny_b": (2, 3),
             "tiny_ar": (2, 2), "tiny_ar85": (2, 2), "tiny_ar68": (2, 2), "tiny_ar148": (1, 2), "tiny_21k": (2, 2), "tiny_21k224": (2, 3)}[case]
 
 

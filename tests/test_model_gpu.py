@@ -21,7 +21,7 @@ def _setup(case):
     return g, model.cuda(), x.cuda()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224", "fv0", "fv4", "ar0"])
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_qk", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224", "fv0", "fv4", "ar0"])
 def test_eval_logits_match_reference(case):
     g, model, x = _setup(case)
     with torch.no_grad():
@@ -45,7 +45,7 @@ def _sample(t, n=512):
     return f[::stride].float().cpu()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224", "fv0", "fv4", "ar0"])
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_qk", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224", "fv0", "fv4", "ar0"])
 def test_per_module_activations_match_reference_hooks(case):
     """the reference's per-module outputs (forward hooks on patch_embed, every ConvBlock / HAT block,
     every level, the final BatchNorm; fp64, strided samples in tests/golden) against the same points of the

@@ -36,7 +36,7 @@ def _sample(t, n=512):
     return f[::stride].float()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224", "fv0", "fv4",
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_qk", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224", "fv0", "fv4",
                                   "ar0"])
 def test_oracle_eval_matches_reference_fp64(case):
     g = _load(case)
@@ -59,7 +59,7 @@ def test_oracle_eval_matches_reference_fp64(case):
         assert d < 1e-5, (key, d)
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224"])
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_qk", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k", "tiny_21k224"])
 def test_oracle_train_grads_match_reference(case):
     g = _load(case)
     sd = _state_dict(g, torch.float64)

@@ -37,7 +37,7 @@ def _sample(t, n=512):
     return f[::stride].float().cpu()
 
 
-@pytest.mark.parametrize("case", ["tiny_a", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k224", "tiny_21k", "fv0",
+@pytest.mark.parametrize("case", ["tiny_a", "tiny_qk", "tiny_b", "tiny_ar", "tiny_ar85", "tiny_ar68", "tiny_ar148", "tiny_21k224", "tiny_21k", "fv0",
                                   "fv4"])
 def test_train_step_matches_reference(case):
     g, tr, model, logits, loss = _run(case)
