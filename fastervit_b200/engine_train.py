@@ -371,7 +371,7 @@ class TrainPlan(Plan, ConvPartEmitters, TokenLevelEmitters):
             torch.cuda.synchronize()
             out += [dict(name=op[2], ms=evs[i].elapsed_time(evs[i + 1]), flops=flops.get(i, 0.0),
                          phase="bwd" if ops is self.bwd_ops else "fwd", **self._op_desc(op))
-                    for i, op in enumerate(ops)]
+                    for i, op in enumerate(ops) if op[0] not in ("wait_side", "bucket")]   # (markers launch nothing)
         return out
 
 
