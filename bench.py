@@ -41,13 +41,16 @@ WORKLOADS = {
     # side measurements of the `also_measured` block (not BASELINE configs): small-batch latency of the forward launch
     # graph, and a training step of a 21k fine-tuning model whose 24 x 24 windows (S = 576) take the long-window
     # attention backward (fvit_attn_loop_bwd_long)
+    # the default workload with the entrypoint's own stochastic-depth rate (fv.py:1138: 0.3): per-step mask generation
+    # inside the captured step + the row-scale epilogues, same FLOPs
+    "fv4_train_droppath": ("faster_vit_4_224", {}, 128, (224, 224), "train"),
     "fv0_fwd_b8": ("faster_vit_0_224", {}, 8, (224, 224), "fwd"),
     "fv4_21k_384_train": ("faster_vit_4_21k_384", dict(drop_path_rate=0.0), 32, (384, 384), "train"),
 }
 ORACLE_CASE = {"fv0_fwd": "fv0", "fv4_fwd": "fv4", "ar0_fwd": "ar0", "fv0_train": "fv0", "fv4_train": "fv4"}
 # algorithmic forward GFLOP per image (measured on the reference with FlopCounterMode)
 ALG_GFLOP_FWD = {"fv0_fwd": 6.7237, "fv4_fwd": 85.3574, "ar0_fwd": 73.0828,
-                 "fv0_train": 20.3580, "fv4_train": 258.1946}  # train entries: fwd+bwd
+                 "fv0_train": 20.3580, "fv4_train": 258.1946, "fv4_train_droppath": 258.1946}  # train entries: fwd+bwd
 
 
 # published numbers for the same metric (the reference README's inference-throughput column, hardware
@@ -228,6 +231,8 @@ def quick_measure(workload: str, dev, pk: dict, steps: int = 8, warmup: int = 3)
                     "frac": round(gm_fl / (gm_ms / 1e3) / 1e12 / pk["tensor"], 4)},
            "simt_attention_ms": round(simt, 4),
            "vs_baseline": round(value / PUBLISHED_IMG_S[workload], 3) if workload in PUBLISHED_IMG_S else None}
+    if mode == "train":
+        out["drop_path_rate"] = float(getattr(model, "drop_path_rate", 0.0))
     long_bwd = [r["ms"] for r in prof if r["name"] == "fvit_attn_loop_bwd_long"]
     if long_bwd:
         out["attn_loop_bwd_long"] = {"launches": len(long_bwd), "ms": round(sum(long_bwd), 4)}
@@ -544,7 +549,7 @@ def main() -> None:
         del model, xs
         torch.cuda.empty_cache()
         also = {}
-        for wl in ("fv0_fwd", "fv0_train", "ar0_fwd", "fv4_fwd", "fv0_fwd_b8", "fv4_21k_384_train"):
+        for wl in ("fv0_fwd", "fv0_train", "ar0_fwd", "fv4_fwd", "fv4_train_droppath", "fv0_fwd_b8", "fv4_21k_384_train"):
             try:
                 also[wl] = quick_measure(wl, dev, pk)
             except Exception as exc:  # a side measurement must not take the headline line down
